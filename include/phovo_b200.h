@@ -175,6 +175,12 @@ int phovo_set_stream(phovo_ctx* ctx, void* cuda_stream);
 /* 0: plain stream launches with host-side convergence polling; 1 (default): whole Optimize as one
  * CUDA graph with a conditional WHILE node per level (no host sync inside) */
 int phovo_set_use_graph(phovo_ctx* ctx, int enable);
+/* 1 if the last phovo_optimize ran as the CUDA graph (0: plain launches; see phovo_graph_error) */
+int phovo_last_optimize_used_graph(const phovo_ctx* ctx);
+const char* phovo_graph_error(const phovo_ctx* ctx);
+/* build every pyramid level, not only those with max_num_iterations > 0 (the reference builds all,
+ * AN:474-490, but never reads the others); needed only to inspect them with phovo_get_level_image */
+int phovo_set_build_all_levels(phovo_ctx* ctx, int enable);
 
 /* ---- batch of independent pairs (extension; BASELINE config "4096 pairs, sharded by pair") ---- */
 /* All pairs share rows/cols/intrinsics/config.  Inputs are strided arrays of `num_pairs` frames:
@@ -205,9 +211,14 @@ int phovo_synchronize(phovo_ctx* ctx);
 int phovo_shard_configure(phovo_ctx* ctx, int rank, int world);
 /* device pointer to the 32-double reduction buffer: [0..20] H, [21..26] g, [27] cost, [28] count */
 int phovo_shard_buffer(phovo_ctx* ctx, double** dev_ptr);
+/* host-mediated exchange (tests, gloo): copy the buffer out / in through the host (synchronous) */
+int phovo_shard_read_buffer(phovo_ctx* ctx, double out[32]);
+int phovo_shard_write_buffer(phovo_ctx* ctx, const double in[32]);
+int phovo_shard_begin(phovo_ctx* ctx);                           /* uploads the initial state */
 int phovo_shard_begin_level(phovo_ctx* ctx, int level);          /* resets the iteration counter */
 int phovo_shard_partial(phovo_ctx* ctx);                         /* K3a + K3b + local reduce -> buffer */
 int phovo_shard_step(phovo_ctx* ctx, int* done);                 /* solve + update + termination test */
+int phovo_shard_finish(phovo_ctx* ctx);                          /* read back state + stats */
 
 #ifdef __cplusplus
 }

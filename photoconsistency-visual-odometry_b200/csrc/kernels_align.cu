@@ -1,0 +1,318 @@
+// kernels_align.cu -- the per-level alignment iteration of the general path.
+//
+//   K3a  k_winner        : warp every source pixel, winner[target] = max(source index)
+//                          == the reference's raster-order last-writer-wins residual scatter
+//                          (CPhotoconsistencyOdometryAnalytic.h:358; Ceres.h:261)
+//   K3b  k_normal_eq     : ONE fused pass per pixel: warp + residual (gathered through the winner
+//                          map) + 1x6 Jacobian + 21 J^T J + 6 J^T r products, warp-shuffle then
+//                          block reduction into per-block partials (no floating-point atomics)
+//                          (AN:271-366 + the Eigen products of AN:538-539)
+//   K4   k_reduce_solve  : fixed-order sum of the partials, 6x6 solve, state update, termination
+//                          test, stats log, CUDA-graph WHILE condition (AN:538-549, 376-392)
+//
+// All kernels early-exit when pose->done is set, so an iteration enqueued after convergence is a
+// no-op; the integer atomicMax of K3a is order-independent, hence run-to-run reproducible.
+#include "phovo_device.cuh"
+#include "phovo_kernels.h"
+
+namespace phovo {
+namespace {
+
+constexpr int kBlock = 128;
+
+__global__ void k_fill_i32(int* p, int v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void k_set_state(PoseDev* pose, const double* state_dev, int log_capacity, double s0, double s1, double s2, double s3, double s4, double s5) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[6] = {s0, s1, s2, s3, s4, s5};
+  if (state_dev) for (int k = 0; k < 6; ++k) s[k] = state_dev[k];
+  Pose P;
+  pose_from_state(s, P);
+  for (int k = 0; k < 6; ++k) pose->state[k] = s[k];
+  pose_store(P, pose);
+  pose->iteration = 0;
+  pose->done = 0;
+  pose->log_count = 0;
+  pose->log_capacity = log_capacity;
+  for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) pose->iters_per_level[l] = 0;
+}
+
+__global__ void k_begin_level(PoseDev* pose, int max_iters) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  pose->iteration = 0;
+  pose->done = max_iters > 0 ? 0 : 1;
+}
+
+// K3a.  4 B read (D0) + one 4 B atomicMax per valid pixel.
+template <bool CERES>
+__global__ void __launch_bounds__(kBlock) k_winner(LevelParams L, LevelPtrs P, const PoseDev* __restrict__ pose) {
+  if (pose->done) return;
+  Pose T;
+  pose_load(pose, T);
+  const int n = L.rows * L.cols;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const double d = (double)__ldg(P.D0 + i);
+    const int r = i / L.cols, c = i - r * L.cols;
+    Warped w;
+    if (warp_pixel<CERES>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
+  }
+}
+
+__device__ __forceinline__ void linear_init_axis(double x, int size, int& x1, int& x2, double& dx) {
+  // third_party/sample.h:36-50
+  const int ix = (int)x;
+  if (ix < 0) { x1 = 0; x2 = 0; dx = 1.0; }
+  else if (ix > size - 2) { x1 = size - 1; x2 = size - 1; dx = 1.0; }
+  else { x1 = ix; x2 = ix + 1; dx = (double)x2 - x; }
+}
+
+__device__ __forceinline__ double bilinear(const float* __restrict__ img, int cols, int y1, int y2, int x1, int x2, double dy, double dx) {
+  // third_party/sample.h:76-82
+  const double a = (double)__ldg(img + (size_t)y1 * cols + x1), b = (double)__ldg(img + (size_t)y1 * cols + x2);
+  const double c = (double)__ldg(img + (size_t)y2 * cols + x1), d = (double)__ldg(img + (size_t)y2 * cols + x2);
+  return dy * (dx * a + (1.0 - dx) * b) + (1. - dy) * (dx * c + (1.0 - dx) * d);
+}
+
+// K3b.  MODE: 0 analytic bug-compatible, 1 analytic Maxima-exact, 2 Ceres residual.
+// DUMP: additionally write the dense residual vector / Jacobian (parity hook, never on the hot path).
+//
+// Analytic (gather form of AN:271-366): thread i owns source pixel i AND residual slot i:
+//   res[i] = winner[i] >= 0 ? I1[i] - I0[winner[i]] : 0 ; J_i from D0[i], Gx1[i], Gy1[i]
+//   (gradients at the SOURCE index, AN:346-347) ; H += J_i^T J_i ; g += J_i^T res[i].
+//   Reads per pixel: D0, winner, I1, I0[winner] (local gather), Gx, Gy -- each array streamed once.
+// Ceres (CE:156-269): a source pixel's row survives iff it is the winner of its (truncated) target
+//   slot; its residual/Jacobian use bilinear samples of I1/Gx/Gy at the real-valued warp.
+// The winner slot is reset to -1 by the thread that consumed it, so the map is clean for the next
+// iteration without a separate clear pass.
+template <int MODE, bool DUMP>
+__global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P, const PoseDev* __restrict__ pose,
+                                                      double* __restrict__ partials,
+                                                      double* __restrict__ dump_res, double* __restrict__ dump_jac) {
+  __shared__ double smem[(kBlock / 32) * PHOVO_ACC_STRIDE];
+  if (pose->done) return;
+  Pose T;
+  pose_load(pose, T);
+  double acc[PHOVO_NACC];
+#pragma unroll
+  for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+  const int n = L.rows * L.cols;
+  const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const int r = i / L.cols, c = i - r * L.cols;
+    const double d = (double)__ldg(P.D0 + i);
+    Warped w;
+    if (MODE == 2) {
+      const bool ok = warp_pixel<true>(L, T, r, c, d, w);
+      if (!ok) continue;
+      if (P.winner[w.t] != i) continue;   // overwritten by a later source pixel (CE:261)
+      P.winner[w.t] = -1;
+      if (i < i_begin || i >= i_end) continue;
+      int x1, x2, y1, y2; double dx, dy;
+      linear_init_axis(w.tr - 0.5, L.rows, y1, y2, dy);   // sample.h:67-71
+      linear_init_axis(w.tc - 0.5, L.cols, x1, x2, dx);
+      const double s0 = bilinear(P.I1, L.cols, y1, y2, x1, x2, dy, dx);
+      const double s1 = bilinear(P.Gx, L.cols, y1, y2, x1, x2, dy, dx);
+      const double s2 = bilinear(P.Gy, L.cols, y1, y2, x1, x2, dy, dx);
+      const double res = s0 - (double)__ldg(P.I0 + i);
+      double Ju[6], Jv[6], J[6];
+      projection_jacobian<false>(L, T, w, d, Ju, Jv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J[k] = s1 * Ju[k] + s2 * Jv[k];   // jet_extras.h:87-109
+      accumulate_row(acc, J, res);
+      acc[27] = fma(res, res, acc[27]);
+      acc[28] += 1.;
+      if (DUMP) {
+        if (dump_res) dump_res[w.t] = res;
+        if (dump_jac) for (int k = 0; k < 6; ++k) dump_jac[(size_t)w.t * 6 + k] = J[k];
+      }
+    } else {
+      const int win = P.winner[i];
+      P.winner[i] = -1;
+      if (i < i_begin || i >= i_end) continue;
+      double res = 0.;
+      if (win >= 0) {
+        res = (double)__ldg(P.I1 + i) - (double)__ldg(P.I0 + win);
+        acc[27] = fma(res, res, acc[27]);
+      }
+      if (DUMP && dump_res) dump_res[i] = res;
+      const bool ok = warp_pixel<false>(L, T, r, c, d, w);
+      if (!ok) continue;
+      double Ju[6], Jv[6], J[6];
+      projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
+      const double gx = (double)__ldg(P.Gx + i), gy = (double)__ldg(P.Gy + i);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];   // AN:345-348
+      accumulate_row(acc, J, res);
+      acc[28] += 1.;
+      if (DUMP && dump_jac) for (int k = 0; k < 6; ++k) dump_jac[(size_t)i * 6 + k] = J[k];
+    }
+  }
+  const double total = block_reduce<kBlock>(acc, smem);
+  if (threadIdx.x < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + threadIdx.x] = total;
+}
+
+// Sum partials[0..grid) for each of the PHOVO_NACC values in a fixed order: warp v owns value v,
+// lane l adds blocks l, l+32, ... in order, then a fixed butterfly over lanes.  Needs 32 warps.
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int grid, double* totals /* smem[32] */) {
+  const int v = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (v < PHOVO_NACC) {
+    double s = 0.;
+    for (int b = lane; b < grid; b += 32) s += partials[(size_t)b * PHOVO_ACC_STRIDE + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) totals[v] = s;
+  }
+  __syncthreads();
+}
+
+// The Gauss-Newton step and termination test of AN:538-549 / AN:376-392, single thread.
+__device__ void gn_step(const LevelParams& L, PoseDev* pose, const double* totals, phovo_iter_stats* log,
+                        unsigned long long cond_handle) {
+  double g[6], step[6], s_in[6], n2 = 0.;
+  for (int k = 0; k < 6; ++k) { g[k] = totals[21 + k]; n2 = fma(g[k], g[k], n2); s_in[k] = pose->state[k]; }
+  solve6_lu(totals, g, step);
+  double s_out[6];
+  for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];   // AN:539-540
+  const double gnorm = sqrt(n2);
+  const int it = pose->iteration + 1;                                     // AN:547
+  const int done = (it >= L.max_iters) || (gnorm < L.min_grad_norm);      // AN:383-392
+  if (log && pose->log_count < pose->log_capacity) {
+    phovo_iter_stats* e = log + pose->log_count;
+    e->level = L.level; e->iteration = it - 1; e->num_valid = (int)totals[28]; e->accepted = 1;
+    for (int k = 0; k < 21; ++k) e->H[k] = totals[k];
+    for (int k = 0; k < 6; ++k) { e->g[k] = g[k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
+    e->grad_norm = gnorm; e->cost = 0.5 * totals[27]; e->radius = 0.;
+  }
+  pose->log_count += 1;
+  Pose P;
+  pose_from_state(s_out, P);
+  for (int k = 0; k < 6; ++k) pose->state[k] = s_out[k];
+  pose_store(P, pose);
+  pose->iteration = it;
+  pose->iters_per_level[L.level] = it;
+  pose->done = done;
+  if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, done ? 0u : 1u);
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_solve(LevelParams L, PoseDev* pose, const double* __restrict__ partials, int grid,
+                                                       phovo_iter_stats* log, unsigned long long cond_handle) {
+  __shared__ double totals[32];
+  if (pose->done) {
+    if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
+    return;
+  }
+  reduce_partials(partials, grid, totals);
+  if (threadIdx.x == 0) gn_step(L, pose, totals, log, cond_handle);
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_only(LevelParams L, const PoseDev* pose, const double* __restrict__ partials, int grid,
+                                                      phovo_iter_stats* out) {
+  __shared__ double totals[32];
+  reduce_partials(partials, grid, totals);
+  if (threadIdx.x == 0) {
+    out->level = L.level; out->iteration = 0; out->num_valid = (int)totals[28]; out->accepted = 0;
+    double n2 = 0.;
+    for (int k = 0; k < 21; ++k) out->H[k] = totals[k];
+    for (int k = 0; k < 6; ++k) { out->g[k] = totals[21 + k]; n2 += totals[21 + k] * totals[21 + k]; out->state_in[k] = pose->state[k]; out->state_out[k] = pose->state[k]; }
+    out->grad_norm = sqrt(n2); out->cost = 0.5 * totals[27]; out->radius = 0.;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_to_buffer(const PoseDev* pose, const double* __restrict__ partials, int grid, double* buffer) {
+  __shared__ double totals[32];
+  reduce_partials(partials, grid, totals);
+  if (threadIdx.x < 32) buffer[threadIdx.x] = threadIdx.x < PHOVO_NACC ? totals[threadIdx.x] : 0.;
+}
+
+__global__ void k_solve_from_buffer(LevelParams L, PoseDev* pose, const double* buffer, phovo_iter_stats* log) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (pose->done) return;
+  double totals[32];
+  for (int k = 0; k < 32; ++k) totals[k] = buffer[k];
+  gn_step(L, pose, totals, log, 0ull);
+}
+
+inline int grid_for(int n) {
+  // one pixel per thread up to 8 CTAs per SM, then a fixed persistent grid (grid-stride loop);
+  // the grid is a pure function of the level size, so the partial-sum order is reproducible.
+  const int want = (n + kBlock - 1) / kBlock;
+  const int cap = 148 * 8;
+  return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+}  // namespace
+
+int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n) {
+  const size_t want = (n + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  k_fill_i32<<<blocks, 256, 0, stream>>>(p, value, n);
+  return 1;
+}
+
+int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev, const double s[6], int log_capacity) {
+  if (state_dev) k_set_state<<<1, 32, 0, stream>>>(pose, state_dev, log_capacity, 0, 0, 0, 0, 0, 0);
+  else k_set_state<<<1, 32, 0, stream>>>(pose, nullptr, log_capacity, s[0], s[1], s[2], s[3], s[4], s[5]);
+  return 1;
+}
+
+int launch_begin_level(cudaStream_t stream, PoseDev* pose, int max_iters) {
+  k_begin_level<<<1, 32, 0, stream>>>(pose, max_iters);
+  return 1;
+}
+
+int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, const PoseDev* pose,
+                             double* partials, int* grid_out, double* dump_res, double* dump_jac,
+                             bool clear_winner_first) {
+  const int n = L.rows * L.cols;
+  const int grid = grid_for(n);
+  int launches = 0;
+  if (clear_winner_first) launches += launch_fill_i32(stream, P.winner, -1, (size_t)n);
+  if (L.mode == PHOVO_MODE_CERES) k_winner<true><<<grid, kBlock, 0, stream>>>(L, P, pose);
+  else k_winner<false><<<grid, kBlock, 0, stream>>>(L, P, pose);
+  const bool dump = dump_res || dump_jac;
+  switch (L.mode) {
+    case PHOVO_MODE_ANALYTIC_REF:
+      if (dump) k_normal_eq<0, true><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, dump_res, dump_jac);
+      else k_normal_eq<0, false><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, nullptr, nullptr);
+      break;
+    case PHOVO_MODE_ANALYTIC_FIXED:
+      if (dump) k_normal_eq<1, true><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, dump_res, dump_jac);
+      else k_normal_eq<1, false><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, nullptr, nullptr);
+      break;
+    default:
+      if (dump) k_normal_eq<2, true><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, dump_res, dump_jac);
+      else k_normal_eq<2, false><<<grid, kBlock, 0, stream>>>(L, P, pose, partials, nullptr, nullptr);
+      break;
+  }
+  *grid_out = grid;
+  return launches + 2;
+}
+
+int launch_reduce_solve(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* partials, int grid,
+                        phovo_iter_stats* log, unsigned long long cond_handle) {
+  k_reduce_solve<<<1, 1024, 0, stream>>>(L, pose, partials, grid, log, cond_handle);
+  return 1;
+}
+
+int launch_reduce_only(cudaStream_t stream, const LevelParams& L, const PoseDev* pose, const double* partials, int grid,
+                       phovo_iter_stats* out) {
+  k_reduce_only<<<1, 1024, 0, stream>>>(L, pose, partials, grid, out);
+  return 1;
+}
+
+int launch_reduce_to_buffer(cudaStream_t stream, const double* partials, int grid, double* buffer) {
+  k_reduce_to_buffer<<<1, 1024, 0, stream>>>(nullptr, partials, grid, buffer);
+  return 1;
+}
+
+int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* buffer,
+                             phovo_iter_stats* log) {
+  k_solve_from_buffer<<<1, 32, 0, stream>>>(L, pose, buffer, log);
+  return 1;
+}
+
+}  // namespace phovo

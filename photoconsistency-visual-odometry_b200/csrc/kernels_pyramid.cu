@@ -1,0 +1,191 @@
+// kernels_pyramid.cu -- frame setup for the general (any resolution, any config) path:
+// K1 pyramid level from the full-resolution source, K2b Gaussian blur, K2 Scharr + fp32 store.
+// Replaces CPhotoconsistencyOdometryAnalytic.h:115-189 (BuildPyramid / BuildDerivativesPyramids).
+// The batched path has its own fused, shared-memory version (kernels_batch.cu).
+#include <math.h>
+
+#include "phovo_kernels.h"
+
+namespace phovo {
+namespace {
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ double load_src(const void* base, size_t step_bytes, int r, int c, double scale);
+template <>
+__device__ __forceinline__ double load_src<uint8_t>(const void* base, size_t step, int r, int c, double scale) {
+  return __dmul_rn((double)__ldg((const uint8_t*)base + (size_t)r * step + c), scale);
+}
+template <>
+__device__ __forceinline__ double load_src<uint16_t>(const void* base, size_t step, int r, int c, double scale) {
+  return __dmul_rn((double)__ldg((const uint16_t*)((const char*)base + (size_t)r * step) + c), scale);
+}
+template <>
+__device__ __forceinline__ double load_src<float>(const void* base, size_t step, int r, int c, double) {
+  return (double)__ldg((const float*)((const char*)base + (size_t)r * step) + c);
+}
+template <>
+__device__ __forceinline__ double load_src<double>(const void* base, size_t step, int r, int c, double) {
+  return __ldg((const double*)((const char*)base + (size_t)r * step) + c);
+}
+
+// One axis of OpenCV's INTER_LINEAR table: f = (float)((d+0.5)*scale - 0.5); s = floor(f); f -= s.
+__device__ __forceinline__ void linear_axis(int d, double scale, int ssize, bool is_x, int& s0, float& w1) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (is_x && s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  s0 = s; w1 = f;
+}
+
+// K1.  One thread per output pixel.  For the exact factor 2^-level the four taps are the central
+// 2x2 of the pixel's 2^level cell with weights 1/2 (horizontal pair first, then vertical) --
+// cv::resize INTER_LINEAR from the ORIGINAL image, AN:132.  A warp reads one contiguous span of
+// each of two source rows, so every 32-byte sector fetched is used by the warp.
+template <typename T>
+__global__ void __launch_bounds__(256) k_build_level(const void* __restrict__ src, size_t step, double src_scale,
+                                                     int rows, int cols, int level, double scale,
+                                                     double* __restrict__ dst, int orows, int ocols) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ocols || y >= orows) return;
+  if (level == 0) {
+    dst[(size_t)y * ocols + x] = load_src<T>(src, step, y, x, src_scale);
+    return;
+  }
+  int sx, sy; float fx, fy;
+  linear_axis(x, scale, cols, true, sx, fx);
+  linear_axis(y, scale, rows, false, sy, fy);
+  const int y0 = min(max(sy, 0), rows - 1), y1 = min(max(sy + 1, 0), rows - 1);
+  double r0, r1;
+  if (sx + 1 < cols) {
+    const double a0 = (double)(1.f - fx), a1 = (double)fx;
+    r0 = __dadd_rn(__dmul_rn(load_src<T>(src, step, y0, sx, src_scale), a0), __dmul_rn(load_src<T>(src, step, y0, sx + 1, src_scale), a1));
+    r1 = __dadd_rn(__dmul_rn(load_src<T>(src, step, y1, sx, src_scale), a0), __dmul_rn(load_src<T>(src, step, y1, sx + 1, src_scale), a1));
+  } else {
+    r0 = load_src<T>(src, step, y0, sx, src_scale);
+    r1 = load_src<T>(src, step, y1, sx, src_scale);
+  }
+  const double b0 = (double)(1.f - fy), b1 = (double)fy;
+  dst[(size_t)y * ocols + x] = __dadd_rn(__dmul_rn(r0, b0), __dmul_rn(r1, b1));
+}
+
+struct GaussTaps { double k[32]; int n; };
+
+// K2b row pass: generic cv RowFilter order (taps accumulated left to right).
+__global__ void __launch_bounds__(256) k_gauss_rows(const double* __restrict__ src, double* __restrict__ dst, int rows, int cols, GaussTaps t) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= cols) return;
+  const double* S = src + (size_t)r * cols;
+  const int a = t.n / 2;
+  double s = __dmul_rn(t.k[0], S[reflect101(c - a, cols)]);
+  for (int k = 1; k < t.n; ++k) s = __dadd_rn(s, __dmul_rn(t.k[k], S[reflect101(c - a + k, cols)]));
+  dst[(size_t)r * cols + c] = s;
+}
+// K2b column pass: cv SymmColumnFilter order (centre tap, then symmetric pairs).
+__global__ void __launch_bounds__(256) k_gauss_cols(const double* __restrict__ src, double* __restrict__ dst, int rows, int cols, GaussTaps t) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= cols) return;
+  const int a = t.n / 2;
+  double s = __dmul_rn(t.k[a], src[(size_t)r * cols + c]);
+  for (int k = 1; k <= a; ++k) {
+    const double p = src[(size_t)reflect101(r + k, rows) * cols + c], q = src[(size_t)reflect101(r - k, rows) * cols + c];
+    s = __dadd_rn(s, __dmul_rn(t.k[a + k], __dadd_rn(p, q)));
+  }
+  dst[(size_t)r * cols + c] = s;
+}
+
+__global__ void __launch_bounds__(256) k_store_f32(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (float)src[i];
+}
+
+// K2: Scharr in x and y with cv::Scharr's separable evaluation order (derivative kernel [-1 0 1],
+// smoothing kernel [3 10 3]*scale) + the fp32 store of the image itself.  32x8 tiles with a
+// 1-pixel halo staged in shared memory so every level pixel is read from global memory once
+// (plus halo), then 18 shared-memory reads per pixel.
+#define SCH_TW 32
+#define SCH_TH 8
+__global__ void __launch_bounds__(SCH_TW * SCH_TH) k_scharr_store(const double* __restrict__ img, int rows, int cols,
+                                                                   double ks0, double ks1,
+                                                                   float* __restrict__ I, float* __restrict__ Gx, float* __restrict__ Gy) {
+  __shared__ double tile[SCH_TH + 2][SCH_TW + 2];
+  const int x0 = blockIdx.x * SCH_TW, y0 = blockIdx.y * SCH_TH;
+  for (int i = threadIdx.y * SCH_TW + threadIdx.x; i < (SCH_TH + 2) * (SCH_TW + 2); i += SCH_TW * SCH_TH) {
+    const int ty = i / (SCH_TW + 2), tx = i % (SCH_TW + 2);
+    const int gy = reflect101(min(y0 + ty - 1, rows), rows), gx = reflect101(min(x0 + tx - 1, cols), cols);
+    tile[ty][tx] = img[(size_t)gy * cols + gx];
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  const int tx = threadIdx.x + 1, ty = threadIdx.y + 1;
+  // dx: row filter [-1 0 1] on three rows, then column filter centre-first
+  const double dm = __dsub_rn(tile[ty - 1][tx + 1], tile[ty - 1][tx - 1]);
+  const double d0 = __dsub_rn(tile[ty][tx + 1], tile[ty][tx - 1]);
+  const double dp = __dsub_rn(tile[ty + 1][tx + 1], tile[ty + 1][tx - 1]);
+  const double gx = __dadd_rn(__dmul_rn(ks1, d0), __dmul_rn(ks0, __dadd_rn(dp, dm)));
+  // dy: row filter [3 10 3]*scale left-to-right on rows y-1 and y+1, then column [-1 0 1]
+  const double sm = __dadd_rn(__dadd_rn(__dmul_rn(ks0, tile[ty - 1][tx - 1]), __dmul_rn(ks1, tile[ty - 1][tx])), __dmul_rn(ks0, tile[ty - 1][tx + 1]));
+  const double sp = __dadd_rn(__dadd_rn(__dmul_rn(ks0, tile[ty + 1][tx - 1]), __dmul_rn(ks1, tile[ty + 1][tx])), __dmul_rn(ks0, tile[ty + 1][tx + 1]));
+  const double gy = __dsub_rn(sp, sm);
+  const size_t o = (size_t)y * cols + x;
+  I[o] = (float)tile[ty][tx];
+  Gx[o] = (float)gx;
+  Gy[o] = (float)gy;
+}
+
+}  // namespace
+
+int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_t step, double src_scale,
+                       int rows, int cols, int level, double* dst, int orows, int ocols) {
+  dim3 block(64, 4), grid((ocols + 63) / 64, (orows + 3) / 4);
+  const double scale = ldexp(1.0, level);
+  switch (src_type) {
+    case SRC_U8:  k_build_level<uint8_t><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
+    case SRC_U16: k_build_level<uint16_t><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
+    case SRC_F32: k_build_level<float><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
+    default:      k_build_level<double><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
+  }
+  return 1;
+}
+
+int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows, int cols, int ksize, double sigma) {
+  if (ksize <= 1) return 0;
+  GaussTaps t; t.n = ksize;
+  // cv::getGaussianKernel(ksize, sigma, CV_64F)
+  const double sigmaX = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+  const double scale2X = -0.5 / (sigmaX * sigmaX);
+  double sum = 0;
+  for (int i = 0; i < ksize; ++i) { const double x = i - (ksize - 1) * 0.5; t.k[i] = exp(scale2X * x * x); sum += t.k[i]; }
+  sum = 1. / sum;
+  for (int i = 0; i < ksize; ++i) t.k[i] *= sum;
+  dim3 block(256), grid((cols + 255) / 256, rows);
+  k_gauss_rows<<<grid, block, 0, stream>>>(img, tmp, rows, cols, t);
+  k_gauss_cols<<<grid, block, 0, stream>>>(tmp, img, rows, cols, t);
+  return 2;
+}
+
+int launch_store_f32(cudaStream_t stream, const double* src, float* dst, size_t n) {
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  k_store_f32<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(src, dst, n);
+  return 1;
+}
+
+int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
+                        float* I, float* Gx, float* Gy) {
+  double ks0 = 3., ks1 = 10.;
+  if (scale != 1.) { ks0 *= scale; ks1 *= scale; }
+  dim3 block(SCH_TW, SCH_TH), grid((cols + SCH_TW - 1) / SCH_TW, (rows + SCH_TH - 1) / SCH_TH);
+  k_scharr_store<<<grid, block, 0, stream>>>(img, rows, cols, ks0, ks1, I, Gx, Gy);
+  return 1;
+}
+
+}  // namespace phovo

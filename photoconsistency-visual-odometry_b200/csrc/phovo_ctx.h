@@ -1,0 +1,81 @@
+// phovo_ctx.h -- the context object behind the C ABI (one CUDA device + one stream).
+#ifndef PHOVO_CTX_H_
+#define PHOVO_CTX_H_
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "phovo_internal.h"
+#include "phovo_kernels.h"
+
+struct phovo_batch_state;  // phovo_batch.cu
+
+struct phovo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err, graph_error;
+
+  phovo_config cfg;
+  double K[9] = {0};
+  bool have_K = false;
+  bool build_all_levels = false;
+  bool have_src = false, have_tgt = false;
+
+  // geometry of the current frames
+  int rows = 0, cols = 0;
+  int lrows[PHOVO_MAX_LEVELS] = {0}, lcols[PHOVO_MAX_LEVELS] = {0};
+
+  // HBM layout (general path): per active level five dense row-major fp32 images
+  float* I0[PHOVO_MAX_LEVELS] = {nullptr};
+  float* D0[PHOVO_MAX_LEVELS] = {nullptr};
+  float* I1[PHOVO_MAX_LEVELS] = {nullptr};
+  float* Gx[PHOVO_MAX_LEVELS] = {nullptr};
+  float* Gy[PHOVO_MAX_LEVELS] = {nullptr};
+  size_t lcap[PHOVO_MAX_LEVELS][5] = {{0}};
+  int* winner = nullptr; size_t winner_cap = 0;           // one int per pixel of the largest active level
+  double* scratch64[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};
+  double* partials = nullptr; size_t partials_cap = 0;    // [grid][32] per-block normal-equation partials
+  char* stage_gray[2] = {nullptr, nullptr}; size_t stage_gray_cap[2] = {0, 0};
+  char* stage_depth = nullptr; size_t stage_depth_cap = 0;
+  double* dump_res = nullptr; size_t dump_res_cap = 0;
+  double* dump_jac = nullptr; size_t dump_jac_cap = 0;
+
+  // solver state
+  double state[6] = {0};
+  PoseDev* d_pose = nullptr; PoseDev* h_pose = nullptr;
+  phovo_iter_stats* d_log = nullptr; phovo_iter_stats* h_log = nullptr; int log_cap = 0;
+  phovo_iter_stats* d_eval = nullptr; phovo_iter_stats* h_eval = nullptr;
+  double* d_state_in = nullptr; double* h_state_in = nullptr;
+  std::vector<phovo_iter_stats> log;
+
+  // CUDA graph of the whole Optimize()
+  bool use_graph = true, graph_broken = false;
+  cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+  int graph_launches_fixed = 0, graph_launches_per_iter = 0;
+  int last_used_graph = 0;
+
+  // row sharding
+  int shard_rank = 0, shard_world = 1, shard_level = -1;
+  double* d_shard = nullptr;
+
+  // bookkeeping
+  cudaEvent_t ev_copy = nullptr; cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool h2d_pending = false, copy_event_armed = false, setup_timed = false;
+  int64_t launches = 0;
+
+  phovo_batch_state* batch = nullptr;
+
+  int fail(int code, const std::string& what);
+  int cuda_fail(const char* what, cudaError_t e);
+  bool level_active(int l) const;
+  LevelParams level_params(int level) const;
+  phovo::LevelPtrs level_ptrs(int level) const;
+  void invalidate_graph();
+};
+
+void phovo_batch_release(phovo_ctx* ctx);
+
+#endif

@@ -1,0 +1,57 @@
+// phovo_kernels.h -- host-callable launchers of the CUDA kernels (one per kernel family).
+// Every launcher enqueues on `stream`, returns the number of kernels it launched and never
+// synchronises.  Error checking is done by the caller with cudaGetLastError().
+#ifndef PHOVO_KERNELS_H_
+#define PHOVO_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phovo_internal.h"
+
+namespace phovo {
+
+// ---- frame setup (kernels_pyramid.cu) --------------------------------------------------------
+enum SrcType { SRC_U8 = 0, SRC_F64 = 1, SRC_F32 = 2, SRC_U16 = 3 };
+
+// K1: one pyramid level straight from the full-resolution source image (cv::resize INTER_LINEAR
+// by 2^-level from the ORIGINAL, AN:132) with the element conversion fused in
+// (u8 * 1/255, AN:471; u16 * depth_scale).  Output fp64 scratch (orows x ocols, dense).
+int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_t src_step_bytes,
+                       double src_scale, int rows, int cols, int level, double* dst, int orows, int ocols);
+// K2b: cv::GaussianBlur(k x k, sigma) applied once, BORDER_REFLECT_101, fp64 in place via `tmp`.
+int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows, int cols, int ksize, double sigma);
+// fp64 scratch -> fp32 level storage
+int launch_store_f32(cudaStream_t stream, const double* src, float* dst, size_t n);
+// K2: Scharr x/y (AN:181-187) from the fp64 level image + fp32 store of I1, Gx, Gy in one pass.
+int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
+                        float* I, float* Gx, float* Gy);
+
+// ---- alignment (kernels_align.cu) ------------------------------------------------------------
+struct LevelPtrs {
+  const float* I0; const float* D0; const float* I1; const float* Gx; const float* Gy;
+  int* winner;        // rows*cols ints, all -1 between iterations
+};
+
+int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);
+int launch_begin_level(cudaStream_t stream, PoseDev* pose, int max_iters);
+// K3a + K3b (+ optional dense residual / Jacobian dump) for one iteration; respects pose->done.
+// partials: [grid][PHOVO_ACC_STRIDE] doubles.  Returns kernels launched; *grid_out = blocks of K3b.
+int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, const PoseDev* pose,
+                             double* partials, int* grid_out, double* dump_res, double* dump_jac,
+                             bool clear_winner_first);
+// K4: fixed-order sum of the partials, 6x6 solve, state update, termination test, stats log.
+// cond_handle != 0: also drives the CUDA-graph WHILE node (cudaGraphSetConditional).
+int launch_reduce_solve(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* partials, int grid,
+                        phovo_iter_stats* log, unsigned long long cond_handle);
+// evaluation only: totals -> stats entry `out` (device), no step
+int launch_reduce_only(cudaStream_t stream, const LevelParams& L, const PoseDev* pose, const double* partials, int grid,
+                       phovo_iter_stats* out);
+// row-sharded variant: totals -> 32-double buffer, then solve from the (all-reduced) buffer
+int launch_reduce_to_buffer(cudaStream_t stream, const double* partials, int grid, double* buffer);
+int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* buffer,
+                             phovo_iter_stats* log);
+int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
+
+}  // namespace phovo
+#endif

@@ -1,0 +1,264 @@
+"""Python mirror of the reference's solver interface over the C ABI.
+
+`CPhotoconsistencyOdometryCuda` has the same methods, argument meaning and call order as
+`phovo::CPhotoconsistencyOdometry<TPixel,TCoordinate>` (CPhotoconsistencyOdometry.h:137-179) and
+its analytic implementation (CPhotoconsistencyOdometryAnalytic.h:448-607), so tests read like
+the reference apps (PhotoconsistencyFrameAlignment.cpp:90-105).  The C++ adapter with the
+identical surface is include/CPhotoconsistencyOdometryCuda.h.  All compute happens in
+libphovo_b200.so on the GPU; nothing here has a CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import PhovoError
+
+
+class CPhotoconsistencyOdometryCuda:
+    def __init__(self, device=0, mode=capi.MODE_ANALYTIC_REF):
+        self._L = capi.lib()
+        h = C.c_void_p()
+        rc = self._L.phovo_create(device, C.byref(h))
+        if rc != capi.OK:
+            raise PhovoError(rc, (self._L.phovo_last_error(None) or b"").decode())
+        self._h = h
+        self._check(self._L.phovo_set_mode(self._h, mode))
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != capi.OK:
+            raise PhovoError(rc, (self._L.phovo_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.phovo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference interface --------------------------------------------------------------
+    def ReadConfigurationFile(self, fileName):                      # AN:581-607 / CE:526-576
+        self._check(self._L.phovo_load_config_yaml(self._h, os.fsencode(fileName)))
+
+    def SetMinDepth(self, minD):                                    # AN:448-451
+        cfg = self.GetConfig()
+        self._check(self._L.phovo_set_depth_range(self._h, float(minD), cfg.max_depth))
+
+    def SetMaxDepth(self, maxD):                                    # AN:454-457
+        cfg = self.GetConfig()
+        self._check(self._L.phovo_set_depth_range(self._h, cfg.min_depth, float(maxD)))
+
+    def SetIntrinsicMatrix(self, intrinsicMatrix):                  # AN:460-463
+        K = np.ascontiguousarray(intrinsicMatrix, dtype=np.float64).reshape(9)
+        self._check(self._L.phovo_set_intrinsics(self._h, K.ctypes.data_as(capi._dp)))
+
+    @staticmethod
+    def _depth_args(depthImage, depth_scale):
+        if isinstance(depthImage, np.ndarray):
+            if depthImage.dtype == np.float64:
+                t = capi.DEPTH_F64
+            elif depthImage.dtype == np.float32:
+                t = capi.DEPTH_F32
+            elif depthImage.dtype == np.uint16:
+                t = capi.DEPTH_U16
+            else:
+                raise TypeError("depth must be float64, float32 or uint16")
+            if depthImage.strides[1] != depthImage.itemsize:
+                depthImage = np.ascontiguousarray(depthImage)
+            return depthImage, t, depthImage.strides[0], depthImage.ctypes.data
+        # torch tensor (host pinned or device)
+        import torch
+        t = {torch.float64: capi.DEPTH_F64, torch.float32: capi.DEPTH_F32, torch.uint16: capi.DEPTH_U16,
+             torch.int16: capi.DEPTH_U16}[depthImage.dtype]
+        return depthImage, t, depthImage.stride(0) * depthImage.element_size(), depthImage.data_ptr()
+
+    @staticmethod
+    def _gray_args(img):
+        if isinstance(img, np.ndarray):
+            if img.dtype != np.uint8:
+                raise TypeError("intensity image must be uint8")
+            if img.strides[1] != 1:
+                img = np.ascontiguousarray(img)
+            return img, img.strides[0], img.ctypes.data, img.shape
+        return img, img.stride(0), img.data_ptr(), tuple(img.shape)
+
+    def SetSourceFrame(self, intensityImage, depthImage, depth_scale=1.0):   # AN:466-476
+        g, gstep, gptr, shape = self._gray_args(intensityImage)
+        d, dtype, dstep, dptr = self._depth_args(depthImage, depth_scale)
+        if tuple(d.shape) != tuple(shape):
+            raise ValueError("intensity and depth image sizes differ")
+        self._check(self._L.phovo_set_source(self._h, gptr, gstep, dptr, dtype, dstep, float(depth_scale),
+                                             shape[0], shape[1]))
+
+    def SetTargetFrame(self, intensityImage, depthImage=None):      # AN:479-491 (depth ignored, AN:484)
+        g, gstep, gptr, shape = self._gray_args(intensityImage)
+        self._check(self._L.phovo_set_target(self._h, gptr, gstep, shape[0], shape[1]))
+
+    def SetInitialStateVector(self, initialStateVector):            # AN:494-497
+        s = np.ascontiguousarray(initialStateVector, dtype=np.float64).reshape(6)
+        self._check(self._L.phovo_set_initial_state(self._h, s.ctypes.data_as(capi._dp)))
+
+    def Optimize(self):                                             # AN:500-563
+        self._check(self._L.phovo_optimize(self._h))
+
+    def GetOptimalStateVector(self):                                # AN:566-569
+        s = np.zeros(6)
+        self._check(self._L.phovo_get_state(self._h, s.ctypes.data_as(capi._dp)))
+        return s
+
+    def GetOptimalRigidTransformationMatrix(self):                  # AN:572-578
+        m = np.zeros(16)
+        self._check(self._L.phovo_get_rt(self._h, m.ctypes.data_as(capi._dp)))
+        return m.reshape(4, 4)
+
+    # -- extensions (not in the reference) --------------------------------------------------
+    def SetConfig(self, cfg):
+        self._check(self._L.phovo_set_config(self._h, C.byref(cfg)))
+
+    def GetConfig(self):
+        cfg = capi.Config()
+        self._check(self._L.phovo_get_config(self._h, C.byref(cfg)))
+        return cfg
+
+    def SetMode(self, mode):
+        self._check(self._L.phovo_set_mode(self._h, mode))
+
+    def SetUseGraph(self, enable):
+        self._check(self._L.phovo_set_use_graph(self._h, int(enable)))
+
+    def SetBuildAllLevels(self, enable):
+        self._check(self._L.phovo_set_build_all_levels(self._h, int(enable)))
+
+    def SetStream(self, cuda_stream):
+        self._check(self._L.phovo_set_stream(self._h, cuda_stream))
+
+    def UsedGraph(self):
+        return bool(self._L.phovo_last_optimize_used_graph(self._h))
+
+    def GraphError(self):
+        return (self._L.phovo_graph_error(self._h) or b"").decode()
+
+    def PromoteTargetToSource(self, depthImage, depth_scale=1.0):
+        d, dtype, dstep, dptr = self._depth_args(depthImage, depth_scale)
+        self._check(self._L.phovo_promote_target_to_source(self._h, dptr, dtype, dstep, float(depth_scale)))
+
+    def IterationStats(self):
+        out = []
+        for i in range(self._L.phovo_num_iter_stats(self._h)):
+            s = capi.IterStats()
+            self._check(self._L.phovo_get_iter_stats(self._h, i, C.byref(s)))
+            out.append(s.as_dict())
+        return out
+
+    def LevelImage(self, which, level):
+        r, c = C.c_int32(), C.c_int32()
+        self._check(self._L.phovo_get_level_image(self._h, which, level, None, C.byref(r), C.byref(c)))
+        out = np.zeros((r.value, c.value), dtype=np.float32)
+        self._check(self._L.phovo_get_level_image(self._h, which, level, out.ctypes.data, C.byref(r), C.byref(c)))
+        return out
+
+    def EvalNormalEquations(self, level, state):
+        s = np.ascontiguousarray(state, dtype=np.float64).reshape(6)
+        st = capi.IterStats()
+        self._check(self._L.phovo_eval_normal_equations(self._h, level, s.ctypes.data_as(capi._dp), C.byref(st)))
+        return st.as_dict()
+
+    def EvalResiduals(self, level, state, shape):
+        s = np.ascontiguousarray(state, dtype=np.float64).reshape(6)
+        n = shape[0] * shape[1]
+        res, jac = np.zeros(n), np.zeros((n, 6))
+        self._check(self._L.phovo_eval_residuals(self._h, level, s.ctypes.data_as(capi._dp), res.ctypes.data, jac.ctypes.data))
+        return res, jac
+
+    def Timings(self):
+        a, b = C.c_float(), C.c_float()
+        self._check(self._L.phovo_get_timings(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def LaunchCount(self):
+        return int(self._L.phovo_launch_count(self._h))
+
+    def Synchronize(self):
+        self._check(self._L.phovo_synchronize(self._h))
+
+    # batch of independent pairs --------------------------------------------------------------
+    def BatchAlign(self, gray0, depth0, gray1, initial_states=None, depth_scale=1.0):
+        """Host (numpy / pinned torch) or device (torch) arrays [P,R,C]; returns (states[P,6], iterations[P,MAXL])."""
+        P, R, Cc = tuple(gray0.shape)
+        if isinstance(depth0, np.ndarray):
+            dtype = {np.dtype(np.float64): capi.DEPTH_F64, np.dtype(np.float32): capi.DEPTH_F32,
+                     np.dtype(np.uint16): capi.DEPTH_U16}[depth0.dtype]
+        else:
+            import torch
+            dtype = {torch.float64: capi.DEPTH_F64, torch.float32: capi.DEPTH_F32, torch.uint16: capi.DEPTH_U16,
+                     torch.int16: capi.DEPTH_U16}[depth0.dtype]
+        states = np.zeros((P, 6))
+        iters = np.zeros((P, capi.MAXL), dtype=np.int32)
+        init = None if initial_states is None else np.ascontiguousarray(initial_states, dtype=np.float64)
+        self._check(self._L.phovo_batch_align(self._h, P, R, Cc, capi._ptr(gray0), capi._ptr(depth0), dtype,
+                                              float(depth_scale), capi._ptr(gray1), capi._ptr(init),
+                                              states.ctypes.data, iters.ctypes.data))
+        return states, iters
+
+    def BatchAlignDevice(self, gray0, depth0, gray1, states_out, iters_out, initial_states=None, depth_scale=1.0):
+        """All torch device tensors; asynchronous on the context stream."""
+        import torch
+        P, R, Cc = tuple(gray0.shape)
+        dtype = {torch.float64: capi.DEPTH_F64, torch.float32: capi.DEPTH_F32, torch.uint16: capi.DEPTH_U16,
+                 torch.int16: capi.DEPTH_U16}[depth0.dtype]
+        self._check(self._L.phovo_batch_align_device(self._h, P, R, Cc, gray0.data_ptr(), depth0.data_ptr(), dtype,
+                                                     float(depth_scale), gray1.data_ptr(),
+                                                     None if initial_states is None else initial_states.data_ptr(),
+                                                     states_out.data_ptr(), iters_out.data_ptr()))
+
+    def BatchSetRecordStats(self, enable):
+        self._check(self._L.phovo_batch_set_record_stats(self._h, int(enable)))
+
+    def BatchIterationStats(self, pair):
+        out = []
+        for i in range(self._L.phovo_batch_num_iter_stats(self._h, pair)):
+            s = capi.IterStats()
+            self._check(self._L.phovo_batch_get_iter_stats(self._h, pair, i, C.byref(s)))
+            out.append(s.as_dict())
+        return out
+
+    # row-sharded single pair -------------------------------------------------------------------
+    def ShardConfigure(self, rank, world):
+        self._check(self._L.phovo_shard_configure(self._h, rank, world))
+
+    def ShardBuffer(self):
+        p = C.c_void_p()
+        self._check(self._L.phovo_shard_buffer(self._h, C.byref(p)))
+        return p.value
+
+    def ShardReadBuffer(self):
+        out = np.zeros(32)
+        self._check(self._L.phovo_shard_read_buffer(self._h, out.ctypes.data_as(capi._dp)))
+        return out
+
+    def ShardWriteBuffer(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(32)
+        self._check(self._L.phovo_shard_write_buffer(self._h, v.ctypes.data_as(capi._dp)))
+
+    def ShardBegin(self):
+        self._check(self._L.phovo_shard_begin(self._h))
+
+    def ShardBeginLevel(self, level):
+        self._check(self._L.phovo_shard_begin_level(self._h, level))
+
+    def ShardPartial(self):
+        self._check(self._L.phovo_shard_partial(self._h))
+
+    def ShardStep(self, want_done=True):
+        d = C.c_int32(0)
+        self._check(self._L.phovo_shard_step(self._h, C.byref(d) if want_done else None))
+        return bool(d.value)
+
+    def ShardFinish(self):
+        self._check(self._L.phovo_shard_finish(self._h))

@@ -1,0 +1,442 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden vectors.
+
+Bars (BASELINE.json north star): per-iteration J^T J / J^T r within 1e-5 relative, final pose
+within 1e-4 m / 1e-5 rad, identical executed iteration counts, bitwise run-to-run reproducible.
+All tests need a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (REL_NORMAL_EQ, assert_logs_match, assert_pose_close, g_rel_err, golden_log, h_rel_err,
+                     load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+def conv_cfg(oracle, cfg):
+    """product Config -> oracle Config (same POD layout)"""
+    return oracle.Config.from_buffer_copy(bytes(cfg))
+
+
+def make_odo(phovo, cfg, K, graph=True, build_all=False):
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    odo.SetConfig(cfg)
+    odo.SetIntrinsicMatrix(K)
+    odo.SetUseGraph(graph)
+    if build_all:
+        odo.SetBuildAllLevels(True)
+    return odo
+
+
+def run_gpu(odo, g0, d0, g1, state0=None):
+    odo.SetSourceFrame(g0, d0)
+    odo.SetTargetFrame(g1, None)
+    odo.SetInitialStateVector(np.zeros(6) if state0 is None else state0)
+    odo.Optimize()
+    return odo.GetOptimalStateVector(), odo.IterationStats()
+
+
+def run_oracle(oracle, cfg, K, g0, d0, g1, storage_f32=False, state0=None):
+    o = oracle.Oracle(conv_cfg(oracle, cfg), K, storage_f32=storage_f32)
+    o.set_source(g0, d0)
+    o.set_target(g1)
+    o.set_initial_state(np.zeros(6) if state0 is None else state0)
+    o.optimize()
+    return o
+
+
+# ---------------------------------------------------------------------------------------------
+def test_library_loaded_is_the_in_tree_cuda_build(phovo):
+    import os
+    assert os.path.samefile(phovo.capi.LIB_PATH, os.path.join(os.path.dirname(phovo.__file__), "libphovo_b200.so"))
+    assert b"sm_100a" in phovo.capi.lib().phovo_version()
+
+
+@pytest.mark.parametrize("shape,levels", [((480, 640), 4), ((135, 241), 3)])
+def test_pyramid_and_gradient_images(phovo, oracle, shape, levels):
+    """K1/K2 vs AN:115-189: every level of I0, D0, I1, Gx, Gy."""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(shape[0], shape[1], K=K, seed=3)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = levels
+    odo = make_odo(phovo, cfg, K, build_all=True)
+    odo.SetSourceFrame(g0, d0)
+    odo.SetTargetFrame(g1)
+    o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+    o.set_source(g0, d0)
+    o.set_target(g1)
+    for lvl in range(levels):
+        for which, tol in ((0, 1e-7), (1, 5e-7), (2, 1e-7), (3, 2e-6), (4, 2e-6)):
+            ref = o.level_image(which, lvl)
+            got = odo.LevelImage(which, lvl)
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got.astype(np.float64) - ref)) <= tol, (which, lvl)
+            # the device value is the correctly rounded fp32 of the reference double (up to the
+            # last-ulp differences of the double evaluation order): allow 1 float ulp on <0.1% of pixels
+            ref32 = ref.astype(np.float32)
+            bad = got != ref32
+            assert bad.mean() < 1e-3
+            assert np.max(np.abs(got[bad].astype(np.float64) - ref32[bad])) <= np.max(np.spacing(np.abs(ref32[bad]))) if bad.any() else True
+
+
+def test_strided_and_typed_inputs(phovo, oracle):
+    """Mat::step honoured for u8 and depth; f64 / f32 / u16 depth give the same pyramids."""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(120, 160, seed=4)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 3
+    for l, v in enumerate((3, 3, 3)):
+        cfg.max_num_iterations[l] = v
+    odo = make_odo(phovo, cfg, K)
+    s_ref, log_ref = run_gpu(odo, g0, d0, g1)
+    # strided views (row padding)
+    gp = np.zeros((120, 200), np.uint8); gp[:, :160] = g0
+    dp = np.zeros((120, 170)); dp[:, :160] = d0
+    g1p = np.zeros((120, 192), np.uint8); g1p[:, :160] = g1
+    s2, log2 = run_gpu(odo, gp[:, :160], dp[:, :160], g1p[:, :160])
+    assert np.array_equal(s_ref, s2)
+    # f32 depth: the synthetic depth is f32-representable, so results are identical
+    s3, _ = run_gpu(odo, g0, d0.astype(np.float32), g1)
+    assert np.array_equal(s_ref, s3)
+    # u16 depth in 1/5000 m (VisualOdometry.cpp:163): compare against the oracle fed raw*scale
+    raw = np.clip(np.rint(d0 * 5000.), 0, 65535).astype(np.uint16)
+    odo.SetSourceFrame(g0, raw, depth_scale=1. / 5000.)
+    odo.SetTargetFrame(g1)
+    odo.SetInitialStateVector(np.zeros(6))
+    odo.Optimize()
+    o = run_oracle(oracle, cfg, K, g0, raw.astype(np.float64) * (1. / 5000.), g1)
+    assert_logs_match(odo.IterationStats(), o.iter_stats(), what="u16 depth")
+    assert_pose_close(odo.GetOptimalStateVector(), o.state())
+
+
+@pytest.mark.parametrize("cfg_name,mode,K_name,seed", [
+    ("config_4_level_optimization_analytic", 0, "K_FRAME_ALIGNMENT", 0),      # BASELINE config 1
+    ("config_4_level_optimization_analytic", 1, "K_FRAME_ALIGNMENT", 1),      # Maxima-exact Jacobian
+    ("config_5_level_optimization_analytic", 0, "K_VISUAL_ODOMETRY", 2),      # BASELINE config 2 setup
+])
+def test_alignment_matches_oracle_640x480(phovo, oracle, cfg_name, mode, K_name, seed):
+    K = getattr(phovo.synth, K_name)
+    g0, d0, g1, _ = phovo.synth.make_pair(480, 640, K=K, seed=seed)
+    cfg = phovo.configs.to_config(cfg_name, phovo.capi, mode=mode)
+    odo = make_odo(phovo, cfg, K)
+    s, log = run_gpu(odo, g0, d0, g1)
+    o = run_oracle(oracle, cfg, K, g0, d0, g1)
+    assert_logs_match(log, o.iter_stats(), rel=REL_NORMAL_EQ, what=cfg_name)
+    assert_pose_close(s, o.state(), cfg_name)
+    for a, b in zip(log, o.iter_stats()):
+        assert abs(a["grad_norm"] - b["grad_norm"]) < 1e-5 * b["grad_norm"]
+        assert np.max(np.abs(a["state_out"] - b["state_out"])) < 1e-7
+    # against the oracle with fp32 image storage the only differences left are summation order
+    # and FMA contraction: three orders of magnitude tighter
+    o32 = run_oracle(oracle, cfg, K, g0, d0, g1, storage_f32=True)
+    assert_logs_match(log, o32.iter_stats(), rel=1e-9, what=cfg_name + " (f32 storage oracle)")
+    assert np.max(np.abs(s - o32.state())) < 1e-10
+    Rt = odo.GetOptimalRigidTransformationMatrix()
+    assert np.max(np.abs(Rt - o.rt())) < 1e-4
+
+
+def test_graph_and_stream_paths_are_bitwise_identical_and_reproducible(phovo):
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(480, 640, seed=5)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    odo_g = make_odo(phovo, cfg, K, graph=True)
+    odo_s = make_odo(phovo, cfg, K, graph=False)
+    sg, lg = run_gpu(odo_g, g0, d0, g1)
+    assert odo_g.UsedGraph(), "CUDA-graph WHILE path was not used: " + odo_g.GraphError()
+    ss, ls = run_gpu(odo_s, g0, d0, g1)
+    assert not odo_s.UsedGraph()
+    assert np.array_equal(sg, ss) and len(lg) == len(ls)
+    for a, b in zip(lg, ls):
+        assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"])
+    for _ in range(3):      # run-to-run: no floating-point atomics anywhere
+        s2, l2 = run_gpu(odo_g, g0, d0, g1)
+        assert np.array_equal(sg, s2)
+        assert all(np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"]) for a, b in zip(lg, l2))
+    # a fresh frame through the same (cached) graph
+    g0b, d0b, g1b, _ = phovo.synth.make_pair(480, 640, seed=6, xi=phovo.synth.random_motion(6))
+    sgb, _ = run_gpu(odo_g, g0b, d0b, g1b)
+    ssb, _ = run_gpu(odo_s, g0b, d0b, g1b)
+    assert np.array_equal(sgb, ssb) and not np.array_equal(sgb, sg)
+
+
+@pytest.mark.parametrize("name", ["pair_96x128_ref", "pair_96x128_fixed", "pair_90x135_ref"])
+def test_alignment_matches_golden(phovo, name):
+    gd = load_golden(name)
+    cfg = phovo.default_config()
+    cfg.mode = int(gd["fixed"])
+    cfg.num_levels = int(gd["levels"])
+    for l in range(phovo.MAXL):
+        cfg.max_num_iterations[l] = int(gd["iters"][l]) if l < cfg.num_levels else 0
+        cfg.min_gradient_norm[l] = float(gd["min_grad"])
+    odo = make_odo(phovo, cfg, gd["K"])
+    s, log = run_gpu(odo, gd["gray0"], gd["depth0"], gd["gray1"])
+    assert_logs_match(log, golden_log(gd), what=name)
+    assert_pose_close(s, gd["final_state"], name)
+    for i in range(3):
+        lvl, st = int(gd["eval%d_level" % i]), gd["eval%d_state" % i]
+        if cfg.max_num_iterations[lvl] == 0:
+            continue
+        e = odo.EvalNormalEquations(lvl, st)
+        assert e["num_valid"] == int(gd["eval%d_count" % i])
+        assert h_rel_err(e["H"], gd["eval%d_H" % i]) < REL_NORMAL_EQ
+        assert g_rel_err(e["g"], gd["eval%d_g" % i]) < REL_NORMAL_EQ
+        res, _ = odo.EvalResiduals(lvl, st, odo.LevelImage(0, lvl).shape)
+        assert np.max(np.abs(res - gd["eval%d_res" % i])) < 2e-7      # two fp32-stored intensities
+        assert np.array_equal(res != 0, gd["eval%d_res" % i] != 0) or np.mean((res != 0) != (gd["eval%d_res" % i] != 0)) < 1e-3
+
+
+def test_eval_at_random_states_and_dense_rows(phovo, oracle):
+    """Normal equations, residual vector (target-indexed scatter) and Jacobian rows (source-indexed)
+    at states away from the optimisation trajectory, both Jacobian variants."""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(240, 320, seed=8)
+    rng = np.random.default_rng(8)
+    for mode in (0, 1):
+        cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi, mode=mode)
+        cfg.num_levels = 3
+        for l in range(3):
+            cfg.max_num_iterations[l] = 1
+        odo = make_odo(phovo, cfg, K)
+        odo.SetSourceFrame(g0, d0)
+        odo.SetTargetFrame(g1)
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K, storage_f32=True)
+        o.set_source(g0, d0)
+        o.set_target(g1)
+        for lvl in range(3):
+            for _ in range(3):
+                st = np.concatenate([rng.uniform(-0.05, 0.05, 3), rng.uniform(-0.03, 0.03, 3)])
+                e = odo.EvalNormalEquations(lvl, st)
+                r = o.eval(lvl, st, want_residuals=True, want_jacobian=True)
+                assert e["num_valid"] == r["num_valid"]
+                assert h_rel_err(e["H"], r["H"]) < 1e-10 and g_rel_err(e["g"], r["g"]) < 1e-9
+                assert abs(e["cost"] - r["cost"]) < 1e-10 * r["cost"]
+                res, jac = odo.EvalResiduals(lvl, st, o.level_image(0, lvl).shape)
+                assert np.array_equal(res, r["residuals"])          # same fp32 operands, one subtraction
+                assert np.max(np.abs(jac - r["jacobian"])) < 1e-11 * max(1.0, np.max(np.abs(r["jacobian"])))
+
+
+def test_semantics_round_half_away_strict_depth_on_gpu(phovo, oracle):
+    rows, cols = 4, 8
+    K = np.array([[8., 0, 3.5], [0, 8., 1.5], [0, 0, 1]])
+    g = (np.arange(rows * cols).reshape(rows, cols) * 3 % 251).astype(np.uint8)
+    d = np.full((rows, cols), 2.0)
+    d[0, 0], d[0, 1] = 0.3, 5.0
+    cfg = phovo.default_config()
+    cfg.num_levels = 1
+    cfg.max_num_iterations[0] = 1
+    odo = make_odo(phovo, cfg, K)
+    odo.SetSourceFrame(g, d)
+    odo.SetTargetFrame(g)
+    o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+    o.set_source(g, d)
+    o.set_target(g)
+    for tx in (0.125, -0.125, -0.0625, 0.0):
+        st = np.array([tx, 0, 0, 0, 0, 0])
+        e = odo.EvalNormalEquations(0, st)
+        r = o.eval(0, st, want_residuals=True)
+        assert e["num_valid"] == r["num_valid"]
+        res, _ = odo.EvalResiduals(0, st, (rows, cols))
+        assert np.array_equal(res, r["residuals"])
+    assert odo.EvalNormalEquations(0, np.array([0.125, 0, 0, 0, 0, 0]))["num_valid"] == rows * (cols - 1) - 2
+
+
+def test_zero_iteration_levels_step_then_stop_and_nonzero_initial_state(phovo, oracle):
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(240, 320, seed=9)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    for l, (m, thr) in enumerate(((0, 300.), (3, 0.), (0, 300.), (50, 1e9))):
+        cfg.max_num_iterations[l] = m
+        cfg.min_gradient_norm[l] = thr
+    s0 = np.array([0.002, -0.001, 0.003, 0.001, 0.0005, -0.001])
+    for graph in (True, False):
+        odo = make_odo(phovo, cfg, K, graph=graph)
+        s, log = run_gpu(odo, g0, d0, g1, state0=s0)
+        o = run_oracle(oracle, cfg, K, g0, d0, g1, state0=s0)
+        assert [(e["level"], e["iteration"]) for e in log] == [(3, 0), (1, 0), (1, 1), (1, 2)]
+        assert_logs_match(log, o.iter_stats())
+        assert_pose_close(s, o.state())
+        assert np.array_equal(log[0]["state_in"], s0)
+    cfg0 = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    for l in range(4):
+        cfg0.max_num_iterations[l] = 0
+    odo = make_odo(phovo, cfg0, K)
+    s, log = run_gpu(odo, g0, d0, g1, state0=s0)
+    assert len(log) == 0 and np.array_equal(s, s0)
+
+
+def test_blur_configuration(phovo, oracle):
+    """K2b: blurFilterSize > 0 (GaussianBlur twice, AN:144-148) on intensity pyramids only."""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(240, 320, seed=10)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 3
+    for l, (k, m) in enumerate(((3, 2), (5, 4), (7, 6))):
+        cfg.blur_filter_size[l] = k
+        cfg.max_num_iterations[l] = m
+    odo = make_odo(phovo, cfg, K, build_all=True)
+    s, log = run_gpu(odo, g0, d0, g1)
+    o = run_oracle(oracle, cfg, K, g0, d0, g1)
+    for lvl in range(3):
+        for which in (0, 2, 3, 4):
+            assert np.max(np.abs(odo.LevelImage(which, lvl) - o.level_image(which, lvl))) < 2e-6
+        assert np.array_equal(odo.LevelImage(1, lvl), o.level_image(1, lvl).astype(np.float32))   # depth is not blurred
+    assert_logs_match(log, o.iter_stats(), what="blur")
+    assert_pose_close(s, o.state())
+
+
+def test_vo_promote_target_to_source(phovo, oracle):
+    """VO loop (VisualOdometry.cpp:222-257): frame k's target pyramid reused as frame k+1's source."""
+    K = phovo.synth.K_VISUAL_ODOMETRY
+    frames = [phovo.synth.make_sequence_frame(k, 240, 320, K=K) for k in range(4)]
+    cfg = phovo.configs.to_config("config_5_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 4
+    for l, m in enumerate((0, 5, 20, 50)):
+        cfg.max_num_iterations[l] = m
+    a = make_odo(phovo, cfg, K)
+    b = make_odo(phovo, cfg, K)
+    b.SetSourceFrame(*frames[0])
+    for k in range(1, 4):
+        a.SetSourceFrame(*frames[k - 1])
+        a.SetTargetFrame(frames[k][0])
+        a.SetInitialStateVector(np.zeros(6))
+        a.Optimize()
+        if k > 1:
+            b.PromoteTargetToSource(frames[k - 1][1])
+        b.SetTargetFrame(frames[k][0])
+        b.SetInitialStateVector(np.zeros(6))
+        b.Optimize()
+        assert np.array_equal(a.GetOptimalStateVector(), b.GetOptimalStateVector())
+        o = run_oracle(oracle, cfg, K, frames[k - 1][0], frames[k - 1][1], frames[k][0])
+        assert_logs_match(b.IterationStats(), o.iter_stats(), what="vo frame %d" % k)
+        assert_pose_close(b.GetOptimalStateVector(), o.state())
+
+
+def test_row_sharded_partials_sum_to_full(phovo, oracle):
+    """Config-5 style row sharding emulated on one GPU: the per-rank 27 partial sums add up to the
+    single-GPU normal equations, and stepping from the summed buffer reproduces Optimize()."""
+    K = np.array([[1050., 0, 639.5], [0, 1050., 359.5], [0, 0, 1]])
+    g0, d0, g1, _ = phovo.synth.make_pair(720, 1280, K=K, seed=11)
+    cfg = phovo.configs.to_config("config_6_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 5
+    for l, m in enumerate((0, 0, 5, 20, 50)):
+        cfg.max_num_iterations[l] = m
+    full = make_odo(phovo, cfg, K)
+    s_full, log_full = run_gpu(full, g0, d0, g1)
+    world = 4
+    ranks = []
+    for r in range(world):
+        odo = make_odo(phovo, cfg, K)
+        odo.ShardConfigure(r, world)
+        odo.SetSourceFrame(g0, d0)
+        odo.SetTargetFrame(g1)
+        odo.SetInitialStateVector(np.zeros(6))
+        odo.ShardBegin()
+        ranks.append(odo)
+    n_iter = 0
+    for level in range(cfg.num_levels - 1, -1, -1):
+        if cfg.max_num_iterations[level] == 0:
+            continue
+        for odo in ranks:
+            odo.ShardBeginLevel(level)
+        while True:
+            host = []
+            for odo in ranks:
+                odo.ShardPartial()
+                host.append(odo.ShardReadBuffer())
+            total = np.zeros(32)
+            for h in host:                                  # the all-reduce, in rank order
+                total = total + h
+            ref = log_full[n_iter]
+            assert h_rel_err(total[:21], ref["H"]) < 1e-12 and g_rel_err(total[21:27], ref["g"]) < 1e-10
+            assert int(total[28]) == ref["num_valid"]
+            done = []
+            for odo in ranks:
+                odo.ShardWriteBuffer(total)
+                done.append(odo.ShardStep())
+            n_iter += 1
+            assert len(set(done)) == 1
+            if done[0]:
+                break
+    assert n_iter == len(log_full)
+    for odo in ranks:
+        odo.ShardFinish()
+        assert np.max(np.abs(odo.GetOptimalStateVector() - s_full)) < 1e-12
+
+
+def test_ceres_mode_residual_jacobian_and_lm(phovo, oracle):
+    """K5 (CE:156-269 + sample.h) vs golden / oracle; restated LM trajectory vs the oracle's."""
+    gd = load_golden("ceres_24x32")
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
+    cfg.num_levels = 2
+    cfg.max_num_iterations[0], cfg.max_num_iterations[1] = 5, 10
+    odo = make_odo(phovo, cfg, gd["K"])
+    odo.SetSourceFrame(gd["gray0"], gd["depth0"])
+    odo.SetTargetFrame(gd["gray1"])
+    o32 = oracle.Oracle(conv_cfg(oracle, cfg), gd["K"], storage_f32=True)
+    o32.set_source(gd["gray0"], gd["depth0"].astype(np.float64))
+    o32.set_target(gd["gray1"])
+    for lvl in (0, 1):
+        shape = odo.LevelImage(0, lvl).shape
+        res, jac = odo.EvalResiduals(lvl, gd["state"], shape)
+        assert np.max(np.abs(res - gd["res%d" % lvl])) < 5e-7
+        assert np.array_equal(res != 0, gd["res%d" % lvl] != 0)           # same scatter pattern
+        assert np.max(np.abs(jac - gd["jac%d" % lvl])) < 1e-5 * np.max(np.abs(gd["jac%d" % lvl]))
+        r = o32.eval(lvl, gd["state"], want_residuals=True, want_jacobian=True)
+        assert np.max(np.abs(res - r["residuals"])) < 1e-15
+        assert np.max(np.abs(jac - r["jacobian"])) < 1e-11 * np.max(np.abs(r["jacobian"]))
+        e = odo.EvalNormalEquations(lvl, gd["state"])
+        assert h_rel_err(e["H"], r["H"]) < 1e-10 and g_rel_err(e["g"], r["g"]) < 1e-9
+        assert abs(e["cost"] - r["cost"]) <= 1e-12 * r["cost"]
+    # full Ceres-config run on a larger pair against the oracle's restated LM
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(240, 320, seed=12)
+    cfg = phovo.configs.to_config("config_4_level_optimization_ceres", phovo.capi)
+    odo = make_odo(phovo, cfg, K)
+    s, log = run_gpu(odo, g0, d0, g1)
+    o = run_oracle(oracle, cfg, K, g0, d0, g1)
+    olog = o.iter_stats()
+    assert [(e["level"], e["iteration"], e["accepted"]) for e in log] == [(e["level"], e["iteration"], e["accepted"]) for e in olog]
+    for a, b in zip(log, olog):
+        assert abs(a["cost"] - b["cost"]) < 1e-5 * b["cost"]
+    assert_pose_close(s, o.state(), "ceres LM")
+
+
+def test_error_paths(phovo):
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(60, 80, seed=1)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 2
+    cfg.max_num_iterations[0] = cfg.max_num_iterations[1] = 2
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    odo.SetConfig(cfg)
+    with pytest.raises(phovo.PhovoError):            # target before source (AN:171 reads pyramid0)
+        odo.SetTargetFrame(g1)
+    odo.SetSourceFrame(g0, d0)
+    with pytest.raises(phovo.PhovoError):            # size mismatch
+        odo.SetTargetFrame(g1[:30])
+    odo.SetTargetFrame(g1)
+    with pytest.raises(phovo.PhovoError):            # intrinsics missing
+        odo.Optimize()
+    odo.SetIntrinsicMatrix(K)
+    odo.SetInitialStateVector(np.zeros(6))
+    odo.Optimize()
+    # all depth invalid -> singular normal equations -> NaN in the reference; we report it
+    odo.SetSourceFrame(g0, np.zeros_like(d0))
+    odo.SetTargetFrame(g1)
+    odo.SetInitialStateVector(np.zeros(6))
+    with pytest.raises(phovo.PhovoError) as e:
+        odo.Optimize()
+    assert e.value.code == phovo.capi.E_NUMERIC
+    with pytest.raises(phovo.PhovoError):
+        odo.ReadConfigurationFile("/nonexistent/config.yml")
+    bad = phovo.default_config()
+    bad.num_levels = 0
+    with pytest.raises(phovo.PhovoError):
+        odo.SetConfig(bad)
+    # too many levels for the image
+    cfg.num_levels = 9
+    odo.SetConfig(cfg)
+    with pytest.raises(phovo.PhovoError):
+        odo.SetSourceFrame(g0, d0)
