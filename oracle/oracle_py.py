@@ -133,7 +133,7 @@ class Oracle:
         self.h = self.L.pho_create()
         self.cfg = cfg
         self.L.pho_set_config(self.h, C.byref(cfg))
-        self.L.pho_set_options(self.h, int(storage_f32), int(lean))
+        self.L.pho_set_options(self.h, int(storage_f32), int(lean))   # storage_f32: 0 | 1 (all fp32) | 2 (fp32, depth fp64)
         self.K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
         self.L.pho_set_intrinsics(self.h, _d(self.K))
 

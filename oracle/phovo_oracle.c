@@ -278,7 +278,7 @@ void pho_set_source(pho_oracle* o, const uint8_t* gray, size_t gray_step, const 
   if (o->storage_f32)
     for (int l = 0; l < o->cfg.num_levels; ++l) {
       round_to_f32(o->I0[l], (size_t)o->rows[l] * o->cols[l]);
-      round_to_f32(o->D0[l], (size_t)o->rows[l] * o->cols[l]);
+      if (o->storage_f32 == 1) round_to_f32(o->D0[l], (size_t)o->rows[l] * o->cols[l]);
     }
   o->have_src = 1;
 }

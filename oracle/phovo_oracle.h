@@ -56,8 +56,9 @@ pho_oracle* pho_create(void);
 void pho_destroy(pho_oracle* o);
 void pho_set_config(pho_oracle* o, const phovo_config* cfg);
 /* oracle-only switches:
- *  storage_f32  : round every pyramid/gradient level to float after building it (emulates the
- *                 device's fp32 image storage so integer decisions can be compared exactly)
+ *  storage_f32  : 1 = round every pyramid/gradient level to float after building it (emulates the
+ *                 device's fp32 image storage so integer decisions can be compared exactly);
+ *                 2 = the same but the depth pyramid stays double (the device's Ceres-mode layout)
  *  lean         : skip the reference's per-pass allocation + setZero of the N x 7 doubles and the
  *                 materialised Jacobian (AN:519-524); identical results, used only for timing   */
 void pho_set_options(pho_oracle* o, int storage_f32, int lean);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kBlock) k_winner(LevelParams L, LevelPtrs P, c
   pose_load(pose, T);
   const int n = L.rows * L.cols;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    const double d = (double)__ldg(P.D0 + i);
+    const double d = CERES && P.D0d ? __ldg(P.D0d + i) : (double)__ldg(P.D0 + i);
     const int r = i / L.cols, c = i - r * L.cols;
     Warped w;
     if (warp_pixel<CERES>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
@@ -103,14 +103,16 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
   const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
     const int r = i / L.cols, c = i - r * L.cols;
-    const double d = (double)__ldg(P.D0 + i);
+    const double d = (MODE == 2 && P.D0d) ? __ldg(P.D0d + i) : (double)__ldg(P.D0 + i);
     Warped w;
     if (MODE == 2) {
       const bool ok = warp_pixel<true>(L, T, r, c, d, w);
       if (!ok) continue;
+      const bool mine = i >= i_begin && i < i_end;
+      if (mine) acc[28] += 1.;
       if (P.winner[w.t] != i) continue;   // overwritten by a later source pixel (CE:261)
       P.winner[w.t] = -1;
-      if (i < i_begin || i >= i_end) continue;
+      if (!mine) continue;
       int x1, x2, y1, y2; double dx, dy;
       linear_init_axis(w.tr - 0.5, L.rows, y1, y2, dy);   // sample.h:67-71
       linear_init_axis(w.tc - 0.5, L.cols, x1, x2, dx);
@@ -124,7 +126,6 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
       for (int k = 0; k < 6; ++k) J[k] = s1 * Ju[k] + s2 * Jv[k];   // jet_extras.h:87-109
       accumulate_row(acc, J, res);
       acc[27] = fma(res, res, acc[27]);
-      acc[28] += 1.;
       if (DUMP) {
         if (dump_res) dump_res[w.t] = res;
         if (dump_jac) for (int k = 0; k < 6; ++k) dump_jac[(size_t)w.t * 6 + k] = J[k];

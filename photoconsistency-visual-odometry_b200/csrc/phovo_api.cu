@@ -68,6 +68,7 @@ LevelPtrs phovo_ctx::level_ptrs(int level) const {
   LevelPtrs P;
   P.I0 = I0[level]; P.D0 = D0[level]; P.I1 = I1[level]; P.Gx = Gx[level]; P.Gy = Gy[level];
   P.winner = winner;
+  P.D0d = cfg.mode == PHOVO_MODE_CERES ? D0d[level] : nullptr;
   return P;
 }
 
@@ -119,6 +120,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
       ctx->lcap[l][a] = cap;
       if (before != *arrs[a]) changed = true;
     }
+    if (ctx->cfg.mode == PHOVO_MODE_CERES) CK(ensure(&ctx->D0d[l], &ctx->d0d_cap[l], n));
   }
   if (max_px == 0) max_px = 1;
   {
@@ -201,6 +203,8 @@ static int build_depth(phovo_ctx* ctx, const void* dev_depth, int depth_type, si
     const int r = ctx->lrows[l], c = ctx->lcols[l];
     ctx->launches += launch_build_level(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, l, ctx->scratch64[0], r, c);
     ctx->launches += launch_store_f32(ctx->stream, ctx->scratch64[0], ctx->D0[l], (size_t)r * c);
+    if (ctx->cfg.mode == PHOVO_MODE_CERES)
+      CK(cudaMemcpyAsync(ctx->D0d[l], ctx->scratch64[0], sizeof(double) * (size_t)r * c, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CK(cudaGetLastError());
   return PHOVO_OK;
@@ -264,6 +268,7 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   ctx->invalidate_graph();
   phovo_batch_release(ctx);
   for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
+    cudaFree(ctx->D0d[l]);
     cudaFree(ctx->I0[l]); cudaFree(ctx->D0[l]); cudaFree(ctx->I1[l]); cudaFree(ctx->Gx[l]); cudaFree(ctx->Gy[l]);
   }
   cudaFree(ctx->winner); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
@@ -337,7 +342,12 @@ extern "C" int phovo_load_config_yaml(phovo_ctx* ctx, const char* path) {
 
 extern "C" int phovo_set_mode(phovo_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return PHOVO_E_INVALID;
-  if (ctx->cfg.mode != mode) { ctx->cfg.mode = mode; ctx->invalidate_graph(); }
+  if (ctx->cfg.mode != mode) {
+    // Ceres mode keeps an fp64 copy of the depth pyramid: frames must be set again after a switch
+    if (ctx->cfg.mode == PHOVO_MODE_CERES || mode == PHOVO_MODE_CERES) ctx->have_src = ctx->have_tgt = false;
+    ctx->cfg.mode = mode;
+    ctx->invalidate_graph();
+  }
   return PHOVO_OK;
 }
 

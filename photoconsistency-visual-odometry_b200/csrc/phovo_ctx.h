@@ -34,6 +34,7 @@ struct phovo_ctx {
   float* I1[PHOVO_MAX_LEVELS] = {nullptr};
   float* Gx[PHOVO_MAX_LEVELS] = {nullptr};
   float* Gy[PHOVO_MAX_LEVELS] = {nullptr};
+  double* D0d[PHOVO_MAX_LEVELS] = {nullptr}; size_t d0d_cap[PHOVO_MAX_LEVELS] = {0};  // Ceres mode only
   size_t lcap[PHOVO_MAX_LEVELS][5] = {{0}};
   int* winner = nullptr; size_t winner_cap = 0;           // one int per pixel of the largest active level
   double* scratch64[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};

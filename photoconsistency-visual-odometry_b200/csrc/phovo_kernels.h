@@ -31,6 +31,9 @@ int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int co
 struct LevelPtrs {
   const float* I0; const float* D0; const float* I1; const float* Gx; const float* Gy;
   int* winner;        // rows*cols ints, all -1 between iterations
+  const double* D0d;  // fp64 depth level (Ceres mode only, else null): the truncation scatter of
+                      // CE:250-251 sits on integer boundaries at the identity state, so fp32 depth
+                      // rounding would flip slots there
 };
 
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);
