@@ -203,6 +203,9 @@ int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable);
 int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int index, phovo_iter_stats* out);
 int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);
 int phovo_synchronize(phovo_ctx* ctx);
+/* device time (CUDA events on the context stream) of the two kernels of the last
+ * phovo_batch_align_device call: pyramid (K1b) and align (K3-batch); blocks until they finished */
+int phovo_batch_get_kernel_times(phovo_ctx* ctx, float* pyramid_ms, float* align_ms);
 
 /* ---- row-sharded single pair across ranks (extension; BASELINE config 7680x4320) -------- */
 /* Rank `rank` of `world` evaluates source rows [row_begin,row_end) of each level (the library

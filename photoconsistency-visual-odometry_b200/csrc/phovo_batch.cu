@@ -1,17 +1,330 @@
-// phovo_batch.cu -- batch-of-pairs extension (placeholder until the persistent kernel lands).
+// phovo_batch.cu -- host side of the batch-of-pairs extension (phovo_batch_* in phovo_b200.h).
+//
+// HBM layout: inputs stay in the caller's layout ([P][rows][cols] u8 / depth); the pyramid kernel
+// writes one packed record per pair holding, for each ACTIVE level, I0 and I1 as u16 tap sums and
+// D0 as fp32 (8 B/px; 192 000 B per 640x480 pair under the 4-level config).  The align kernel
+// reads each record exactly once.  Host inputs are streamed in chunks through two device staging
+// slots on two streams so that the PCIe copy of chunk k+1 overlaps the kernels of chunk k.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "phovo_batch.h"
 #include "phovo_ctx.h"
 
-struct phovo_batch_state { int dummy; };
-void phovo_batch_release(phovo_ctx* ctx) { delete ctx->batch; ctx->batch = nullptr; }
+using namespace phovo;
 
-extern "C" int phovo_batch_align(phovo_ctx* ctx, int, int, int, const uint8_t*, const void*, int, double,
-                                 const uint8_t*, const double*, double*, int32_t*) {
-  return ctx ? ctx->fail(PHOVO_E_UNSUPPORTED, "batch path not built yet") : PHOVO_E_INVALID;
+struct phovo_batch_state {
+  // packed level records
+  uint8_t* store = nullptr; size_t store_cap = 0;
+  // outputs of the last call (device)
+  double* states = nullptr; size_t states_cap = 0;
+  int32_t* iters = nullptr; size_t iters_cap = 0;
+  double* init = nullptr; size_t init_cap = 0;
+  phovo_iter_stats* log = nullptr; size_t log_cap_entries = 0;
+  int32_t* log_counts = nullptr; size_t log_counts_cap = 0;
+  // host mirrors of the stats (filled on demand)
+  std::vector<phovo_iter_stats> h_log; std::vector<int32_t> h_log_counts;
+  int log_per_pair = 0; int last_pairs = 0; bool log_fetched = false;
+  bool record_stats = false;
+  // staging for host inputs: two slots
+  uint8_t* stage_g0[2] = {nullptr, nullptr}; uint8_t* stage_g1[2] = {nullptr, nullptr}; char* stage_d[2] = {nullptr, nullptr};
+  size_t stage_cap_g[2] = {0, 0}, stage_cap_g1[2] = {0, 0}, stage_cap_d[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  double* h_states_pinned = nullptr; int32_t* h_iters_pinned = nullptr; size_t h_out_cap = 0;
+  size_t prepared_smem = 0;
+  int sm_count = 0;
+  cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // before pyramid / between / after align
+  bool timed = false;
+};
+
+#define CK(call)                                                      \
+  do {                                                                \
+    cudaError_t e_ = (call);                                          \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(#call, e_);          \
+  } while (0)
+
+template <class T>
+static cudaError_t ensure(T** p, size_t* cap, size_t want) {
+  if (*cap >= want && *p) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc((void**)p, want * sizeof(T));
+  if (e == cudaSuccess) *cap = want;
+  return e;
 }
-extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int, int, int, const uint8_t*, const void*, int, double,
-                                        const uint8_t*, const double*, double*, int32_t*) {
-  return ctx ? ctx->fail(PHOVO_E_UNSUPPORTED, "batch path not built yet") : PHOVO_E_INVALID;
+
+void phovo_batch_release(phovo_ctx* ctx) {
+  phovo_batch_state* b = ctx->batch;
+  if (!b) return;
+  cudaFree(b->store); cudaFree(b->states); cudaFree(b->iters); cudaFree(b->init); cudaFree(b->log); cudaFree(b->log_counts);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(b->stage_g0[s]); cudaFree(b->stage_g1[s]); cudaFree(b->stage_d[s]);
+    if (b->ev_copied[s]) cudaEventDestroy(b->ev_copied[s]);
+    if (b->ev_consumed[s]) cudaEventDestroy(b->ev_consumed[s]);
+  }
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  cudaFreeHost(b->h_states_pinned); cudaFreeHost(b->h_iters_pinned);
+  delete b;
+  ctx->batch = nullptr;
 }
-extern "C" int phovo_batch_set_record_stats(phovo_ctx* ctx, int) { return ctx ? PHOVO_OK : PHOVO_E_INVALID; }
-extern "C" int phovo_batch_get_iter_stats(const phovo_ctx*, int, int, phovo_iter_stats*) { return PHOVO_E_UNSUPPORTED; }
-extern "C" int phovo_batch_num_iter_stats(const phovo_ctx*, int) { return 0; }
+
+static int get_state(phovo_ctx* ctx, phovo_batch_state** out) {
+  if (!ctx->batch) {
+    ctx->batch = new phovo_batch_state();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->batch->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->batch->copy_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      CK(cudaEventCreateWithFlags(&ctx->batch->ev_copied[s], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->batch->ev_consumed[s], cudaEventDisableTiming));
+    }
+  }
+  *out = ctx->batch;
+  return PHOVO_OK;
+}
+
+static void level_size(int rows, int cols, int level, int* orows, int* ocols) {
+  const double f = ldexp(1.0, -level);
+  *orows = level == 0 ? rows : (int)lrint(rows * f);
+  *ocols = level == 0 ? cols : (int)lrint(cols * f);
+}
+
+// Parameter block for a rows x cols batch under the context's config; fails loudly when a
+// configuration cannot run in the shared-memory-resident kernel (there is no slower fallback
+// inside this entry point: the caller is told to use the per-pair API).
+static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, int* nmax_out) {
+  if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
+  if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
+  if (ctx->cfg.mode == PHOVO_MODE_CERES) return ctx->fail(PHOVO_E_UNSUPPORTED, "the batch kernel implements the analytic solver only");
+  memset(bp, 0, sizeof(*bp));
+  bp->num_pairs = num_pairs; bp->rows = rows; bp->cols = cols;
+  bp->mode = ctx->cfg.mode; bp->log_cap = log_cap;
+  bp->min_depth = ctx->cfg.min_depth; bp->max_depth = ctx->cfg.max_depth;
+  int a = 0, nmax = 0;
+  unsigned long long off = 0;
+  for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
+    if (ctx->cfg.max_num_iterations[level] <= 0) continue;
+    if (level == 0) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: level 0 does not fit in shared memory; use the per-pair API");
+    if (ctx->cfg.blur_filter_size[level] > 1) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: blurFilterSize > 0 is only supported by the per-pair API");
+    int lr, lc;
+    level_size(rows, cols, level, &lr, &lc);
+    if (lr < 1 || lc < 1) return ctx->fail(PHOVO_E_INVALID, "image too small for the number of pyramid levels");
+    const int n = lr * lc;
+    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
+    nmax = std::max(nmax, n);
+    bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
+    bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
+    bp->px_offset[a + 1] = bp->px_offset[a] + n;
+    const unsigned long long n16 = ((unsigned long long)n * 2 + 15) & ~15ull, n32 = ((unsigned long long)n * 4 + 15) & ~15ull;
+    bp->off_D0[a] = off; off += n32;
+    bp->off_I0[a] = off; off += n16;
+    bp->off_I1[a] = off; off += n16;
+    // CPhotoconsistencyOdometryAnalytic.h:203-209
+    const double scaleFactor = 1.0 / pow(2, level);
+    bp->fx[a] = ctx->K[0] * scaleFactor; bp->fy[a] = ctx->K[4] * scaleFactor;
+    bp->ox[a] = ctx->K[2] * scaleFactor; bp->oy[a] = ctx->K[5] * scaleFactor;
+    bp->inv_fx[a] = 1.f / bp->fx[a]; bp->inv_fy[a] = 1.f / bp->fy[a];
+    bp->lambda[a] = ctx->cfg.lambda_step[level]; bp->min_grad[a] = ctx->cfg.min_gradient_norm[level];
+    bp->grad_k[a] = ctx->cfg.grad_scale[level] / 1020.0;
+    ++a;
+  }
+  bp->num_active = a;
+  bp->record_bytes = off ? off : 16;
+  *nmax_out = nmax;
+  return PHOVO_OK;
+}
+
+static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& bp, int nmax, cudaStream_t stream,
+                      const uint8_t* g0, const void* d0, int depth_type, double depth_scale, const uint8_t* g1,
+                      uint8_t* store, const double* init, double* states, int32_t* iters,
+                      phovo_iter_stats* log, int32_t* log_counts) {
+  CK(cudaMemsetAsync(iters, 0, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)bp.num_pairs, stream));
+  if (bp.num_active == 0) {  // nothing to optimise: the state passes through (AN:526)
+    if (init) CK(cudaMemcpyAsync(states, init, sizeof(double) * 6 * (size_t)bp.num_pairs, cudaMemcpyDeviceToDevice, stream));
+    else CK(cudaMemsetAsync(states, 0, sizeof(double) * 6 * (size_t)bp.num_pairs, stream));
+    return PHOVO_OK;
+  }
+  const size_t smem = batch_align_smem_bytes(nmax);
+  if (b->prepared_smem < smem) {
+    CK(batch_align_prepare(smem));
+    b->prepared_smem = smem;
+  }
+  const int src = depth_type == PHOVO_DEPTH_F64 ? SRC_F64 : depth_type == PHOVO_DEPTH_F32 ? SRC_F32 : SRC_U16;
+  if (!b->ev_k[0]) for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&b->ev_k[i]));
+  CK(cudaEventRecord(b->ev_k[0], stream));
+  ctx->launches += launch_batch_pyramid(stream, bp, g0, d0, src, depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0, g1, store);
+  CK(cudaEventRecord(b->ev_k[1], stream));
+  const int grid = std::min(bp.num_pairs, b->sm_count);   // one persistent CTA per SM
+  ctx->launches += launch_batch_align(stream, bp, grid, smem, store, init, states, iters, log, log_counts);
+  CK(cudaEventRecord(b->ev_k[2], stream));
+  b->timed = true;
+  CK(cudaGetLastError());
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_get_kernel_times(phovo_ctx* ctx, float* pyramid_ms, float* align_ms) {
+  if (!ctx || !ctx->batch || !ctx->batch->timed) return PHOVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->batch->ev_k[2]));
+  float a = 0, c = 0;
+  CK(cudaEventElapsedTime(&a, ctx->batch->ev_k[0], ctx->batch->ev_k[1]));
+  CK(cudaEventElapsedTime(&c, ctx->batch->ev_k[1], ctx->batch->ev_k[2]));
+  if (pyramid_ms) *pyramid_ms = a;
+  if (align_ms) *align_ms = c;
+  return PHOVO_OK;
+}
+
+static size_t depth_elt(int t) { return t == PHOVO_DEPTH_F64 ? 8 : t == PHOVO_DEPTH_F32 ? 4 : 2; }
+
+extern "C" int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable) {
+  if (!ctx) return PHOVO_E_INVALID;
+  phovo_batch_state* b; int rc = get_state(ctx, &b);
+  if (rc) return rc;
+  b->record_stats = enable != 0;
+  return PHOVO_OK;
+}
+
+static int prepare_log(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int* log_cap) {
+  *log_cap = 0;
+  b->last_pairs = num_pairs; b->log_fetched = false; b->log_per_pair = 0;
+  if (!b->record_stats) return PHOVO_OK;
+  int total = 0;
+  for (int l = 0; l < ctx->cfg.num_levels; ++l) total += ctx->cfg.max_num_iterations[l];
+  if (total < 1) total = 1;
+  CK(ensure(&b->log, &b->log_cap_entries, (size_t)num_pairs * total));
+  CK(ensure(&b->log_counts, &b->log_counts_cap, (size_t)num_pairs));
+  b->log_per_pair = total;
+  *log_cap = total;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                                        const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1,
+                                        const double* initial_states, double* states, int32_t* iters) {
+  if (!ctx || !gray0 || !depth0 || !gray1 || !states || !iters) return PHOVO_E_INVALID;
+  if (depth_type < 0 || depth_type > 2) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
+  CK(cudaSetDevice(ctx->device));
+  phovo_batch_state* b; int rc = get_state(ctx, &b);
+  if (rc) return rc;
+  int log_cap = 0;
+  if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
+  BatchParams bp; int nmax = 0;
+  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &nmax))) return rc;
+  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
+  return run_device(ctx, b, bp, nmax, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store,
+                    initial_states, states, iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
+}
+
+static bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                                 const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1,
+                                 const double* initial_states, double* states, int32_t* iterations) {
+  if (!ctx || !gray0 || !depth0 || !gray1) return PHOVO_E_INVALID;
+  if (depth_type < 0 || depth_type > 2) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
+  CK(cudaSetDevice(ctx->device));
+  phovo_batch_state* b; int rc = get_state(ctx, &b);
+  if (rc) return rc;
+  int log_cap = 0;
+  if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
+  BatchParams bp; int nmax = 0;
+  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &nmax))) return rc;
+  CK(ensure(&b->states, &b->states_cap, (size_t)num_pairs * 6));
+  CK(ensure(&b->iters, &b->iters_cap, (size_t)num_pairs * PHOVO_MAX_LEVELS));
+  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
+  const double* d_init = nullptr;
+  if (initial_states) {
+    CK(ensure(&b->init, &b->init_cap, (size_t)num_pairs * 6));
+    CK(cudaMemcpyAsync(b->init, initial_states, sizeof(double) * 6 * (size_t)num_pairs, cudaMemcpyDefault, ctx->stream));
+    d_init = b->init;
+  }
+  if (b->h_out_cap < (size_t)num_pairs) {
+    cudaFreeHost(b->h_states_pinned); cudaFreeHost(b->h_iters_pinned);
+    b->h_states_pinned = nullptr; b->h_iters_pinned = nullptr; b->h_out_cap = 0;
+    CK(cudaMallocHost((void**)&b->h_states_pinned, sizeof(double) * 6 * (size_t)num_pairs));
+    CK(cudaMallocHost((void**)&b->h_iters_pinned, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)num_pairs));
+    b->h_out_cap = num_pairs;
+  }
+  const bool on_device = is_device_pointer(gray0) && is_device_pointer(depth0) && is_device_pointer(gray1);
+  const size_t frame = (size_t)rows * cols, delt = depth_elt(depth_type);
+  if (on_device) {
+    rc = run_device(ctx, b, bp, nmax, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store, d_init,
+                    b->states, b->iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
+    if (rc) return rc;
+  } else {
+    // chunked, double-buffered upload: copies run on copy_stream, kernels on ctx->stream
+    // a chunk is four waves of persistent CTAs: large enough to amortise the ragged tail of a
+    // wave (pairs need different iteration counts), small enough to overlap with the next copy
+    const int chunk = std::max(1, std::min(num_pairs, 4 * b->sm_count));
+    for (int s = 0; s < 2; ++s) {
+      CK(ensure(&b->stage_g0[s], &b->stage_cap_g[s], frame * chunk));
+      CK(ensure(&b->stage_g1[s], &b->stage_cap_g1[s], frame * chunk));
+      CK(ensure(&b->stage_d[s], &b->stage_cap_d[s], frame * chunk * delt));
+    }
+    CK(cudaMemsetAsync(b->iters, 0, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)num_pairs, ctx->stream));
+    int slot = 0, used[2] = {0, 0};
+    for (int p0 = 0; p0 < num_pairs; p0 += chunk, slot ^= 1) {
+      const int np = std::min(chunk, num_pairs - p0);
+      if (used[slot]) CK(cudaStreamWaitEvent(b->copy_stream, b->ev_consumed[slot], 0));
+      CK(cudaMemcpyAsync(b->stage_g0[slot], gray0 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
+      CK(cudaMemcpyAsync(b->stage_g1[slot], gray1 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
+      CK(cudaMemcpyAsync(b->stage_d[slot], (const char*)depth0 + (size_t)p0 * frame * delt, frame * np * delt, cudaMemcpyHostToDevice, b->copy_stream));
+      CK(cudaEventRecord(b->ev_copied[slot], b->copy_stream));
+      CK(cudaStreamWaitEvent(ctx->stream, b->ev_copied[slot], 0));
+      BatchParams cp = bp;
+      cp.num_pairs = np;
+      rc = run_device(ctx, b, cp, nmax, ctx->stream, b->stage_g0[slot], b->stage_d[slot], depth_type, depth_scale, b->stage_g1[slot],
+                      b->store + (size_t)p0 * bp.record_bytes, d_init ? d_init + (size_t)p0 * 6 : nullptr,
+                      b->states + (size_t)p0 * 6, b->iters + (size_t)p0 * PHOVO_MAX_LEVELS,
+                      log_cap ? b->log + (size_t)p0 * log_cap : nullptr, log_cap ? b->log_counts + p0 : nullptr);
+      if (rc) return rc;
+      CK(cudaEventRecord(b->ev_consumed[slot], ctx->stream));
+      used[slot] = 1;
+    }
+  }
+  CK(cudaMemcpyAsync(b->h_states_pinned, b->states, sizeof(double) * 6 * (size_t)num_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(b->h_iters_pinned, b->iters, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)num_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (states) memcpy(states, b->h_states_pinned, sizeof(double) * 6 * (size_t)num_pairs);
+  if (iterations) memcpy(iterations, b->h_iters_pinned, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)num_pairs);
+  return PHOVO_OK;
+}
+
+static int fetch_log(const phovo_ctx* cctx) {
+  phovo_ctx* ctx = const_cast<phovo_ctx*>(cctx);
+  phovo_batch_state* b = ctx->batch;
+  if (!b || !b->log_per_pair) return PHOVO_E_INVALID;
+  if (b->log_fetched) return PHOVO_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  b->h_log.resize((size_t)b->last_pairs * b->log_per_pair);
+  b->h_log_counts.resize(b->last_pairs);
+  CK(cudaMemcpy(b->h_log.data(), b->log, sizeof(phovo_iter_stats) * b->h_log.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b->h_log_counts.data(), b->log_counts, sizeof(int32_t) * b->last_pairs, cudaMemcpyDeviceToHost));
+  b->log_fetched = true;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair) {
+  if (!ctx || !ctx->batch) return 0;
+  if (fetch_log(ctx) != PHOVO_OK) return 0;
+  if (pair < 0 || pair >= ctx->batch->last_pairs) return 0;
+  return std::min(ctx->batch->h_log_counts[pair], ctx->batch->log_per_pair);
+}
+
+extern "C" int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int index, phovo_iter_stats* out) {
+  if (!ctx || !out || !ctx->batch) return PHOVO_E_INVALID;
+  const int n = phovo_batch_num_iter_stats(ctx, pair);
+  if (index < 0 || index >= n) return PHOVO_E_INVALID;
+  *out = ctx->batch->h_log[(size_t)pair * ctx->batch->log_per_pair + index];
+  return PHOVO_OK;
+}

@@ -1,0 +1,47 @@
+// phovo_batch.h -- parameter block and launchers of the batched (one CTA per pair) path.
+#ifndef PHOVO_BATCH_H_
+#define PHOVO_BATCH_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phovo_internal.h"
+
+namespace phovo {
+
+constexpr int kBatchThreads = 384;          // 12 warps: 170 registers per thread, fp64 pipe saturated
+constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + scratch must fit 227 KB; also < 65535 (u16 winner)
+
+// Everything the two batch kernels need, passed by value (__grid_constant__).
+struct BatchParams {
+  int num_pairs, rows, cols;
+  int num_active;                       // active levels, coarse -> fine
+  int mode;
+  int log_cap;                          // per-pair stats slots (0: do not record)
+  int level[PHOVO_MAX_LEVELS];          // pyramid level index of active level a
+  int lrows[PHOVO_MAX_LEVELS], lcols[PHOVO_MAX_LEVELS];
+  int max_iters[PHOVO_MAX_LEVELS];
+  int px_offset[PHOVO_MAX_LEVELS + 1];  // prefix sum of level pixel counts (pyramid kernel indexing)
+  unsigned long long off_I0[PHOVO_MAX_LEVELS], off_I1[PHOVO_MAX_LEVELS], off_D0[PHOVO_MAX_LEVELS];
+  unsigned long long record_bytes;      // bytes of one pair's packed level record in HBM
+  double fx[PHOVO_MAX_LEVELS], fy[PHOVO_MAX_LEVELS], ox[PHOVO_MAX_LEVELS], oy[PHOVO_MAX_LEVELS];
+  double inv_fx[PHOVO_MAX_LEVELS], inv_fy[PHOVO_MAX_LEVELS];
+  double lambda[PHOVO_MAX_LEVELS], min_grad[PHOVO_MAX_LEVELS];
+  double grad_k[PHOVO_MAX_LEVELS];      // imageGradientsScalingFactor / 1020
+  double min_depth, max_depth;
+};
+
+// K1b: all active pyramid levels of I0, I1 (as exact u16 tap sums) and D0 (fp32) for every pair,
+// one pass over the full-resolution inputs.  depth_type: SRC_F64 / SRC_F32 / SRC_U16.
+int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8_t* gray0, const void* depth0,
+                         int depth_type, double depth_scale, const uint8_t* gray1, uint8_t* store);
+// K3-batch: persistent CTAs, one pair at a time per CTA, level images resident in shared memory,
+// whole coarse-to-fine Gauss-Newton loop on chip.
+int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
+                       const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log,
+                       int32_t* log_counts);
+size_t batch_align_smem_bytes(int max_level_pixels);
+cudaError_t batch_align_prepare(size_t smem_bytes);
+
+}  // namespace phovo
+#endif

@@ -217,6 +217,12 @@ class CPhotoconsistencyOdometryCuda:
                                                      None if initial_states is None else initial_states.data_ptr(),
                                                      states_out.data_ptr(), iters_out.data_ptr()))
 
+    def BatchKernelTimes(self):
+        """(pyramid_ms, align_ms) of the last BatchAlignDevice call, CUDA events on the context stream."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self._L.phovo_batch_get_kernel_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def BatchSetRecordStats(self, enable):
         self._check(self._L.phovo_batch_set_record_stats(self._h, int(enable)))
 

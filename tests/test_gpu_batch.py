@@ -1,0 +1,128 @@
+"""Batched persistent kernel (one CTA per pair, level images resident in shared memory) against
+the oracle and against the per-pair general path.  Needs a GPU."""
+import numpy as np
+import pytest
+
+from helpers import assert_logs_match, assert_pose_close
+from test_gpu_parity import conv_cfg, make_odo, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_batch(oracle, cfg, K, g0, d0, g1, threads=8):
+    st, it, _, _ = oracle.align_batch(conv_cfg(oracle, cfg), K, g0, d0.astype(np.float64), g1, num_threads=threads, lean=True)
+    return st, it
+
+
+@pytest.mark.parametrize("cfg_name,K_name,mode", [
+    ("config_4_level_optimization_analytic", "K_FRAME_ALIGNMENT", 0),      # BASELINE config 4 (small batch)
+    ("config_5_level_optimization_analytic", "K_VISUAL_ODOMETRY", 0),
+    ("config_4_level_optimization_analytic", "K_FRAME_ALIGNMENT", 1),
+])
+def test_batch_matches_oracle_640x480(phovo, oracle, cfg_name, K_name, mode):
+    K = getattr(phovo.synth, K_name)
+    P = 6
+    g0, d0, g1, xis = phovo.synth.make_batch(P, 480, 640, K=K, seed0=100)
+    cfg = phovo.configs.to_config(cfg_name, phovo.capi, mode=mode)
+    odo = make_odo(phovo, cfg, K)
+    odo.BatchSetRecordStats(True)
+    st, it = odo.BatchAlign(g0, d0.astype(np.float32), g1)
+    ost, oit = oracle_batch(oracle, cfg, K, g0, d0, g1)
+    assert np.array_equal(it, oit), (it, oit)           # executed iterations per level, every pair
+    for p in range(P):
+        assert_pose_close(st[p], ost[p], "pair %d" % p)
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+        o.set_source(g0[p], d0[p])
+        o.set_target(g1[p])
+        o.set_initial_state(np.zeros(6))
+        o.optimize()
+        assert_logs_match(odo.BatchIterationStats(p), o.iter_stats(), what="pair %d" % p)
+    # the per-pair general path gives the same answers (different summation order only)
+    for p in (0, P - 1):
+        s, log = run_gpu(odo, g0[p], d0[p], g1[p])
+        assert np.max(np.abs(s - st[p])) < 1e-10
+        assert len(log) == int(it[p].sum())
+    # f64 depth input and device-resident inputs give bitwise the same result
+    st64, it64 = odo.BatchAlign(g0, d0, g1)
+    assert np.array_equal(st64, st) and np.array_equal(it64, it)
+    import torch
+    tg0, td0, tg1 = (torch.from_numpy(a).cuda() for a in (g0, d0.astype(np.float32), g1))
+    stdev, itdev = odo.BatchAlign(tg0, td0, tg1)
+    assert np.array_equal(stdev, st) and np.array_equal(itdev, it)
+    out_s = torch.zeros((P, 6), dtype=torch.float64, device="cuda")
+    out_i = torch.zeros((P, phovo.MAXL), dtype=torch.int32, device="cuda")
+    odo.BatchAlignDevice(tg0, td0, tg1, out_s, out_i)
+    odo.Synchronize()
+    assert np.array_equal(out_s.cpu().numpy(), st) and np.array_equal(out_i.cpu().numpy(), it)
+
+
+def test_batch_is_order_and_grid_independent(phovo):
+    """Pair p's result does not depend on the batch it travels in (fixed thread->pixel mapping):
+    this is what makes 1-GPU and N-GPU sharded runs bitwise identical."""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    P = 5
+    g0, d0, g1, _ = phovo.synth.make_batch(P, 240, 320, K=K, seed0=200)
+    d0 = d0.astype(np.float32)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.num_levels = 3
+    for l, m in enumerate((0, 20, 50)):
+        cfg.max_num_iterations[l] = m
+    odo = make_odo(phovo, cfg, K)
+    st, it = odo.BatchAlign(g0, d0, g1)
+    perm = np.array([3, 0, 4, 1, 2])
+    st2, it2 = odo.BatchAlign(g0[perm], d0[perm], g1[perm])
+    assert np.array_equal(st2, st[perm]) and np.array_equal(it2, it[perm])
+    st3, it3 = odo.BatchAlign(g0[2:3], d0[2:3], g1[2:3])
+    assert np.array_equal(st3[0], st[2])
+    # initial states are honoured per pair
+    init = np.tile(np.array([1e-3, -1e-3, 2e-3, 1e-3, 0, -1e-3]), (P, 1))
+    st4, _ = odo.BatchAlign(g0, d0, g1, initial_states=init)
+    assert not np.array_equal(st4, st)
+
+
+def test_batch_odd_size_and_u16_depth(phovo, oracle):
+    K = np.array([[120., 0, 70.], [0, 118., 46.], [0, 0, 1]])
+    P = 3
+    g0, d0, g1, _ = phovo.synth.make_batch(P, 93, 141, K=K, seed0=300)
+    cfg = phovo.default_config()
+    cfg.num_levels = 3
+    for l, (m, thr) in enumerate(((0, 300.), (8, 100.), (12, 100.))):
+        cfg.max_num_iterations[l] = m
+        cfg.min_gradient_norm[l] = thr
+    odo = make_odo(phovo, cfg, K)
+    raw = np.clip(np.rint(d0 * 5000.), 0, 65535).astype(np.uint16)
+    st, it = odo.BatchAlign(g0, raw, g1, depth_scale=1. / 5000.)
+    ost, oit = oracle_batch(oracle, cfg, K, g0, raw.astype(np.float64) * (1. / 5000.), g1, threads=3)
+    assert np.array_equal(it, oit)
+    for p in range(P):
+        assert_pose_close(st[p], ost[p])
+
+
+def test_batch_unsupported_configurations_fail_loudly(phovo):
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)
+    d0 = d0.astype(np.float32)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.max_num_iterations[1] = 3          # level 1 = 240x320 = 76 800 px does not fit in shared memory
+    odo = make_odo(phovo, cfg, K)
+    with pytest.raises(phovo.PhovoError) as e:
+        odo.BatchAlign(g0, d0, g1)
+    assert e.value.code == phovo.capi.E_UNSUPPORTED
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    cfg.blur_filter_size[3] = 3
+    odo.SetConfig(cfg)
+    with pytest.raises(phovo.PhovoError) as e:
+        odo.BatchAlign(g0, d0, g1)
+    assert e.value.code == phovo.capi.E_UNSUPPORTED
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
+    odo.SetConfig(cfg)
+    with pytest.raises(phovo.PhovoError) as e:
+        odo.BatchAlign(g0, d0, g1)
+    assert e.value.code == phovo.capi.E_UNSUPPORTED
+    # all levels inactive: states pass through
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    for l in range(4):
+        cfg.max_num_iterations[l] = 0
+    odo.SetConfig(cfg)
+    st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((1, 6), 0.01))
+    assert np.array_equal(st, np.full((1, 6), 0.01)) and not it.any()
