@@ -160,7 +160,7 @@ void phovo_state_to_rt(const double state[6], double rt[16]);
 int phovo_num_iter_stats(const phovo_ctx* ctx);
 int phovo_get_iter_stats(const phovo_ctx* ctx, int index, phovo_iter_stats* out);
 /* which: 0 I0, 1 D0, 2 I1, 3 Gx1, 4 Gy1.  dst may be NULL to query the size. */
-int phovo_get_level_image(phovo_ctx* ctx, int which, int level, float* dst, int* rows, int* cols);
+int phovo_get_level_image(phovo_ctx* ctx, int which, int level, double* dst, int* rows, int* cols);
 /* Evaluate the normal equations once at `state` on `level` without stepping (fills H,g,cost,num_valid). */
 int phovo_eval_normal_equations(phovo_ctx* ctx, int level, const double state[6], phovo_iter_stats* out);
 /* Ceres-mode parity hook: residual vector (rows*cols doubles) and optional Jacobian

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kBlock) k_winner(LevelParams L, LevelPtrs P, c
   pose_load(pose, T);
   const int n = L.rows * L.cols;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    const double d = CERES && P.D0d ? __ldg(P.D0d + i) : (double)__ldg(P.D0 + i);
+    const double d = __ldg(P.D0 + i);
     const int r = i / L.cols, c = i - r * L.cols;
     Warped w;
     if (warp_pixel<CERES>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
@@ -70,10 +70,10 @@ __device__ __forceinline__ void linear_init_axis(double x, int size, int& x1, in
   else { x1 = ix; x2 = ix + 1; dx = (double)x2 - x; }
 }
 
-__device__ __forceinline__ double bilinear(const float* __restrict__ img, int cols, int y1, int y2, int x1, int x2, double dy, double dx) {
+__device__ __forceinline__ double bilinear(const double* __restrict__ img, int cols, int y1, int y2, int x1, int x2, double dy, double dx) {
   // third_party/sample.h:76-82
-  const double a = (double)__ldg(img + (size_t)y1 * cols + x1), b = (double)__ldg(img + (size_t)y1 * cols + x2);
-  const double c = (double)__ldg(img + (size_t)y2 * cols + x1), d = (double)__ldg(img + (size_t)y2 * cols + x2);
+  const double a = __ldg(img + (size_t)y1 * cols + x1), b = __ldg(img + (size_t)y1 * cols + x2);
+  const double c = __ldg(img + (size_t)y2 * cols + x1), d = __ldg(img + (size_t)y2 * cols + x2);
   return dy * (dx * a + (1.0 - dx) * b) + (1. - dy) * (dx * c + (1.0 - dx) * d);
 }
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
   const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
     const int r = i / L.cols, c = i - r * L.cols;
-    const double d = (MODE == 2 && P.D0d) ? __ldg(P.D0d + i) : (double)__ldg(P.D0 + i);
+    const double d = __ldg(P.D0 + i);
     Warped w;
     if (MODE == 2) {
       const bool ok = warp_pixel<true>(L, T, r, c, d, w);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
       const double s0 = bilinear(P.I1, L.cols, y1, y2, x1, x2, dy, dx);
       const double s1 = bilinear(P.Gx, L.cols, y1, y2, x1, x2, dy, dx);
       const double s2 = bilinear(P.Gy, L.cols, y1, y2, x1, x2, dy, dx);
-      const double res = s0 - (double)__ldg(P.I0 + i);
+      const double res = s0 - __ldg(P.I0 + i);
       double Ju[6], Jv[6], J[6];
       projection_jacobian<false>(L, T, w, d, Ju, Jv);
 #pragma unroll
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
       if (i < i_begin || i >= i_end) continue;
       double res = 0.;
       if (win >= 0) {
-        res = (double)__ldg(P.I1 + i) - (double)__ldg(P.I0 + win);
+        res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
         acc[27] = fma(res, res, acc[27]);
       }
       if (DUMP && dump_res) dump_res[i] = res;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
       if (!ok) continue;
       double Ju[6], Jv[6], J[6];
       projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
-      const double gx = (double)__ldg(P.Gx + i), gy = (double)__ldg(P.Gy + i);
+      const double gx = __ldg(P.Gx + i), gy = __ldg(P.Gy + i);
 #pragma unroll
       for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];   // AN:345-348
       accumulate_row(acc, J, res);

@@ -1,15 +1,22 @@
 // kernels_batch.cu -- the batched path (BASELINE config "N independent 640x480 pairs"):
 //
 //   K1b k_batch_pyramid : one streaming pass over the full-resolution inputs of every pair that
-//        writes, for each ACTIVE pyramid level only, I0 and I1 as exact 10-bit tap sums (u16,
-//        value = sum/1020) and D0 as fp32.  HBM-bound.  (AN:115-163 with blur 0.)
+//        writes, for each ACTIVE pyramid level only, I0 and I1 as EXACT 10-bit tap sums (u16,
+//        value = sum/1020) and D0 as fp64 (the reference's own double average).  HBM-bound.
+//        (AN:115-163 with blur 0.)
 //   K3-batch k_batch_align : persistent CTAs; a CTA takes one pair at a time, keeps the level's
-//        I0/I1/D0 + the 16-bit winner map resident in shared memory (10 B/px), recomputes the
-//        Scharr gradients from the resident I1 on the fly, and runs the complete coarse-to-fine
-//        Gauss-Newton loop (AN:500-563) without leaving the SM: no HBM traffic per iteration,
-//        no grid-wide synchronisation, no atomics on floating-point data.  The thread->pixel
-//        mapping is fixed, so results are bitwise reproducible and independent of which SM, CTA
-//        or GPU processes the pair.
+//        I0/I1 tap sums, the 16-bit winner map and the 16-bit target map resident in shared
+//        memory (8 B/px), streams D0 (fp64) from L2, recomputes the Scharr gradients exactly from
+//        the resident I1 sums (integer arithmetic), and runs the complete coarse-to-fine
+//        Gauss-Newton loop (AN:500-563) without leaving the SM: no grid-wide synchronisation, no
+//        atomics on floating-point data.  The thread->pixel mapping is fixed, so results are
+//        bitwise reproducible and independent of which SM, CTA or GPU processes the pair.
+//
+// Why exact storage: the residual scatter (AN:358) makes the cost piecewise constant in the
+// warp; when a level does not converge (it often runs to max_num_iterations) any 1e-7
+// perturbation (e.g. fp32 images) flips a rounding somewhere along the 50-iteration trajectory
+// and the final pose moves by >1e-4 in ~15% of pairs.  Integer tap sums + fp64 depth keep the
+// device within ~1e-15 of the reference's doubles, so trajectories stay together.
 #include "phovo_batch.h"
 #include "phovo_device.cuh"
 #include "phovo_kernels.h"
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
   uint8_t* rec = store + pair * bp.record_bytes;
   ((uint16_t*)(rec + bp.off_I0[a]))[q] = (uint16_t)s0;
   ((uint16_t*)(rec + bp.off_I1[a]))[q] = (uint16_t)s1;
-  ((float*)(rec + bp.off_D0[a]))[q] = (float)dv;
+  ((double*)(rec + bp.off_D0[a]))[q] = dv;
 }
 
 // 16-bit "max" into shared memory: 0 = empty, otherwise source index + 1.
@@ -93,15 +100,13 @@ __device__ __forceinline__ void smem_max_u16(unsigned short* addr, unsigned shor
 }
 
 struct BatchShared {
-  double state[6];
-  PoseDev pose;          // only the rotation / trig fields are used
+  PoseDev pose;          // state + rotation / trig of the current iterate
   double totals[32];
   int done;
   int iteration;
 };
 
-// The intensity the general path would have stored: fp32(sum/1020) widened to double.
-__device__ __forceinline__ double intensity(unsigned short s) { return (double)__double2float_rn((double)s * (1.0 / 1020.0)); }
+constexpr unsigned short kNoTarget = 0xFFFFu;
 
 template <int MODE>
 __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ BatchParams bp, const uint8_t* __restrict__ store,
@@ -109,12 +114,12 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
                                                        int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
                                                        int32_t* __restrict__ log_counts, int nmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: D0 f32[nmax] | I0 u16[nmax] | I1 u16[nmax] | win u16[nmax] | reduction scratch | BatchShared
-  float* sD0 = (float*)smem_raw;
-  unsigned short* sI0 = (unsigned short*)(sD0 + nmax);
+  // layout: I0 u16[nmax] | I1 u16[nmax] | win u16[nmax] | tgt u16[nmax] | reduction scratch | BatchShared
+  unsigned short* sI0 = (unsigned short*)smem_raw;
   unsigned short* sI1 = sI0 + nmax;
   unsigned short* sWin = sI1 + nmax;
-  double* sRed = (double*)(((uintptr_t)(sWin + nmax) + 15) & ~(uintptr_t)15);
+  unsigned short* sTgt = sWin + nmax;
+  double* sRed = (double*)(sTgt + nmax);
   BatchShared* sh = (BatchShared*)(sRed + (BT / 32) * PHOVO_ACC_STRIDE);
   const int tid = threadIdx.x;
 
@@ -132,15 +137,14 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
     const uint8_t* rec = store + (size_t)pair * bp.record_bytes;
     for (int a = 0; a < bp.num_active; ++a) {
       const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
+      const double* __restrict__ gD0 = (const double*)(rec + bp.off_D0[a]);
       __syncthreads();   // previous level / pair fully consumed before the buffers are overwritten
       {
         // HBM -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
-        const uint4* gD = (const uint4*)(rec + bp.off_D0[a]);
         const uint4* gI0 = (const uint4*)(rec + bp.off_I0[a]);
         const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
-        uint4* d4 = (uint4*)sD0; uint4* i04 = (uint4*)sI0; uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
-        const int nd = (n * 4 + 15) / 16, ni = (n * 2 + 15) / 16;
-        for (int k = tid; k < nd; k += BT) d4[k] = __ldg(gD + k);
+        uint4* i04 = (uint4*)sI0; uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
+        const int ni = (n * 2 + 15) / 16;
         for (int k = tid; k < ni; k += BT) { i04[k] = __ldg(gI0 + k); i14[k] = __ldg(gI1 + k); w4[k] = make_uint4(0, 0, 0, 0); }
       }
       if (tid == 0) { sh->done = 0; sh->iteration = 0; }
@@ -151,47 +155,77 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
       L.min_depth = bp.min_depth; L.max_depth = bp.max_depth; L.rows = rows; L.cols = cols;
       L.lambda = bp.lambda[a]; L.min_grad_norm = bp.min_grad[a]; L.max_iters = bp.max_iters[a]; L.level = bp.level[a];
       const double gk = bp.grad_k[a];
+      // pixel i = tid + k*BT: (r, c) advance by a fixed (dr, dc) per step -- no division in the loops
+      const int r_first = tid / cols, c_first = tid - r_first * cols;
+      const int dr = BT / cols, dc = BT - dr * cols;
 
       for (int it = 0; it < L.max_iters; ++it) {
         Pose T;
         pose_load(&sh->pose, T);
-        // ---- phase A: winner map (AN:358 last-writer-wins == max source index) ----
+        // ---- phase A1: warp every source pixel; record its target slot; plain (racy) store of
+        //      the candidate winner -- colliding writers are resolved in A2 ----
+        {
+          int r = r_first, c = c_first;
+          for (int i = tid; i < n; i += BT) {
+            Warped w;
+            unsigned short t = kNoTarget;
+            if (warp_pixel<false>(L, T, r, c, __ldg(gD0 + i), w)) { t = (unsigned short)w.t; sWin[w.t] = (unsigned short)(i + 1); }
+            sTgt[i] = t;
+            c += dc; r += dr;
+            if (c >= cols) { c -= cols; ++r; }
+          }
+        }
+        __syncthreads();
+        // ---- phase A2: a source that should have won its slot but lost the store race fixes it
+        //      (AN:358 last-writer-wins in raster order == largest source index); ~1% of pixels ----
         for (int i = tid; i < n; i += BT) {
-          const int r = i / cols, c = i - r * cols;
-          Warped w;
-          if (warp_pixel<false>(L, T, r, c, (double)sD0[i], w)) smem_max_u16(sWin + w.t, (unsigned short)(i + 1));
+          const unsigned short t = sTgt[i];
+          if (t != kNoTarget && sWin[t] < (unsigned short)(i + 1)) smem_max_u16(sWin + t, (unsigned short)(i + 1));
         }
         __syncthreads();
         // ---- phase B: residual + Jacobian + normal equations (AN:271-366, 538-539) ----
         double acc[PHOVO_NACC];
 #pragma unroll
         for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
-        for (int i = tid; i < n; i += BT) {
-          const int r = i / cols, c = i - r * cols;
-          const unsigned short win = sWin[i];
-          sWin[i] = 0;
-          double res = 0.;
-          if (win) {
-            res = intensity(sI1[i]) - intensity(sI0[win - 1]);
-            acc[27] = fma(res, res, acc[27]);
-          }
-          Warped w;
-          const double d = (double)sD0[i];
-          if (!warp_pixel<false>(L, T, r, c, d, w)) continue;
-          // Scharr of I1 at the SOURCE index (AN:346-347), reflect-101, from the resident tap sums
-          const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
-          const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
-          const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
-          const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
-          const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
-          const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
-          const double gx = (double)__double2float_rn((double)gxn * gk), gy = (double)__double2float_rn((double)gyn * gk);
-          double Ju[6], Jv[6], J[6];
-          projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
+        {
+          int r = r_first, c = c_first;
+          for (int i = tid; i < n; i += BT) {
+            const unsigned short win = sWin[i];
+            sWin[i] = 0;
+            double res = 0.;
+            if (win) {
+              // I = sum/1020: one rounding, within 2 ulp of the reference's convertTo + resize doubles
+              res = (double)((int)sI1[i] - (int)sI0[win - 1]) * (1.0 / 1020.0);
+              acc[27] = fma(res, res, acc[27]);
+            }
+            if (sTgt[i] != kNoTarget) {
+              const double d = __ldg(gD0 + i);
+              Warped w;
+              w.px = __dmul_rn(__dmul_rn(__dsub_rn((double)c, L.ox), d), L.inv_fx);
+              w.py = __dmul_rn(__dmul_rn(__dsub_rn((double)r, L.oy), d), L.inv_fy);
+              w.q0 = __dadd_rn(__dadd_rn(__dmul_rn(T.R00, w.px), __dmul_rn(T.R01, w.py)), __dmul_rn(T.R02, d));
+              w.q1 = __dadd_rn(__dadd_rn(__dmul_rn(T.R10, w.px), __dmul_rn(T.R11, w.py)), __dmul_rn(T.R12, d));
+              w.q2 = __dadd_rn(__dadd_rn(__dmul_rn(T.R20, w.px), __dmul_rn(T.R21, w.py)), __dmul_rn(T.R22, d));
+              w.X = __dadd_rn(w.q0, T.x); w.Y = __dadd_rn(w.q1, T.y); w.Z = __dadd_rn(w.q2, T.z);
+              w.iz = __ddiv_rn(1.0, w.Z);
+              // Scharr of I1 at the SOURCE index (AN:346-347), reflect-101, exact integer numerators
+              const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
+              const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
+              const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
+              const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
+              const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
+              const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
+              const double gx = (double)gxn * gk, gy = (double)gyn * gk;
+              double Ju[6], Jv[6], J[6];
+              projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];
-          accumulate_row(acc, J, res);
-          acc[28] += 1.;
+              for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];
+              accumulate_row(acc, J, res);
+              acc[28] += 1.;
+            }
+            c += dc; r += dr;
+            if (c >= cols) { c -= cols; ++r; }
+          }
         }
         const double total = block_reduce<BT>(acc, sRed);
         if (tid < PHOVO_NACC) sh->totals[tid] = total;
@@ -235,7 +269,7 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
 
 size_t batch_align_smem_bytes(int nmax) {
   nmax = (nmax + 7) & ~7;
-  return (size_t)nmax * 10 + 16 + (size_t)(BT / 32) * PHOVO_ACC_STRIDE * sizeof(double) + sizeof(BatchShared) + 64;
+  return (size_t)nmax * 8 + (size_t)(BT / 32) * PHOVO_ACC_STRIDE * sizeof(double) + sizeof(BatchShared) + 64;
 }
 
 cudaError_t batch_align_prepare(size_t smem_bytes) {

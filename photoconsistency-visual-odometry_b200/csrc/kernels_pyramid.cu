@@ -1,5 +1,6 @@
 // kernels_pyramid.cu -- frame setup for the general (any resolution, any config) path:
-// K1 pyramid level from the full-resolution source, K2b Gaussian blur, K2 Scharr + fp32 store.
+// K1 pyramid level from the full-resolution source, K2b Gaussian blur, K2 Scharr.  All level images are fp64, bit-identical
+// to the reference's cv::Mat_<double> pyramids (same operation order, no FMA contraction).
 // Replaces CPhotoconsistencyOdometryAnalytic.h:115-189 (BuildPyramid / BuildDerivativesPyramids).
 // The batched path has its own fused, shared-memory version (kernels_batch.cu).
 #include <math.h>
@@ -101,21 +102,15 @@ __global__ void __launch_bounds__(256) k_gauss_cols(const double* __restrict__ s
   dst[(size_t)r * cols + c] = s;
 }
 
-__global__ void __launch_bounds__(256) k_store_f32(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = (float)src[i];
-}
-
 // K2: Scharr in x and y with cv::Scharr's separable evaluation order (derivative kernel [-1 0 1],
-// smoothing kernel [3 10 3]*scale) + the fp32 store of the image itself.  32x8 tiles with a
+// smoothing kernel [3 10 3]*scale).  32x8 tiles with a
 // 1-pixel halo staged in shared memory so every level pixel is read from global memory once
 // (plus halo), then 18 shared-memory reads per pixel.
 #define SCH_TW 32
 #define SCH_TH 8
 __global__ void __launch_bounds__(SCH_TW * SCH_TH) k_scharr_store(const double* __restrict__ img, int rows, int cols,
                                                                    double ks0, double ks1,
-                                                                   float* __restrict__ I, float* __restrict__ Gx, float* __restrict__ Gy) {
+                                                                   double* __restrict__ Gx, double* __restrict__ Gy) {
   __shared__ double tile[SCH_TH + 2][SCH_TW + 2];
   const int x0 = blockIdx.x * SCH_TW, y0 = blockIdx.y * SCH_TH;
   for (int i = threadIdx.y * SCH_TW + threadIdx.x; i < (SCH_TH + 2) * (SCH_TW + 2); i += SCH_TW * SCH_TH) {
@@ -137,9 +132,9 @@ __global__ void __launch_bounds__(SCH_TW * SCH_TH) k_scharr_store(const double* 
   const double sp = __dadd_rn(__dadd_rn(__dmul_rn(ks0, tile[ty + 1][tx - 1]), __dmul_rn(ks1, tile[ty + 1][tx])), __dmul_rn(ks0, tile[ty + 1][tx + 1]));
   const double gy = __dsub_rn(sp, sm);
   const size_t o = (size_t)y * cols + x;
-  I[o] = (float)tile[ty][tx];
-  Gx[o] = (float)gx;
-  Gy[o] = (float)gy;
+
+  Gx[o] = gx;
+  Gy[o] = gy;
 }
 
 }  // namespace
@@ -173,18 +168,12 @@ int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows
   return 2;
 }
 
-int launch_store_f32(cudaStream_t stream, const double* src, float* dst, size_t n) {
-  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  k_store_f32<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(src, dst, n);
-  return 1;
-}
-
 int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
-                        float* I, float* Gx, float* Gy) {
+                        double* Gx, double* Gy) {
   double ks0 = 3., ks1 = 10.;
   if (scale != 1.) { ks0 *= scale; ks1 *= scale; }
   dim3 block(SCH_TW, SCH_TH), grid((cols + SCH_TW - 1) / SCH_TW, (rows + SCH_TH - 1) / SCH_TH);
-  k_scharr_store<<<grid, block, 0, stream>>>(img, rows, cols, ks0, ks1, I, Gx, Gy);
+  k_scharr_store<<<grid, block, 0, stream>>>(img, rows, cols, ks0, ks1, Gx, Gy);
   return 1;
 }
 

@@ -68,7 +68,6 @@ LevelPtrs phovo_ctx::level_ptrs(int level) const {
   LevelPtrs P;
   P.I0 = I0[level]; P.D0 = D0[level]; P.I1 = I1[level]; P.Gx = Gx[level]; P.Gy = Gy[level];
   P.winner = winner;
-  P.D0d = cfg.mode == PHOVO_MODE_CERES ? D0d[level] : nullptr;
   return P;
 }
 
@@ -112,15 +111,14 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
     if (!ctx->level_active(l)) continue;
     const size_t n = (size_t)ctx->lrows[l] * ctx->lcols[l];
     if (n > max_px) max_px = n;
-    float** arrs[5] = {&ctx->I0[l], &ctx->D0[l], &ctx->I1[l], &ctx->Gx[l], &ctx->Gy[l]};
+    double** arrs[5] = {&ctx->I0[l], &ctx->D0[l], &ctx->I1[l], &ctx->Gx[l], &ctx->Gy[l]};
     for (int a = 0; a < 5; ++a) {
       size_t cap = ctx->lcap[l][a];
-      float* before = *arrs[a];
+      double* before = *arrs[a];
       CK(ensure(arrs[a], &cap, n));
       ctx->lcap[l][a] = cap;
       if (before != *arrs[a]) changed = true;
     }
-    if (ctx->cfg.mode == PHOVO_MODE_CERES) CK(ensure(&ctx->D0d[l], &ctx->d0d_cap[l], n));
   }
   if (max_px == 0) max_px = 1;
   {
@@ -184,14 +182,14 @@ static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bo
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
     const int r = ctx->lrows[l], c = ctx->lcols[l];
-    ctx->launches += launch_build_level(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, l, ctx->scratch64[0], r, c);
+    double* img = target ? ctx->I1[l] : ctx->I0[l];
+    ctx->launches += launch_build_level(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, l, img, r, c);
     const int k = ctx->cfg.blur_filter_size[l];
     if (k > 1) {  // AN:144-148: GaussianBlur(k, sigma 3) twice
-      ctx->launches += launch_gaussian_blur(ctx->stream, ctx->scratch64[0], ctx->scratch64[1], r, c, k, 3.);
-      ctx->launches += launch_gaussian_blur(ctx->stream, ctx->scratch64[0], ctx->scratch64[1], r, c, k, 3.);
+      ctx->launches += launch_gaussian_blur(ctx->stream, img, ctx->scratch64[0], r, c, k, 3.);
+      ctx->launches += launch_gaussian_blur(ctx->stream, img, ctx->scratch64[0], r, c, k, 3.);
     }
-    if (target) ctx->launches += launch_scharr_store(ctx->stream, ctx->scratch64[0], r, c, ctx->cfg.grad_scale[l], ctx->I1[l], ctx->Gx[l], ctx->Gy[l]);
-    else ctx->launches += launch_store_f32(ctx->stream, ctx->scratch64[0], ctx->I0[l], (size_t)r * c);
+    if (target) ctx->launches += launch_scharr_store(ctx->stream, img, r, c, ctx->cfg.grad_scale[l], ctx->Gx[l], ctx->Gy[l]);
   }
   CK(cudaGetLastError());
   return PHOVO_OK;
@@ -201,10 +199,7 @@ static int build_depth(phovo_ctx* ctx, const void* dev_depth, int depth_type, si
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
     const int r = ctx->lrows[l], c = ctx->lcols[l];
-    ctx->launches += launch_build_level(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, l, ctx->scratch64[0], r, c);
-    ctx->launches += launch_store_f32(ctx->stream, ctx->scratch64[0], ctx->D0[l], (size_t)r * c);
-    if (ctx->cfg.mode == PHOVO_MODE_CERES)
-      CK(cudaMemcpyAsync(ctx->D0d[l], ctx->scratch64[0], sizeof(double) * (size_t)r * c, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += launch_build_level(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, l, ctx->D0[l], r, c);
   }
   CK(cudaGetLastError());
   return PHOVO_OK;
@@ -268,7 +263,6 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   ctx->invalidate_graph();
   phovo_batch_release(ctx);
   for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
-    cudaFree(ctx->D0d[l]);
     cudaFree(ctx->I0[l]); cudaFree(ctx->D0[l]); cudaFree(ctx->I1[l]); cudaFree(ctx->Gx[l]); cudaFree(ctx->Gy[l]);
   }
   cudaFree(ctx->winner); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
@@ -343,8 +337,6 @@ extern "C" int phovo_load_config_yaml(phovo_ctx* ctx, const char* path) {
 extern "C" int phovo_set_mode(phovo_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return PHOVO_E_INVALID;
   if (ctx->cfg.mode != mode) {
-    // Ceres mode keeps an fp64 copy of the depth pyramid: frames must be set again after a switch
-    if (ctx->cfg.mode == PHOVO_MODE_CERES || mode == PHOVO_MODE_CERES) ctx->have_src = ctx->have_tgt = false;
     ctx->cfg.mode = mode;
     ctx->invalidate_graph();
   }
@@ -440,7 +432,7 @@ extern "C" int phovo_promote_target_to_source(phovo_ctx* ctx, const void* depth,
   // (same convert + resize + blur, AN:471-474 vs AN:484-487): swap the level buffers.
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
-    float* t = ctx->I0[l]; ctx->I0[l] = ctx->I1[l]; ctx->I1[l] = t;
+    double* t = ctx->I0[l]; ctx->I0[l] = ctx->I1[l]; ctx->I1[l] = t;
     size_t c = ctx->lcap[l][0]; ctx->lcap[l][0] = ctx->lcap[l][2]; ctx->lcap[l][2] = c;
   }
   ctx->invalidate_graph();
@@ -690,7 +682,7 @@ extern "C" int phovo_get_iter_stats(const phovo_ctx* ctx, int index, phovo_iter_
   return PHOVO_OK;
 }
 
-extern "C" int phovo_get_level_image(phovo_ctx* ctx, int which, int level, float* dst, int* rows, int* cols) {
+extern "C" int phovo_get_level_image(phovo_ctx* ctx, int which, int level, double* dst, int* rows, int* cols) {
   if (!ctx || which < 0 || which > 4 || level < 0 || level >= ctx->cfg.num_levels) return PHOVO_E_INVALID;
   if (!ctx->level_active(level)) return ctx->fail(PHOVO_E_INVALID, "level was not built (no iterations configured; see phovo_set_build_all_levels)");
   if ((which <= 1 && !ctx->have_src) || (which >= 2 && !ctx->have_tgt)) return ctx->fail(PHOVO_E_INVALID, "frame not set");
@@ -698,8 +690,8 @@ extern "C" int phovo_get_level_image(phovo_ctx* ctx, int which, int level, float
   if (cols) *cols = ctx->lcols[level];
   if (!dst) return PHOVO_OK;
   CK(cudaSetDevice(ctx->device));
-  const float* src = which == 0 ? ctx->I0[level] : which == 1 ? ctx->D0[level] : which == 2 ? ctx->I1[level] : which == 3 ? ctx->Gx[level] : ctx->Gy[level];
-  CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)ctx->lrows[level] * ctx->lcols[level], cudaMemcpyDeviceToHost, ctx->stream));
+  const double* src = which == 0 ? ctx->I0[level] : which == 1 ? ctx->D0[level] : which == 2 ? ctx->I1[level] : which == 3 ? ctx->Gx[level] : ctx->Gy[level];
+  CK(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)ctx->lrows[level] * ctx->lcols[level], cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PHOVO_OK;
 }

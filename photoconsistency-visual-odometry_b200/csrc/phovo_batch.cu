@@ -2,7 +2,7 @@
 //
 // HBM layout: inputs stay in the caller's layout ([P][rows][cols] u8 / depth); the pyramid kernel
 // writes one packed record per pair holding, for each ACTIVE level, I0 and I1 as u16 tap sums and
-// D0 as fp32 (8 B/px; 192 000 B per 640x480 pair under the 4-level config).  The align kernel
+// D0 as fp64 (12 B/px; 288 000 B per 640x480 pair under the 4-level config).  The align kernel
 // reads each record exactly once.  Host inputs are streamed in chunks through two device staging
 // slots on two streams so that the PCIe copy of chunk k+1 overlaps the kernels of chunk k.
 #include <math.h>
@@ -115,13 +115,13 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     level_size(rows, cols, level, &lr, &lc);
     if (lr < 1 || lc < 1) return ctx->fail(PHOVO_E_INVALID, "image too small for the number of pyramid levels");
     const int n = lr * lc;
-    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
+    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (28160 px); use the per-pair API");
     nmax = std::max(nmax, n);
     bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
     bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
     bp->px_offset[a + 1] = bp->px_offset[a] + n;
-    const unsigned long long n16 = ((unsigned long long)n * 2 + 15) & ~15ull, n32 = ((unsigned long long)n * 4 + 15) & ~15ull;
-    bp->off_D0[a] = off; off += n32;
+    const unsigned long long n16 = ((unsigned long long)n * 2 + 15) & ~15ull, n64 = ((unsigned long long)n * 8 + 15) & ~15ull;
+    bp->off_D0[a] = off; off += n64;
     bp->off_I0[a] = off; off += n16;
     bp->off_I1[a] = off; off += n16;
     // CPhotoconsistencyOdometryAnalytic.h:203-209

@@ -10,7 +10,7 @@
 namespace phovo {
 
 constexpr int kBatchThreads = 384;          // 12 warps: 170 registers per thread, fp64 pipe saturated
-constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + scratch must fit 227 KB; also < 65535 (u16 winner)
+constexpr int kBatchMaxLevelPixels = 28160; // 8 B/px of shared memory + scratch must fit 227 KB; also < 65535 (u16 maps)
 
 // Everything the two batch kernels need, passed by value (__grid_constant__).
 struct BatchParams {
@@ -31,7 +31,7 @@ struct BatchParams {
   double min_depth, max_depth;
 };
 
-// K1b: all active pyramid levels of I0, I1 (as exact u16 tap sums) and D0 (fp32) for every pair,
+// K1b: all active pyramid levels of I0, I1 (as exact u16 tap sums) and D0 (fp64) for every pair,
 // one pass over the full-resolution inputs.  depth_type: SRC_F64 / SRC_F32 / SRC_U16.
 int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8_t* gray0, const void* depth0,
                          int depth_type, double depth_scale, const uint8_t* gray1, uint8_t* store);

@@ -28,13 +28,13 @@ struct phovo_ctx {
   int rows = 0, cols = 0;
   int lrows[PHOVO_MAX_LEVELS] = {0}, lcols[PHOVO_MAX_LEVELS] = {0};
 
-  // HBM layout (general path): per active level five dense row-major fp32 images
-  float* I0[PHOVO_MAX_LEVELS] = {nullptr};
-  float* D0[PHOVO_MAX_LEVELS] = {nullptr};
-  float* I1[PHOVO_MAX_LEVELS] = {nullptr};
-  float* Gx[PHOVO_MAX_LEVELS] = {nullptr};
-  float* Gy[PHOVO_MAX_LEVELS] = {nullptr};
-  double* D0d[PHOVO_MAX_LEVELS] = {nullptr}; size_t d0d_cap[PHOVO_MAX_LEVELS] = {0};  // Ceres mode only
+  // HBM layout (general path): per active level five dense row-major fp64 images -- bit-identical to the
+  // reference's cv::Mat_<double> levels (fp32 storage makes ~15% of trajectories diverge)
+  double* I0[PHOVO_MAX_LEVELS] = {nullptr};
+  double* D0[PHOVO_MAX_LEVELS] = {nullptr};
+  double* I1[PHOVO_MAX_LEVELS] = {nullptr};
+  double* Gx[PHOVO_MAX_LEVELS] = {nullptr};
+  double* Gy[PHOVO_MAX_LEVELS] = {nullptr};
   size_t lcap[PHOVO_MAX_LEVELS][5] = {{0}};
   int* winner = nullptr; size_t winner_cap = 0;           // one int per pixel of the largest active level
   double* scratch64[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};

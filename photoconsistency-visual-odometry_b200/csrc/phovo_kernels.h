@@ -21,19 +21,14 @@ int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_
                        double src_scale, int rows, int cols, int level, double* dst, int orows, int ocols);
 // K2b: cv::GaussianBlur(k x k, sigma) applied once, BORDER_REFLECT_101, fp64 in place via `tmp`.
 int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows, int cols, int ksize, double sigma);
-// fp64 scratch -> fp32 level storage
-int launch_store_f32(cudaStream_t stream, const double* src, float* dst, size_t n);
-// K2: Scharr x/y (AN:181-187) from the fp64 level image + fp32 store of I1, Gx, Gy in one pass.
+// K2: Scharr x/y (AN:181-187) from the fp64 level image, same evaluation order as cv::Scharr.
 int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
-                        float* I, float* Gx, float* Gy);
+                        double* Gx, double* Gy);
 
 // ---- alignment (kernels_align.cu) ------------------------------------------------------------
 struct LevelPtrs {
-  const float* I0; const float* D0; const float* I1; const float* Gx; const float* Gy;
+  const double* I0; const double* D0; const double* I1; const double* Gx; const double* Gy;
   int* winner;        // rows*cols ints, all -1 between iterations
-  const double* D0d;  // fp64 depth level (Ceres mode only, else null): the truncation scatter of
-                      // CE:250-251 sits on integer boundaries at the identity state, so fp32 depth
-                      // rounding would flip slots there
 };
 
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);

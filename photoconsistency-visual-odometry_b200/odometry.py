@@ -159,7 +159,7 @@ class CPhotoconsistencyOdometryCuda:
     def LevelImage(self, which, level):
         r, c = C.c_int32(), C.c_int32()
         self._check(self._L.phovo_get_level_image(self._h, which, level, None, C.byref(r), C.byref(c)))
-        out = np.zeros((r.value, c.value), dtype=np.float32)
+        out = np.zeros((r.value, c.value), dtype=np.float64)
         self._check(self._L.phovo_get_level_image(self._h, which, level, out.ctypes.data, C.byref(r), C.byref(c)))
         return out
 
