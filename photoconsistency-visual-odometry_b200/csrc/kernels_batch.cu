@@ -4,13 +4,13 @@
 //        writes, for each ACTIVE pyramid level only, I0 and I1 as EXACT 10-bit tap sums (u16,
 //        value = sum/1020) and D0 as fp64 (the reference's own double average).  HBM-bound.
 //        (AN:115-163 with blur 0.)
-//   K3-batch k_batch_align : persistent CTAs; a CTA takes one pair at a time, keeps the level's
-//        I0/I1 tap sums, the 16-bit winner map and the 16-bit target map resident in shared
-//        memory (8 B/px), streams D0 (fp64) from L2, recomputes the Scharr gradients exactly from
-//        the resident I1 sums (integer arithmetic), and runs the complete coarse-to-fine
-//        Gauss-Newton loop (AN:500-563) without leaving the SM: no grid-wide synchronisation, no
-//        atomics on floating-point data.  The thread->pixel mapping is fixed, so results are
-//        bitwise reproducible and independent of which SM, CTA or GPU processes the pair.
+//   K3-batch k_batch_align : persistent CTAs; a CTA takes one pair at a time and runs the complete
+//        coarse-to-fine Gauss-Newton loop (AN:500-563) without leaving the SM: winner words,
+//        Scharr numerators and I1 resident in shared memory (10 B/px), D0 / I0 streamed from the
+//        pair's record in L2, warp-transposed fixed-order reduction, the 6x6 solve in one warp.
+//        No grid-wide synchronisation, no atomics on floating-point data; the thread->pixel
+//        mapping is fixed, so results are bitwise reproducible and independent of which SM, CTA
+//        or GPU processes the pair.
 //
 // Why exact storage: the residual scatter (AN:358) makes the cost piecewise constant in the
 // warp; when a level does not converge (it often runs to max_num_iterations) any 1e-7
@@ -89,175 +89,341 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
   ((double*)(rec + bp.off_D0[a]))[q] = dv;
 }
 
-// 16-bit "max" into shared memory: 0 = empty, otherwise source index + 1.
-__device__ __forceinline__ void smem_max_u16(unsigned short* addr, unsigned short v) {
-  unsigned short old = *addr;
-  while (v > old) {
-    const unsigned short prev = atomicCAS(addr, old, v);
-    if (prev == old) break;
-    old = prev;
-  }
-}
+// ---------------------------------------------------------------------------------------------
+// K3-batch building blocks
+// ---------------------------------------------------------------------------------------------
+constexpr int NW = BT / 32;
+static_assert(kBatchMaxLevelPixels <= 64 * BT, "per-thread validity mask is 64 bits");
+static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 in 16 bits");
 
 struct BatchShared {
   PoseDev pose;          // state + rotation / trig of the current iterate
   double totals[32];
   int done;
   int iteration;
+  int pair;
+  int pad;
 };
 
-constexpr unsigned short kNoTarget = 0xFFFFu;
+// MUFU.RCP64H seed: 1/x to ~20 bits, low word zero.
+__device__ __forceinline__ double rcp_seed(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+// Correctly rounded 1/x for x in the normal range: the fast path nvcc itself emits for `1.0 / x`
+// (seed, two Newton steps folded into three FMAs, one residual correction), without the
+// exponent-range test and slow-path call -- the caller guarantees 1e-300 < |x| < 1e300.
+__device__ __forceinline__ double rcp_rn_normal(double x) {
+  const double r0 = rcp_seed(x);
+  double e = fma(-x, r0, 1.0);
+  e = fma(e, e, e);
+  const double r1 = fma(r0, e, r0);
+  const double e2 = fma(-x, r1, 1.0);
+  return fma(r1, e2, r1);
+}
+// 1/x to about one ulp (relative error ~ seed_error^3 = 2^-60 before rounding): Jacobian use only.
+__device__ __forceinline__ double rcp_1ulp(double x) {
+  const double r0 = rcp_seed(x);
+  double e = fma(-x, r0, 1.0);
+  e = fma(e, e, e);
+  return fma(r0, e, r0);
+}
 
+// Sum 32 values across the 32 lanes of a warp with 31 shuffle-adds (recursive halving): on return
+// lane L holds, in x[0], the warp-wide sum of the callers' x[L].  The order of the additions is a
+// pure function of the lane index, so the result is bitwise reproducible.
+__device__ __forceinline__ double warp_transpose_sum(double (&x)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const double send = up ? x[j] : x[j + o];
+      const double keep = up ? x[j + o] : x[j];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return x[0];
+}
+
+// Gauss-Newton step in ONE warp (AN:538-549 + AN:376-392).  Lane L enters with total[L]
+// ([0..20] upper triangle of J^T J, [21..26] J^T r, [27] sum r^2, [28] count).  Rows of the 6x6
+// system live in lanes 0..5; the symmetric positive definite system is eliminated without
+// pivoting (LDL^T, i.e. the Cholesky solve the north star asks for; the reference's
+// Eigen inverse() is a pivoted LU -- same solution to ~cond*2^-53) with one reciprocal per
+// pivot; substitution is column oriented so the dependent chain is 6 x (shuffle + fma).
+// Then state update, sincos on three lanes, rotation, termination flag.  Lane 0 publishes.
+__device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchParams& bp, int a, int it, int pair,
+                                             BatchShared* sh, phovo_iter_stats* log) {
+  const unsigned FULL = 0xffffffffu;
+  sh->totals[lane] = tot;
+  const int row = lane < 6 ? lane : 5;
+  double A[6], g;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int lo = row < j ? row : j, hi = row < j ? j : row;
+    A[j] = __shfl_sync(FULL, tot, lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo));
+  }
+  g = __shfl_sync(FULL, tot, 21 + row);
+  double n2 = 0.;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const double gk = __shfl_sync(FULL, tot, 21 + k); n2 = fma(gk, gk, n2); }
+  double rinv[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double pk = __shfl_sync(FULL, A[k], k);
+    double prow[6];
+#pragma unroll
+    for (int j = k + 1; j < 6; ++j) prow[j] = __shfl_sync(FULL, A[j], k);
+    const double pg = __shfl_sync(FULL, g, k);
+    rinv[k] = 1.0 / pk;
+    if (lane > k) {
+      const double m = A[k] * rinv[k];
+#pragma unroll
+      for (int j = k + 1; j < 6; ++j) A[j] = fma(-m, prow[j], A[j]);
+      g = fma(-m, pg, g);
+    }
+  }
+  double x[6];
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+    x[k] = __shfl_sync(FULL, g, k) * rinv[k];
+    if (lane < k) g = fma(-A[k], x[k], g);
+  }
+  const double lambda = bp.lambda[a];
+  double s_in[6], s_out[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { s_in[k] = sh->pose.state[k]; s_out[k] = s_in[k] - lambda * x[k]; }   // AN:539-540
+  const int which = lane % 3;
+  const double ang = which == 0 ? s_out[3] : which == 1 ? s_out[4] : s_out[5];
+  double sn, cs;
+  sincos(ang, &sn, &cs);
+  Pose P;
+  P.x = s_out[0]; P.y = s_out[1]; P.z = s_out[2];
+  P.sy = __shfl_sync(FULL, sn, 0); P.cy = __shfl_sync(FULL, cs, 0);
+  P.sp = __shfl_sync(FULL, sn, 1); P.cp = __shfl_sync(FULL, cs, 1);
+  P.sr = __shfl_sync(FULL, sn, 2); P.cr = __shfl_sync(FULL, cs, 2);
+  rotation_from_trig(P);
+  const double gnorm = sqrt(n2);
+  const int done = (it + 1 >= bp.max_iters[a]) || (gnorm < bp.min_grad[a]);   // AN:383-392
+  __syncwarp();
+  if (lane == 0) {
+    if (log && sh->pose.log_count < bp.log_cap) {
+      const double* t = sh->totals;
+      phovo_iter_stats* e = log + (size_t)pair * bp.log_cap + sh->pose.log_count;
+      e->level = bp.level[a]; e->iteration = it; e->num_valid = (int)t[28]; e->accepted = 1;
+      for (int k = 0; k < 21; ++k) e->H[k] = t[k];
+      for (int k = 0; k < 6; ++k) { e->g[k] = t[21 + k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
+      e->grad_norm = gnorm; e->cost = 0.5 * t[27]; e->radius = 0.;
+    }
+    sh->pose.log_count += 1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sh->pose.state[k] = s_out[k];
+    pose_store(P, &sh->pose);
+    sh->done = done;
+    sh->iteration = it + 1;
+  }
+}
+
+// K3-batch.  Persistent CTAs fetch pairs from a global counter (iteration counts differ between
+// pairs, so static assignment leaves SMs idle at the tail).  Per level, resident in shared memory:
+//   sWin u32[n]  winner word per TARGET slot: (source index + 1) << 16 | I0 tap sum of that source;
+//                a native 32-bit shared atomicMax keeps the largest source index == the reference's
+//                raster-order last-writer-wins (AN:358) and carries the winner's intensity along
+//   sG   u32[n]  Scharr numerators of I1 at the pixel (gx low s16, gy high s16), exact integers,
+//                computed once per level from the resident I1 tap sums (AN:165-189)
+//   sI1  u16[n]  I1 tap sums (value = sum / 1020)
+//   sTab f64     (c - ox) per column and (r - oy) per row, the reference's own roundings (AN:282-287)
+// D0 (fp64) and I0 (u16) are streamed from the pair's record (L2) with register prefetch.
+// Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current pose
+// stays in a 64-bit register mask between the two phases of an iteration.
 template <int MODE>
 __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ BatchParams bp, const uint8_t* __restrict__ store,
                                                        const double* __restrict__ init_states, double* __restrict__ states,
                                                        int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
-                                                       int32_t* __restrict__ log_counts, int nmax) {
+                                                       int32_t* __restrict__ log_counts, int nmax, int tabmax,
+                                                       unsigned int* __restrict__ next_pair) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: I0 u16[nmax] | I1 u16[nmax] | win u16[nmax] | tgt u16[nmax] | reduction scratch | BatchShared
-  unsigned short* sI0 = (unsigned short*)smem_raw;
-  unsigned short* sI1 = sI0 + nmax;
-  unsigned short* sWin = sI1 + nmax;
-  unsigned short* sTgt = sWin + nmax;
-  double* sRed = (double*)(sTgt + nmax);
-  BatchShared* sh = (BatchShared*)(sRed + (BT / 32) * PHOVO_ACC_STRIDE);
-  const int tid = threadIdx.x;
+  unsigned* sWin = (unsigned*)smem_raw;
+  unsigned* sG = sWin + nmax;
+  unsigned short* sI1 = (unsigned short*)(sG + nmax);
+  double* sTab = (double*)(sI1 + nmax);
+  double* sRed = sTab + tabmax;
+  BatchShared* sh = (BatchShared*)(sRed + NW * 32);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-  for (int pair = blockIdx.x; pair < bp.num_pairs; pair += gridDim.x) {
+  for (;;) {
     __syncthreads();   // the previous pair's outputs have been read from shared memory
     if (tid == 0) {
-      double s[6];
-      for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)pair * 6 + k] : 0.;
-      Pose P;
-      pose_from_state(s, P);
-      for (int k = 0; k < 6; ++k) sh->pose.state[k] = s[k];
-      pose_store(P, &sh->pose);
-      sh->pose.log_count = 0;
+      const int pair = (int)atomicAdd(next_pair, 1u);
+      sh->pair = pair;
+      if (pair < bp.num_pairs) {
+        double s[6];
+        for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)pair * 6 + k] : 0.;
+        Pose P;
+        pose_from_state(s, P);
+        for (int k = 0; k < 6; ++k) sh->pose.state[k] = s[k];
+        pose_store(P, &sh->pose);
+        sh->pose.log_count = 0;
+      }
     }
+    __syncthreads();
+    const int pair = sh->pair;
+    if (pair >= bp.num_pairs) break;
     const uint8_t* rec = store + (size_t)pair * bp.record_bytes;
+
     for (int a = 0; a < bp.num_active; ++a) {
       const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
       const double* __restrict__ gD0 = (const double*)(rec + bp.off_D0[a]);
-      __syncthreads();   // previous level / pair fully consumed before the buffers are overwritten
+      const unsigned short* __restrict__ gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
+      double* sCx = sTab; double* sRy = sTab + cols;
       {
-        // HBM -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
-        const uint4* gI0 = (const uint4*)(rec + bp.off_I0[a]);
+        // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
         const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
-        uint4* i04 = (uint4*)sI0; uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
-        const int ni = (n * 2 + 15) / 16;
-        for (int k = tid; k < ni; k += BT) { i04[k] = __ldg(gI0 + k); i14[k] = __ldg(gI1 + k); w4[k] = make_uint4(0, 0, 0, 0); }
+        uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
+        const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
+        for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
+        for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);
+        const double ox = bp.ox[a], oy = bp.oy[a];
+        for (int k = tid; k < cols; k += BT) sCx[k] = __dsub_rn((double)k, ox);   // AN:282
+        for (int k = tid; k < rows; k += BT) sRy[k] = __dsub_rn((double)k, oy);   // AN:286
       }
       if (tid == 0) { sh->done = 0; sh->iteration = 0; }
       __syncthreads();
-
-      LevelParams L;
-      L.fx = bp.fx[a]; L.fy = bp.fy[a]; L.ox = bp.ox[a]; L.oy = bp.oy[a]; L.inv_fx = bp.inv_fx[a]; L.inv_fy = bp.inv_fy[a];
-      L.min_depth = bp.min_depth; L.max_depth = bp.max_depth; L.rows = rows; L.cols = cols;
-      L.lambda = bp.lambda[a]; L.min_grad_norm = bp.min_grad[a]; L.max_iters = bp.max_iters[a]; L.level = bp.level[a];
-      const double gk = bp.grad_k[a];
       // pixel i = tid + k*BT: (r, c) advance by a fixed (dr, dc) per step -- no division in the loops
       const int r_first = tid / cols, c_first = tid - r_first * cols;
       const int dr = BT / cols, dc = BT - dr * cols;
+      {
+        // Scharr numerators of I1 (AN:181-187), reflect-101: |gx|,|gy| <= 16 * 1020 fits s16
+        int r = r_first, c = c_first;
+        for (int i = tid; i < n; i += BT) {
+          const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
+          const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
+          const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
+          const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
+          const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
+          const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
+          sG[i] = ((unsigned)gxn & 0xffffu) | ((unsigned)gyn << 16);
+          c += dc; r += dr;
+          if (c >= cols) { c -= cols; ++r; }
+        }
+      }
+      __syncthreads();
 
-      for (int it = 0; it < L.max_iters; ++it) {
+      const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
+      const double min_depth = bp.min_depth, max_depth = bp.max_depth;
+      const double gkfx = bp.grad_k[a] * fx, gkfy = bp.grad_k[a] * fy;
+      const int max_iters = bp.max_iters[a];
+
+      for (int it = 0; it < max_iters; ++it) {
         Pose T;
         pose_load(&sh->pose, T);
-        // ---- phase A1: warp every source pixel; record its target slot; plain (racy) store of
-        //      the candidate winner -- colliding writers are resolved in A2 ----
+        // ---- phase A: warp every source pixel (AN:279-303, fp64, reference operation order, no
+        //      FMA contraction) and bid for its target slot.  Straight-line per pixel so the
+        //      compiler can interleave the dependent chains of consecutive pixels. ----
+        unsigned long long valid = 0ull;
         {
-          int r = r_first, c = c_first;
-          for (int i = tid; i < n; i += BT) {
-            Warped w;
-            unsigned short t = kNoTarget;
-            if (warp_pixel<false>(L, T, r, c, __ldg(gD0 + i), w)) { t = (unsigned short)w.t; sWin[w.t] = (unsigned short)(i + 1); }
-            sTgt[i] = t;
+          int r = r_first, c = c_first, k = 0;
+          int i = tid;
+          double d_next = i < n ? __ldg(gD0 + i) : 0.;
+          unsigned i0_next = i < n ? (unsigned)__ldg(gI0 + i) : 0u;
+          for (; i < n; i += BT, ++k) {
+            const double d = d_next;
+            const unsigned i0 = i0_next;
+            if (i + BT < n) { d_next = __ldg(gD0 + i + BT); i0_next = (unsigned)__ldg(gI0 + i + BT); }
+            const double px = __dmul_rn(__dmul_rn(sCx[c], d), inv_fx);
+            const double py = __dmul_rn(__dmul_rn(sRy[r], d), inv_fy);
+            const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R00, px), __dmul_rn(T.R01, py)), __dmul_rn(T.R02, d)), T.x);
+            const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R10, px), __dmul_rn(T.R11, py)), __dmul_rn(T.R12, d)), T.y);
+            const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R20, px), __dmul_rn(T.R21, py)), __dmul_rn(T.R22, d)), T.z);
+            const double iz = rcp_rn_normal(Z);                                       // AN:294 `1./Z`
+            const double tc = __dadd_rn(__dmul_rn(__dmul_rn(X, fx), iz), ox);
+            const double tr = __dadd_rn(__dmul_rn(__dmul_rn(Y, fy), iz), oy);
+            // C round(): half away from zero == trunc(x + copysign(0.5, x)) with the add rounded toward zero
+            const int tj = __double2int_rz(__dadd_rz(tc, copysign(0.5, tc)));
+            const int ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));
+            const double az = fabs(Z);
+            // strict depth bounds (AN:279-280); |Z| outside the normal range (incl. NaN / 0, where the
+            // reference's int cast is undefined) is out of bounds; saturated casts fail the range test
+            const bool ok = (min_depth < d) & (d < max_depth) & (az > 1e-300) & (az < 1e300) &
+                            ((unsigned)tj < (unsigned)cols) & ((unsigned)ti < (unsigned)rows);
+            if (ok) {
+              atomicMax(sWin + ti * cols + tj, ((unsigned)(i + 1) << 16) | i0);       // AN:358
+              valid |= 1ull << k;
+            }
             c += dc; r += dr;
             if (c >= cols) { c -= cols; ++r; }
           }
         }
         __syncthreads();
-        // ---- phase A2: a source that should have won its slot but lost the store race fixes it
-        //      (AN:358 last-writer-wins in raster order == largest source index); ~1% of pixels ----
-        for (int i = tid; i < n; i += BT) {
-          const unsigned short t = sTgt[i];
-          if (t != kNoTarget && sWin[t] < (unsigned short)(i + 1)) smem_max_u16(sWin + t, (unsigned short)(i + 1));
-        }
-        __syncthreads();
-        // ---- phase B: residual + Jacobian + normal equations (AN:271-366, 538-539) ----
-        double acc[PHOVO_NACC];
+        // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
+        double acc[28];
 #pragma unroll
-        for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+        for (int v = 0; v < 28; ++v) acc[v] = 0.;
         {
-          int r = r_first, c = c_first;
-          for (int i = tid; i < n; i += BT) {
-            const unsigned short win = sWin[i];
-            sWin[i] = 0;
+          const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
+          int r = r_first, c = c_first, k = 0;
+          int i = tid;
+          double d_next = i < n ? __ldg(gD0 + i) : 0.;
+          for (; i < n; i += BT, ++k) {
+            const double d = d_next;
+            if (i + BT < n) d_next = __ldg(gD0 + i + BT);
+            const unsigned w = sWin[i];
+            sWin[i] = 0u;
             double res = 0.;
-            if (win) {
+            if (w) {
               // I = sum/1020: one rounding, within 2 ulp of the reference's convertTo + resize doubles
-              res = (double)((int)sI1[i] - (int)sI0[win - 1]) * (1.0 / 1020.0);
+              res = (double)((int)sI1[i] - (int)(w & 0xffffu)) * (1.0 / 1020.0);
               acc[27] = fma(res, res, acc[27]);
             }
-            if (sTgt[i] != kNoTarget) {
-              const double d = __ldg(gD0 + i);
-              Warped w;
-              w.px = __dmul_rn(__dmul_rn(__dsub_rn((double)c, L.ox), d), L.inv_fx);
-              w.py = __dmul_rn(__dmul_rn(__dsub_rn((double)r, L.oy), d), L.inv_fy);
-              w.q0 = __dadd_rn(__dadd_rn(__dmul_rn(T.R00, w.px), __dmul_rn(T.R01, w.py)), __dmul_rn(T.R02, d));
-              w.q1 = __dadd_rn(__dadd_rn(__dmul_rn(T.R10, w.px), __dmul_rn(T.R11, w.py)), __dmul_rn(T.R12, d));
-              w.q2 = __dadd_rn(__dadd_rn(__dmul_rn(T.R20, w.px), __dmul_rn(T.R21, w.py)), __dmul_rn(T.R22, d));
-              w.X = __dadd_rn(w.q0, T.x); w.Y = __dadd_rn(w.q1, T.y); w.Z = __dadd_rn(w.q2, T.z);
-              w.iz = __ddiv_rn(1.0, w.Z);
-              // Scharr of I1 at the SOURCE index (AN:346-347), reflect-101, exact integer numerators
-              const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
-              const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
-              const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
-              const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
-              const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
-              const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
-              const double gx = (double)gxn * gk, gy = (double)gyn * gk;
-              double Ju[6], Jv[6], J[6];
-              projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
-#pragma unroll
-              for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];
+            if ((valid >> k) & 1ull) {
+              const double px = sCx[c] * d * inv_fx, py = sRy[r] * d * inv_fy;
+              const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+              const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+              const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+              const double iz = rcp_1ulp(q2 + T.z);
+              const unsigned gw = sG[i];
+              // a = Gx1[i] * fx / Z', b = Gy1[i] * fy / Z'   (gradients at the SOURCE index, AN:346-347)
+              const double ga = (double)(short)(gw & 0xffffu) * gkfx * iz;
+              const double gb = (double)((int)gw >> 16) * gkfy * iz;
+              // closed form of AN:243-342, gradient folded in:
+              const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
+              const double B = q1 + T.y;
+              double J[6];
+              J[0] = ga;
+              J[1] = gb;
+              J[2] = -(fma(ga, A, gb * B) * iz);
+              J[3] = fma(gb, q0, -(ga * q1));
+              const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+              J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
+              const double Zr = fma(T.R22, py, -(T.R21 * d));
+              J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
               accumulate_row(acc, J, res);
-              acc[28] += 1.;
             }
             c += dc; r += dr;
             if (c >= cols) { c -= cols; ++r; }
           }
         }
-        const double total = block_reduce<BT>(acc, sRed);
-        if (tid < PHOVO_NACC) sh->totals[tid] = total;
+        // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
+        {
+          double x[32];
+#pragma unroll
+          for (int v = 0; v < 28; ++v) x[v] = acc[v];
+          x[28] = (double)__popcll(valid); x[29] = 0.; x[30] = 0.; x[31] = 0.;
+          sRed[wid * 32 + lane] = warp_transpose_sum(x, lane);
+        }
         __syncthreads();
-        // ---- Gauss-Newton step + termination test (AN:538-549, 376-392), one thread ----
-        if (tid == 0) {
-          const double* t = sh->totals;
-          double g[6], step[6], s_in[6], s_out[6], n2 = 0.;
-          for (int k = 0; k < 6; ++k) { g[k] = t[21 + k]; n2 = fma(g[k], g[k], n2); s_in[k] = sh->pose.state[k]; }
-          solve6_lu(t, g, step);
-          for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];
-          const double gnorm = sqrt(n2);
-          const int done = (it + 1 >= L.max_iters) || (gnorm < L.min_grad_norm);
-          if (log && sh->pose.log_count < bp.log_cap) {
-            phovo_iter_stats* e = log + (size_t)pair * bp.log_cap + sh->pose.log_count;
-            e->level = L.level; e->iteration = it; e->num_valid = (int)t[28]; e->accepted = 1;
-            for (int k = 0; k < 21; ++k) e->H[k] = t[k];
-            for (int k = 0; k < 6; ++k) { e->g[k] = g[k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
-            e->grad_norm = gnorm; e->cost = 0.5 * t[27]; e->radius = 0.;
-          }
-          sh->pose.log_count += 1;
-          Pose P;
-          pose_from_state(s_out, P);
-          for (int k = 0; k < 6; ++k) sh->pose.state[k] = s_out[k];
-          pose_store(P, &sh->pose);
-          sh->done = done;
-          sh->iteration = it + 1;
+        if (wid == 0) {
+          double tot = 0.;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) tot += sRed[w * 32 + lane];
+          warp_gn_step(tot, lane, bp, a, it, pair, sh, log);
         }
         __syncthreads();
         if (sh->done) break;
       }
-      if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + L.level] = sh->iteration;
+      if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + bp.level[a]] = sh->iteration;
     }
     __syncthreads();
     if (tid < 6) states[(size_t)pair * 6 + tid] = sh->pose.state[tid];
@@ -267,9 +433,10 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
 
 }  // namespace
 
-size_t batch_align_smem_bytes(int nmax) {
+size_t batch_align_smem_bytes(int nmax, int tabmax) {
   nmax = (nmax + 7) & ~7;
-  return (size_t)nmax * 8 + (size_t)(BT / 32) * PHOVO_ACC_STRIDE * sizeof(double) + sizeof(BatchShared) + 64;
+  tabmax = (tabmax + 1) & ~1;
+  return (size_t)nmax * 10 + (size_t)tabmax * sizeof(double) + (size_t)NW * 32 * sizeof(double) + sizeof(BatchShared) + 64;
 }
 
 cudaError_t batch_align_prepare(size_t smem_bytes) {
@@ -290,14 +457,19 @@ int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8
 }
 
 int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
-                       const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log, int32_t* log_counts) {
-  int nmax = 0;
-  for (int a = 0; a < bp.num_active; ++a) nmax = max(nmax, bp.lrows[a] * bp.lcols[a]);
+                       const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log, int32_t* log_counts,
+                       unsigned int* next_pair) {
+  int nmax = 0, tabmax = 0;
+  for (int a = 0; a < bp.num_active; ++a) {
+    nmax = max(nmax, bp.lrows[a] * bp.lcols[a]);
+    tabmax = max(tabmax, bp.lrows[a] + bp.lcols[a]);
+  }
   nmax = (nmax + 7) & ~7;
+  tabmax = (tabmax + 1) & ~1;
   if (bp.mode == PHOVO_MODE_ANALYTIC_FIXED)
-    k_batch_align<1><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax);
+    k_batch_align<1><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax, tabmax, next_pair);
   else
-    k_batch_align<0><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax);
+    k_batch_align<0><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax, tabmax, next_pair);
   return 1;
 }
 

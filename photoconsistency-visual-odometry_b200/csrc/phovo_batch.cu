@@ -36,6 +36,7 @@ struct phovo_batch_state {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   double* h_states_pinned = nullptr; int32_t* h_iters_pinned = nullptr; size_t h_out_cap = 0;
   size_t prepared_smem = 0;
+  unsigned int* next_pair = nullptr;   // work counter of the persistent align kernel
   int sm_count = 0;
   cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // before pyramid / between / after align
   bool timed = false;
@@ -60,6 +61,7 @@ static cudaError_t ensure(T** p, size_t* cap, size_t want) {
 void phovo_batch_release(phovo_ctx* ctx) {
   phovo_batch_state* b = ctx->batch;
   if (!b) return;
+  cudaFree(b->next_pair);
   cudaFree(b->store); cudaFree(b->states); cudaFree(b->iters); cudaFree(b->init); cudaFree(b->log); cudaFree(b->log_counts);
   for (int s = 0; s < 2; ++s) {
     cudaFree(b->stage_g0[s]); cudaFree(b->stage_g1[s]); cudaFree(b->stage_d[s]);
@@ -79,6 +81,7 @@ static int get_state(phovo_ctx* ctx, phovo_batch_state** out) {
     CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->batch->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->batch->copy_stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void**)&ctx->batch->next_pair, sizeof(unsigned int)));
     for (int s = 0; s < 2; ++s) {
       CK(cudaEventCreateWithFlags(&ctx->batch->ev_copied[s], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ctx->batch->ev_consumed[s], cudaEventDisableTiming));
@@ -97,7 +100,7 @@ static void level_size(int rows, int cols, int level, int* orows, int* ocols) {
 // Parameter block for a rows x cols batch under the context's config; fails loudly when a
 // configuration cannot run in the shared-memory-resident kernel (there is no slower fallback
 // inside this entry point: the caller is told to use the per-pair API).
-static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, int* nmax_out) {
+static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, size_t* smem_out) {
   if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
   if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
   if (ctx->cfg.mode == PHOVO_MODE_CERES) return ctx->fail(PHOVO_E_UNSUPPORTED, "the batch kernel implements the analytic solver only");
@@ -105,7 +108,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   bp->num_pairs = num_pairs; bp->rows = rows; bp->cols = cols;
   bp->mode = ctx->cfg.mode; bp->log_cap = log_cap;
   bp->min_depth = ctx->cfg.min_depth; bp->max_depth = ctx->cfg.max_depth;
-  int a = 0, nmax = 0;
+  int a = 0, nmax = 0, tabmax = 0;
   unsigned long long off = 0;
   for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
     if (ctx->cfg.max_num_iterations[level] <= 0) continue;
@@ -115,8 +118,9 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     level_size(rows, cols, level, &lr, &lc);
     if (lr < 1 || lc < 1) return ctx->fail(PHOVO_E_INVALID, "image too small for the number of pyramid levels");
     const int n = lr * lc;
-    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (28160 px); use the per-pair API");
+    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
     nmax = std::max(nmax, n);
+    tabmax = std::max(tabmax, lr + lc);
     bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
     bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
     bp->px_offset[a + 1] = bp->px_offset[a] + n;
@@ -135,11 +139,12 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   }
   bp->num_active = a;
   bp->record_bytes = off ? off : 16;
-  *nmax_out = nmax;
+  *smem_out = batch_align_smem_bytes(nmax, tabmax);
+  if (*smem_out > 227 * 1024) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget; use the per-pair API");
   return PHOVO_OK;
 }
 
-static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& bp, int nmax, cudaStream_t stream,
+static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& bp, size_t smem, cudaStream_t stream,
                       const uint8_t* g0, const void* d0, int depth_type, double depth_scale, const uint8_t* g1,
                       uint8_t* store, const double* init, double* states, int32_t* iters,
                       phovo_iter_stats* log, int32_t* log_counts) {
@@ -149,7 +154,6 @@ static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& b
     else CK(cudaMemsetAsync(states, 0, sizeof(double) * 6 * (size_t)bp.num_pairs, stream));
     return PHOVO_OK;
   }
-  const size_t smem = batch_align_smem_bytes(nmax);
   if (b->prepared_smem < smem) {
     CK(batch_align_prepare(smem));
     b->prepared_smem = smem;
@@ -160,7 +164,8 @@ static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& b
   ctx->launches += launch_batch_pyramid(stream, bp, g0, d0, src, depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0, g1, store);
   CK(cudaEventRecord(b->ev_k[1], stream));
   const int grid = std::min(bp.num_pairs, b->sm_count);   // one persistent CTA per SM
-  ctx->launches += launch_batch_align(stream, bp, grid, smem, store, init, states, iters, log, log_counts);
+  CK(cudaMemsetAsync(b->next_pair, 0, sizeof(unsigned int), stream));
+  ctx->launches += launch_batch_align(stream, bp, grid, smem, store, init, states, iters, log, log_counts, b->next_pair);
   CK(cudaEventRecord(b->ev_k[2], stream));
   b->timed = true;
   CK(cudaGetLastError());
@@ -213,10 +218,10 @@ extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows,
   if (rc) return rc;
   int log_cap = 0;
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
-  BatchParams bp; int nmax = 0;
-  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &nmax))) return rc;
+  BatchParams bp; size_t smem = 0;
+  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
   CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
-  return run_device(ctx, b, bp, nmax, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store,
+  return run_device(ctx, b, bp, smem, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store,
                     initial_states, states, iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
 }
 
@@ -236,8 +241,8 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
   if (rc) return rc;
   int log_cap = 0;
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
-  BatchParams bp; int nmax = 0;
-  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &nmax))) return rc;
+  BatchParams bp; size_t smem = 0;
+  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
   CK(ensure(&b->states, &b->states_cap, (size_t)num_pairs * 6));
   CK(ensure(&b->iters, &b->iters_cap, (size_t)num_pairs * PHOVO_MAX_LEVELS));
   CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
@@ -257,7 +262,7 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
   const bool on_device = is_device_pointer(gray0) && is_device_pointer(depth0) && is_device_pointer(gray1);
   const size_t frame = (size_t)rows * cols, delt = depth_elt(depth_type);
   if (on_device) {
-    rc = run_device(ctx, b, bp, nmax, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store, d_init,
+    rc = run_device(ctx, b, bp, smem, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store, d_init,
                     b->states, b->iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
     if (rc) return rc;
   } else {
@@ -282,7 +287,7 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
       CK(cudaStreamWaitEvent(ctx->stream, b->ev_copied[slot], 0));
       BatchParams cp = bp;
       cp.num_pairs = np;
-      rc = run_device(ctx, b, cp, nmax, ctx->stream, b->stage_g0[slot], b->stage_d[slot], depth_type, depth_scale, b->stage_g1[slot],
+      rc = run_device(ctx, b, cp, smem, ctx->stream, b->stage_g0[slot], b->stage_d[slot], depth_type, depth_scale, b->stage_g1[slot],
                       b->store + (size_t)p0 * bp.record_bytes, d_init ? d_init + (size_t)p0 * 6 : nullptr,
                       b->states + (size_t)p0 * 6, b->iters + (size_t)p0 * PHOVO_MAX_LEVELS,
                       log_cap ? b->log + (size_t)p0 * log_cap : nullptr, log_cap ? b->log_counts + p0 : nullptr);

@@ -9,8 +9,9 @@
 
 namespace phovo {
 
-constexpr int kBatchThreads = 384;          // 12 warps: 170 registers per thread, fp64 pipe saturated
-constexpr int kBatchMaxLevelPixels = 28160; // 8 B/px of shared memory + scratch must fit 227 KB; also < 65535 (u16 maps)
+constexpr int kBatchThreads = 384;          // 12 warps, up to 168 registers per thread
+constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + tables + scratch must fit 227 KB (checked exactly
+                                            // by the host); also <= 64 * kBatchThreads (validity mask) and < 65535
 
 // Everything the two batch kernels need, passed by value (__grid_constant__).
 struct BatchParams {
@@ -39,8 +40,8 @@ int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8
 // whole coarse-to-fine Gauss-Newton loop on chip.
 int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
                        const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log,
-                       int32_t* log_counts);
-size_t batch_align_smem_bytes(int max_level_pixels);
+                       int32_t* log_counts, unsigned int* next_pair /* device counter, zero before the launch */);
+size_t batch_align_smem_bytes(int max_level_pixels, int max_rows_plus_cols);
 cudaError_t batch_align_prepare(size_t smem_bytes);
 
 }  // namespace phovo
