@@ -12,19 +12,24 @@
  *   SA = third_party/sample.h          JE = third_party/jet_extras.h
  *   BASE = phovo/include/CPhotoconsistencyOdometry.h
  *
- * PARITY PINNING.  The reference ships no tests, golden vectors or sample data, and it cannot be
- * compiled here as-is (OpenCV C++, Eigen, Ceres and Boost are not installed).  The oracle is
- * therefore pinned three ways, all in tests/ (-m "not gpu"):
- *   1. the third-party image arithmetic (cv::resize, cv::Scharr, cv::GaussianBlur, convertTo) is
- *      checked against OpenCV 4.13 itself through python cv2, live and via tests/golden;
- *   2. the per-pixel / Gauss-Newton restatement is checked against an independently written
- *      numpy restatement (oracle/np_restatement.py) and, for the Jacobian, against a symbolic
- *      re-derivation of phovo/Maxima/derivatives_photoconsistency.wxm;
- *   3. oracle/_ref: the reference's OWN header (AN) compiled unmodified from /root/reference
- *      against minimal stand-ins for the cv:: / Eigen:: types it touches (oracle/shim/), run on
- *      the same inputs -- see oracle/Makefile.  The stand-ins replace third-party code only.
- * The Ceres solver itself (trust-region LM loop) is third-party and absent: Ceres-mode
- * residuals/Jacobians are pinned as above, the LM trajectory is "parity unpinned".
+ * PARITY PINNING.  The reference ships no tests, golden vectors or sample data, and its build
+ * needs OpenCV, Eigen, Ceres and Boost, none of which is installed here.  The oracle is pinned
+ * three ways, all in tests/ (-m "not gpu"):
+ *   1. AGAINST THE REFERENCE'S OWN SOURCE (analytic path): oracle/_ref/libphovo_ref.so is
+ *      CPhotoconsistencyOdometryAnalytic.h compiled UNMODIFIED from /root/reference against minimal
+ *      stand-ins for the cv:: / Eigen:: types it touches (oracle/shim/, oracle/Makefile).  Run on
+ *      the same inputs the oracle agrees with it to the last bit on the tested pairs (per-iteration
+ *      J^T J / J^T r, iteration counts, final state; tests/test_reference_source_pins.py), and
+ *      tests/golden/ref_*.npz are outputs of that library (tests/golden/make_reference_golden.py).
+ *      The stand-ins replace third-party code only; behind them the image arithmetic is (2).
+ *   2. the third-party image arithmetic (cv::resize, cv::Scharr, cv::GaussianBlur, convertTo) is
+ *      checked against OpenCV 4.13 itself through python cv2, live and via tests/golden/cv2_ops.npz;
+ *   3. an independently written numpy restatement (oracle/np_restatement.py) and, for the
+ *      Jacobian, a symbolic re-derivation of phovo/Maxima/derivatives_photoconsistency.wxm.
+ * Ceres mode: the residual functor (CE:156-269, sample.h, jet_extras.h) needs Ceres' Jet type and
+ * cannot be compiled here; its restatement is pinned by (2)/(3) and by finite differences only,
+ * and the Ceres solver itself (trust-region LM) is third-party and absent: the Ceres-mode LM
+ * trajectory is "parity unpinned".
  */
 #ifndef PHOVO_ORACLE_H_
 #define PHOVO_ORACLE_H_

@@ -78,6 +78,18 @@ REFERENCE_CONFIGS = {
 }
 
 
+# NOT from the reference tree: extra configurations used by the parity tests (every level active,
+# lambda != 1, low thresholds so that levels run to their iteration caps).
+EXTRA_CONFIGS = {
+    "test_3_level_all_active": _analytic(3, [3, 6, 10], [1., 1., 1.]),
+}
+EXTRA_CONFIGS["test_3_level_all_active"][K_LAMBDA] = [0.8, 1, 0.9]
+
+
+def _lookup(name):
+    return REFERENCE_CONFIGS[name] if name in REFERENCE_CONFIGS else EXTRA_CONFIGS[name]
+
+
 def to_yaml(values):
     """OpenCV FileStorage YAML 1.0 text for a config dict."""
     lines = ["%YAML:1.0"]
@@ -92,13 +104,13 @@ def to_yaml(values):
 def write_yaml(name, directory):
     path = os.path.join(directory, name + ".yml")
     with open(path, "w") as f:
-        f.write(to_yaml(REFERENCE_CONFIGS[name]))
+        f.write(to_yaml(_lookup(name)))
     return path
 
 
 def to_config(name, capi, mode=None):
     """capi.Config for a named reference configuration without going through a file."""
-    v = REFERENCE_CONFIGS[name]
+    v = _lookup(name)
     cfg = capi.default_config() if hasattr(capi, "default_config") else capi.Config()
     n = capi.MAXL
 

@@ -1,0 +1,100 @@
+"""The C++ drop-in adapter (include/CPhotoconsistencyOdometryCuda.h) driven the way the reference
+apps drive the analytic solver (tests/cpp/frame_alignment_app.cpp mirrors both main()s), checked
+against the CPU oracle.  The binary is compiled against stand-in cv::/Eigen types (tests/cpp/shim)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import assert_pose_close
+from test_gpu_parity import conv_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "tests", "cpp", "_build", "frame_alignment_app")
+
+
+def build_app():
+    subprocess.check_call(["bash", os.path.join(ROOT, "tests", "cpp", "build_adapter_test.sh")], stdout=subprocess.DEVNULL)
+    return APP
+
+
+def test_adapter_compiles_and_fails_loudly_without_gpu(phovo, tmp_path):
+    """No CPU fallback behind the C++ surface either: without a device the constructor throws."""
+    app = build_app()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    cfg = phovo.configs.write_yaml("config_4_level_optimization_analytic", str(tmp_path))
+    args = [app, "align", cfg, "4", "4", "1", "1", "1", "1", "a", "b", "c", "d"]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 3 and "phovo_create" in r.stderr and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_frame_alignment_app_matches_oracle(phovo, oracle, tmp_path):
+    """PhotoconsistencyFrameAlignment.cpp:90-105 through the adapter, strided cv::Mat_ inputs."""
+    app = build_app()
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(480, 640, K=K, seed=21)
+    name = "config_4_level_optimization_analytic"
+    yml = phovo.configs.write_yaml(name, str(tmp_path))
+    paths = {}
+    for nm, arr in (("g0", g0), ("d0", d0.astype(np.float64)), ("g1", g1), ("d1", np.zeros_like(d0, dtype=np.float64))):
+        paths[nm] = str(tmp_path / (nm + ".bin"))
+        arr.tofile(paths[nm])
+    args = [app, "align", yml, "480", "640", repr(K[0, 0]), repr(K[1, 1]), repr(K[0, 2]), repr(K[1, 2]),
+            paths["g0"], paths["d0"], paths["g1"], paths["d1"], "24"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.splitlines() if ln.strip()}
+    state = np.array([float(x) for x in out["state"]])
+    Rt = np.array([float(x) for x in out["Rt"]]).reshape(4, 4)
+    cfg = phovo.configs.to_config(name, phovo.capi)
+    o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+    o.set_source(g0, d0)
+    o.set_target(g1)
+    o.set_initial_state(np.zeros(6))
+    o.optimize()
+    assert int(out["iterations"][0]) == len(o.iter_stats())
+    assert_pose_close(state, o.state(), "C++ adapter")
+    assert np.max(np.abs(state - o.state())) < 1e-10
+    assert np.max(np.abs(Rt - o.rt())) < 1e-10
+
+
+@pytest.mark.gpu
+def test_visual_odometry_app_trajectory_matches_oracle(phovo, oracle, tmp_path):
+    """PhotoconsistencyVisualOdometry.cpp:212-259: zero initial state every frame, pose *= Rt^-1,
+    TUM line `ts tx ty tz qx qy qz qw`; source pyramid reused on the device between frames."""
+    app = build_app()
+    K = phovo.synth.K_VISUAL_ODOMETRY
+    n = 5
+    frames = [phovo.synth.make_sequence_frame(k, 240, 320, K=K) for k in range(n)]
+    for k, (g, d) in enumerate(frames):
+        g.tofile(str(tmp_path / ("gray_%d.bin" % k)))
+        d.astype(np.float64).tofile(str(tmp_path / ("depth_%d.bin" % k)))
+    name = "config_5_level_optimization_analytic"
+    yml = phovo.configs.write_yaml(name, str(tmp_path))
+    traj = str(tmp_path / "trajectory.txt")
+    args = [app, "vo", yml, "240", "320", repr(K[0, 0]), repr(K[1, 1]), repr(K[0, 2]), repr(K[1, 2]), str(n),
+            str(tmp_path / "gray_%d.bin"), str(tmp_path / "depth_%d.bin"), traj]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.loadtxt(traj)
+    assert got.shape == (n - 1, 8)
+    cfg = phovo.configs.to_config(name, phovo.capi)
+    pose = np.eye(4)
+    for k in range(1, n):
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+        o.set_source(*frames[k - 1])
+        o.set_target(frames[k][0])
+        o.set_initial_state(np.zeros(6))
+        o.optimize()
+        pose = pose @ np.linalg.inv(o.rt())
+        assert np.max(np.abs(got[k - 1, 1:4] - pose[:3, 3])) < 1e-9
+        q = got[k - 1, 4:8]
+        x, y, z, w = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert abs(np.linalg.norm(q) - 1) < 1e-12 and np.max(np.abs(R - pose[:3, :3])) < 1e-9
