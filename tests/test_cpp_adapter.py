@@ -43,7 +43,7 @@ def test_frame_alignment_app_matches_oracle(phovo, oracle, tmp_path):
     for nm, arr in (("g0", g0), ("d0", d0.astype(np.float64)), ("g1", g1), ("d1", np.zeros_like(d0, dtype=np.float64))):
         paths[nm] = str(tmp_path / (nm + ".bin"))
         arr.tofile(paths[nm])
-    args = [app, "align", yml, "480", "640", repr(K[0, 0]), repr(K[1, 1]), repr(K[0, 2]), repr(K[1, 2]),
+    args = [app, "align", yml, "480", "640", repr(float(K[0, 0])), repr(float(K[1, 1])), repr(float(K[0, 2])), repr(float(K[1, 2])),
             paths["g0"], paths["d0"], paths["g1"], paths["d1"], "24"]
     r = subprocess.run(args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
@@ -76,7 +76,7 @@ def test_visual_odometry_app_trajectory_matches_oracle(phovo, oracle, tmp_path):
     name = "config_5_level_optimization_analytic"
     yml = phovo.configs.write_yaml(name, str(tmp_path))
     traj = str(tmp_path / "trajectory.txt")
-    args = [app, "vo", yml, "240", "320", repr(K[0, 0]), repr(K[1, 1]), repr(K[0, 2]), repr(K[1, 2]), str(n),
+    args = [app, "vo", yml, "240", "320", repr(float(K[0, 0])), repr(float(K[1, 1])), repr(float(K[0, 2])), repr(float(K[1, 2])), str(n),
             str(tmp_path / "gray_%d.bin"), str(tmp_path / "depth_%d.bin"), traj]
     r = subprocess.run(args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
