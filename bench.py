@@ -46,53 +46,58 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    nvidia-smi -lms as the fallback when pynvml cannot be loaded)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread, self.nvml, self.err = index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except ValueError:
+                    idx = self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, reasons, power))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % (self.err or "timed region too short")]}
+        sm = sorted(x[0] for x in self.samples)
+        mask = 0
+        for x in self.samples:
+            mask |= x[1]
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.smax), "power_w_max": max(x[2] for x in self.samples),
+                "samples": len(self.samples), "reasons": sorted(k for k, b in self.BAD.items() if mask & b)}
 
 
 def algorithmic_bytes(cfg, iters, rows, cols):
@@ -136,7 +141,7 @@ def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=4096, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -269,13 +274,34 @@ def main():
     align_t = float(np.mean(align_ms)) * 1e-3
     pyr_t = float(np.mean(pyr_ms)) * 1e-3
     achieved = iter_bytes / align_t / 1e9
+    px_iters = 0.0
+    for lvl in range(cfg.num_levels):
+        if cfg.max_num_iterations[lvl] > 0:
+            px_iters += float(it_host[:, lvl].sum()) * int(round(ROWS * 0.5 ** lvl)) * int(round(COLS * 0.5 ** lvl))
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+    except Exception:
+        pass
+    fp64 = None
+    if prof.get("fp64_thread_inst_per_px_iter"):
+        rate = px_iters * prof["fp64_thread_inst_per_px_iter"] / align_t
+        fp64 = {"achieved": rate / 1e12, "peak": prof["fp64_peak_thread_inst_per_s"] / 1e12, "unit": "T fp64 thread-instructions/s",
+                "frac": rate / prof["fp64_peak_thread_inst_per_s"], "inst_per_px_iter": prof["fp64_thread_inst_per_px_iter"],
+                "source": "ncu op counters of %s / executed pixel-iterations; peak = %s" % (prof.get("tag"), prof.get("fp64_peak_source"))}
     roofline = {"bound": "hbm", "kernel": "k_batch_align", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": (prof["dram_bytes_per_pair"] * P) if prof.get("dram_bytes_per_pair") else None,
+                "traffic_source": "ncu --set full dram__bytes_read+write of one launch (%s, %d pairs) scaled by pairs" % (prof.get("tag"), prof.get("profiled_pairs", 0)) if prof else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": iter_bytes, "kernel_ms": align_t * 1e3,
                 "share_of_step": align_t / (align_t + pyr_t),
-                "note": "level images are resident in shared memory, so the 20 B/px/iteration of SURVEY 8(d) is served on chip; compulsory HBM traffic is the packed record read once (8 B/px)",
+                "pixel_iterations_per_launch": px_iters,
+                "note": "algorithmic bytes = SURVEY 8(d): 20 B per pixel per executed GN iteration + 216 B of sums; the level is resident in shared memory, so DRAM traffic is the packed record read once and the binding unit is the FP64 pipe (see fp64)",
+                "fp64": fp64,
                 "other_kernels": {"k_batch_pyramid": {"kernel_ms": pyr_t * 1e3, "algorithmic_bytes_per_launch": setup_bytes,
-                                                      "achieved": setup_bytes / pyr_t / 1e9, "frac": setup_bytes / pyr_t / 1e9 / peak}}}
+                                                      "achieved": setup_bytes / pyr_t / 1e9, "frac": setup_bytes / pyr_t / 1e9 / peak,
+                                                      "note": "SURVEY 8(d) counts every input byte; the kernel touches only the 2 of every 4 / 8 rows the central 2x2 taps live in, so compulsory traffic is about half of this"}}}
     # ---- CPU baseline on this box's host cores, bounded sample of the same workload
     cpu = None
     if not args.no_cpu_baseline:

@@ -226,6 +226,81 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
   }
 }
 
+// Per-level / per-iteration lookup tables in shared memory (doubles).  `cols`/`rows` of the level.
+//   exact  : cx[c] = fl(c - ox), ry[r] = fl(r - oy)            the reference's own roundings (AN:282-287), phase A
+//   ray    : cxi[c] = cx[c] * inv_fx, ryi[r] = ry[r] * inv_fy  back-projected ray (px/d, py/d), phase B and table builds
+//   colA/B : {R00 cxi, R10 cxi}, {R20 cxi, -cp cxi}            per ITERATION: the column part of R*(ray) and of dZ'/dpitch
+//   row    : {R01 ryi + R02, R11 ryi + R12, R21 ryi + R22, -(sp sr ryi + sp cr), R22 ryi - R21, R02 ryi - R01, R12 ryi - R11, 0}
+// so that in phase B  q = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
+struct Tables {
+  double* cx; double* ry; double* cxi; double* ryi;
+  double2* colA; double2* colB;   // [cols]
+  double2* row;                   // [rows][4]
+};
+__host__ __device__ inline int table_doubles(int rows, int cols) { return 2 * (rows + cols) + 4 * cols + 8 * rows; }
+
+struct WarpA { int tj, ti; bool ok; };
+
+// Phase A of one pixel: AN:279-303 in fp64 with the reference's operation order and no FMA
+// contraction.  Straight-line code: no branches, so two pixels interleave in one basic block.
+__device__ __forceinline__ WarpA warp_exact(const Pose& T, double cx, double ry, double d, double fx, double fy, double ox, double oy,
+                                            double inv_fx, double inv_fy, double min_depth, double max_depth, int rows, int cols) {
+  const double px = __dmul_rn(__dmul_rn(cx, d), inv_fx);
+  const double py = __dmul_rn(__dmul_rn(ry, d), inv_fy);
+  const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R00, px), __dmul_rn(T.R01, py)), __dmul_rn(T.R02, d)), T.x);
+  const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R10, px), __dmul_rn(T.R11, py)), __dmul_rn(T.R12, d)), T.y);
+  const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R20, px), __dmul_rn(T.R21, py)), __dmul_rn(T.R22, d)), T.z);
+  const double iz = rcp_rn_normal(Z);                                       // AN:294 `1./Z`
+  const double tc = __dadd_rn(__dmul_rn(__dmul_rn(X, fx), iz), ox);
+  const double tr = __dadd_rn(__dmul_rn(__dmul_rn(Y, fy), iz), oy);
+  // C round(): half away from zero == trunc(x + copysign(0.5, x)) with the add rounded toward zero
+  WarpA w;
+  w.tj = __double2int_rz(__dadd_rz(tc, copysign(0.5, tc)));
+  w.ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));
+  const double az = fabs(Z);
+  // strict depth bounds (AN:279-280); |Z| outside the normal range (incl. NaN / 0, where the
+  // reference's int cast is undefined) is out of bounds; saturated casts fail the range test
+  w.ok = (min_depth < d) & (d < max_depth) & (az > 1e-300) & (az < 1e300) &
+         ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);
+  return w;
+}
+
+__device__ __forceinline__ void smem_red_max(unsigned addr, unsigned v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+struct IterConst {          // per-iteration scalars phase B needs besides the tables
+  double x, y, z, cy, sy, rho;
+};
+
+// Phase B of one pixel: J' = J / (gk fx) and the integer residual numerator; the common factors
+// are applied once per iteration to the reduced sums.  Everything is computed unconditionally on
+// sanitised operands and masked, so that two pixels interleave without branches.
+template <int MODE>
+__device__ __forceinline__ void jacobian_row(const IterConst& K, const Tables& tb, int r, int c, double d, bool valid, unsigned gw,
+                                             double J[6]) {
+  const double ds = valid ? d : 1.0;
+  const double2 ca = tb.colA[c], cb = tb.colB[c];
+  const double2 r0 = tb.row[4 * r + 0], r1 = tb.row[4 * r + 1], r2 = tb.row[4 * r + 2], r3 = tb.row[4 * r + 3];
+  const double q0 = ds * (ca.x + r0.x), q1 = ds * (ca.y + r0.y), q2 = ds * (cb.x + r1.x);
+  const double Zs = q2 + K.z;
+  const double iz = rcp_1ulp(valid ? Zs : 1.0);
+  // a' = Gx1[i] / Z', b' = Gy1[i] (fy/fx) / Z'   (gradients at the SOURCE index, AN:346-347)
+  const double ga = valid ? (double)(short)(gw & 0xffffu) * iz : 0.;
+  const double gb = valid ? (double)((int)gw >> 16) * (iz * K.rho) : 0.;
+  // closed form of AN:243-342, gradient folded in
+  const double A = MODE == 0 ? fma(ds * tb.cxi[c], K.x, q0) : q0 + K.x;   // AN:253 bug-compatible / Maxima-exact
+  const double B = q1 + K.y;
+  J[0] = ga;
+  J[1] = gb;
+  J[2] = -(fma(ga, A, gb * B) * iz);
+  J[3] = fma(gb, q0, -(ga * q1));
+  const double Zp = ds * (cb.y + r1.y);
+  J[4] = fma(q2, fma(ga, K.cy, gb * K.sy), Zp * J[2]);
+  const double Zr = ds * r2.x, t5a = ds * r2.y, t5b = ds * r3.x;
+  J[5] = fma(ga, t5a, fma(gb, t5b, Zr * J[2]));
+}
+
 // K3-batch.  Persistent CTAs fetch pairs from a global counter (iteration counts differ between
 // pairs, so static assignment leaves SMs idle at the tail).  Per level, resident in shared memory:
 //   sWin u32[n]  winner word per TARGET slot: (source index + 1) << 16 | I0 tap sum of that source;
@@ -234,10 +309,10 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
 //   sG   u32[n]  Scharr numerators of I1 at the pixel (gx low s16, gy high s16), exact integers,
 //                computed once per level from the resident I1 tap sums (AN:165-189)
 //   sI1  u16[n]  I1 tap sums (value = sum / 1020)
-//   sTab f64     (c - ox) per column and (r - oy) per row, the reference's own roundings (AN:282-287)
-// D0 (fp64) and I0 (u16) are streamed from the pair's record (L2) with register prefetch.
-// Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current pose
-// stays in a 64-bit register mask between the two phases of an iteration.
+//   tables       see struct Tables
+// D0 (fp64) and I0 (u16) are streamed from the pair's record (L2) with register prefetch two trips
+// ahead.  Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current
+// pose stays in a 64-bit register mask between the two phases of an iteration.
 template <int MODE>
 __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ BatchParams bp, const uint8_t* __restrict__ store,
                                                        const double* __restrict__ init_states, double* __restrict__ states,
@@ -252,6 +327,7 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
   double* sRed = sTab + tabmax;
   BatchShared* sh = (BatchShared*)(sRed + NW * 32);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
 
   for (;;) {
     __syncthreads();   // the previous pair's outputs have been read from shared memory
@@ -277,7 +353,10 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
       const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
       const double* __restrict__ gD0 = (const double*)(rec + bp.off_D0[a]);
       const unsigned short* __restrict__ gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
-      double* sCx = sTab; double* sRy = sTab + cols;
+      Tables tb;
+      tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
+      tb.cx = (double*)(tb.row + 4 * rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
+      const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
       {
         // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
         const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
@@ -285,18 +364,20 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
         const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
         for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
         for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);
-        const double ox = bp.ox[a], oy = bp.oy[a];
-        for (int k = tid; k < cols; k += BT) sCx[k] = __dsub_rn((double)k, ox);   // AN:282
-        for (int k = tid; k < rows; k += BT) sRy[k] = __dsub_rn((double)k, oy);   // AN:286
+        for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
+        for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
       }
       if (tid == 0) { sh->done = 0; sh->iteration = 0; }
       __syncthreads();
-      // pixel i = tid + k*BT: (r, c) advance by a fixed (dr, dc) per step -- no division in the loops
-      const int r_first = tid / cols, c_first = tid - r_first * cols;
-      const int dr = BT / cols, dc = BT - dr * cols;
+      // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT: both (r, c) pairs
+      // advance by the fixed step of 2*BT pixels -- no division in the loops
+      const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
+      const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
+      const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
       {
         // Scharr numerators of I1 (AN:181-187), reflect-101: |gx|,|gy| <= 16 * 1020 fits s16
-        int r = r_first, c = c_first;
+        const int dr = BT / cols, dc = BT - dr * cols;
+        int r = r0_first, c = c0_first;
         for (int i = tid; i < n; i += BT) {
           const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
           const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
@@ -311,49 +392,54 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
       }
       __syncthreads();
 
-      const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
       const double min_depth = bp.min_depth, max_depth = bp.max_depth;
-      const double gkfx = bp.grad_k[a] * fx, gkfy = bp.grad_k[a] * fy;
       const int max_iters = bp.max_iters[a];
+      // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
+      const double gkfx = bp.grad_k[a] * fx;
+      const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
 
       for (int it = 0; it < max_iters; ++it) {
         Pose T;
         pose_load(&sh->pose, T);
-        // ---- phase A: warp every source pixel (AN:279-303, fp64, reference operation order, no
-        //      FMA contraction) and bid for its target slot.  Straight-line per pixel so the
-        //      compiler can interleave the dependent chains of consecutive pixels. ----
+        // ---- per-iteration tables for phase B (read after the barrier that ends phase A) ----
+        for (int k = tid; k < cols + rows; k += BT) {
+          if (k < cols) {
+            const double v = tb.cxi[k];
+            tb.colA[k] = make_double2(T.R00 * v, T.R10 * v);
+            tb.colB[k] = make_double2(T.R20 * v, -(T.cp * v));
+          } else {
+            const int r = k - cols;
+            const double v = tb.ryi[r];
+            tb.row[4 * r + 0] = make_double2(fma(T.R01, v, T.R02), fma(T.R11, v, T.R12));
+            tb.row[4 * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
+            tb.row[4 * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
+            tb.row[4 * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
+          }
+        }
+        // ---- phase A: warp every source pixel and bid for its target slot ----
         unsigned long long valid = 0ull;
         {
-          int r = r_first, c = c_first, k = 0;
+          int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first, k = 0;
           int i = tid;
-          double d_next = i < n ? __ldg(gD0 + i) : 0.;
-          unsigned i0_next = i < n ? (unsigned)__ldg(gI0 + i) : 0u;
-          for (; i < n; i += BT, ++k) {
-            const double d = d_next;
-            const unsigned i0 = i0_next;
-            if (i + BT < n) { d_next = __ldg(gD0 + i + BT); i0_next = (unsigned)__ldg(gI0 + i + BT); }
-            const double px = __dmul_rn(__dmul_rn(sCx[c], d), inv_fx);
-            const double py = __dmul_rn(__dmul_rn(sRy[r], d), inv_fy);
-            const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R00, px), __dmul_rn(T.R01, py)), __dmul_rn(T.R02, d)), T.x);
-            const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R10, px), __dmul_rn(T.R11, py)), __dmul_rn(T.R12, d)), T.y);
-            const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R20, px), __dmul_rn(T.R21, py)), __dmul_rn(T.R22, d)), T.z);
-            const double iz = rcp_rn_normal(Z);                                       // AN:294 `1./Z`
-            const double tc = __dadd_rn(__dmul_rn(__dmul_rn(X, fx), iz), ox);
-            const double tr = __dadd_rn(__dmul_rn(__dmul_rn(Y, fy), iz), oy);
-            // C round(): half away from zero == trunc(x + copysign(0.5, x)) with the add rounded toward zero
-            const int tj = __double2int_rz(__dadd_rz(tc, copysign(0.5, tc)));
-            const int ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));
-            const double az = fabs(Z);
-            // strict depth bounds (AN:279-280); |Z| outside the normal range (incl. NaN / 0, where the
-            // reference's int cast is undefined) is out of bounds; saturated casts fail the range test
-            const bool ok = (min_depth < d) & (d < max_depth) & (az > 1e-300) & (az < 1e300) &
-                            ((unsigned)tj < (unsigned)cols) & ((unsigned)ti < (unsigned)rows);
-            if (ok) {
-              atomicMax(sWin + ti * cols + tj, ((unsigned)(i + 1) << 16) | i0);       // AN:358
-              valid |= 1ull << k;
-            }
-            c += dc; r += dr;
-            if (c >= cols) { c -= cols; ++r; }
+          // register prefetch: pixels of this trip (p*), of the next trip (q*), loads for the one after (f*)
+          double p0 = i < n ? __ldg(gD0 + i) : 0., p1 = i + BT < n ? __ldg(gD0 + i + BT) : 0.;
+          double q0 = i + 2 * BT < n ? __ldg(gD0 + i + 2 * BT) : 0., q1 = i + 3 * BT < n ? __ldg(gD0 + i + 3 * BT) : 0.;
+          unsigned u0 = i < n ? (unsigned)__ldg(gI0 + i) : 0u, u1 = i + BT < n ? (unsigned)__ldg(gI0 + i + BT) : 0u;
+          unsigned v0 = i + 2 * BT < n ? (unsigned)__ldg(gI0 + i + 2 * BT) : 0u, v1 = i + 3 * BT < n ? (unsigned)__ldg(gI0 + i + 3 * BT) : 0u;
+          for (; i < n; i += 2 * BT, k += 2) {
+            double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
+            if (i + 4 * BT < n) { f0 = __ldg(gD0 + i + 4 * BT); w0 = (unsigned)__ldg(gI0 + i + 4 * BT); }
+            if (i + 5 * BT < n) { f1 = __ldg(gD0 + i + 5 * BT); w1 = (unsigned)__ldg(gI0 + i + 5 * BT); }
+            const bool in1 = i + BT < n;
+            const WarpA a0 = warp_exact(T, tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, min_depth, max_depth, rows, cols);
+            const WarpA a1 = warp_exact(T, tb.cx[in1 ? c1 : 0], tb.ry[in1 ? r1 : 0], p1, fx, fy, ox, oy, inv_fx, inv_fy, min_depth, max_depth, rows, cols);
+            const bool ok1 = a1.ok & in1;
+            if (a0.ok) smem_red_max(sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);        // AN:358
+            if (ok1) smem_red_max(sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
+            valid |= ((unsigned long long)a0.ok << k) | ((unsigned long long)ok1 << (k + 1));
+            c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
+            c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
+            p0 = q0; p1 = q1; q0 = f0; q1 = f1; u0 = v0; u1 = v1; v0 = w0; v1 = w1;
           }
         }
         __syncthreads();
@@ -362,47 +448,35 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
 #pragma unroll
         for (int v = 0; v < 28; ++v) acc[v] = 0.;
         {
-          const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
-          int r = r_first, c = c_first, k = 0;
+          IterConst K;
+          K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy; K.rho = fy / fx;
+          int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
+          unsigned long long vm = valid;
           int i = tid;
-          double d_next = i < n ? __ldg(gD0 + i) : 0.;
-          for (; i < n; i += BT, ++k) {
-            const double d = d_next;
-            if (i + BT < n) d_next = __ldg(gD0 + i + BT);
-            const unsigned w = sWin[i];
+          double p0 = i < n ? __ldg(gD0 + i) : 0., p1 = i + BT < n ? __ldg(gD0 + i + BT) : 0.;
+          for (; i < n; i += 2 * BT) {
+            double f0 = 0., f1 = 0.;
+            if (i + 2 * BT < n) f0 = __ldg(gD0 + i + 2 * BT);
+            if (i + 3 * BT < n) f1 = __ldg(gD0 + i + 3 * BT);
+            const bool in1 = i + BT < n;
+            const int j1 = in1 ? i + BT : i;
+            const unsigned wa = sWin[i], wb = in1 ? sWin[j1] : 0u;
             sWin[i] = 0u;
-            double res = 0.;
-            if (w) {
-              // I = sum/1020: one rounding, within 2 ulp of the reference's convertTo + resize doubles
-              res = (double)((int)sI1[i] - (int)(w & 0xffffu)) * (1.0 / 1020.0);
-              acc[27] = fma(res, res, acc[27]);
-            }
-            if ((valid >> k) & 1ull) {
-              const double px = sCx[c] * d * inv_fx, py = sRy[r] * d * inv_fy;
-              const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
-              const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
-              const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
-              const double iz = rcp_1ulp(q2 + T.z);
-              const unsigned gw = sG[i];
-              // a = Gx1[i] * fx / Z', b = Gy1[i] * fy / Z'   (gradients at the SOURCE index, AN:346-347)
-              const double ga = (double)(short)(gw & 0xffffu) * gkfx * iz;
-              const double gb = (double)((int)gw >> 16) * gkfy * iz;
-              // closed form of AN:243-342, gradient folded in:
-              const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
-              const double B = q1 + T.y;
-              double J[6];
-              J[0] = ga;
-              J[1] = gb;
-              J[2] = -(fma(ga, A, gb * B) * iz);
-              J[3] = fma(gb, q0, -(ga * q1));
-              const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
-              J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
-              const double Zr = fma(T.R22, py, -(T.R21 * d));
-              J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
-              accumulate_row(acc, J, res);
-            }
-            c += dc; r += dr;
-            if (c >= cols) { c -= cols; ++r; }
+            if (in1) sWin[j1] = 0u;
+            const int ra = wa ? (int)sI1[i] - (int)(wa & 0xffffu) : 0;
+            const int rb = wb ? (int)sI1[j1] - (int)(wb & 0xffffu) : 0;
+            const double resa = (double)ra, resb = (double)rb;
+            double Ja[6], Jb[6];
+            jacobian_row<MODE>(K, tb, r0, c0, p0, (vm & 1ull) != 0, sG[i], Ja);
+            jacobian_row<MODE>(K, tb, in1 ? r1 : 0, in1 ? c1 : 0, p1, (vm & 2ull) != 0, sG[j1], Jb);
+            acc[27] = fma(resa, resa, acc[27]);
+            accumulate_row(acc, Ja, resa);
+            acc[27] = fma(resb, resb, acc[27]);
+            accumulate_row(acc, Jb, resb);
+            vm >>= 2;
+            c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
+            c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
+            p0 = f0; p1 = f1;
           }
         }
         // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
@@ -418,7 +492,7 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
           double tot = 0.;
 #pragma unroll
           for (int w = 0; w < NW; ++w) tot += sRed[w * 32 + lane];
-          warp_gn_step(tot, lane, bp, a, it, pair, sh, log);
+          warp_gn_step(tot * scale, lane, bp, a, it, pair, sh, log);
         }
         __syncthreads();
         if (sh->done) break;
@@ -435,7 +509,7 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
 
 size_t batch_align_smem_bytes(int nmax, int tabmax) {
   nmax = (nmax + 7) & ~7;
-  tabmax = (tabmax + 1) & ~1;
+  tabmax = (tabmax + 1) & ~1;   // doubles of lookup tables, see table_doubles()
   return (size_t)nmax * 10 + (size_t)tabmax * sizeof(double) + (size_t)NW * 32 * sizeof(double) + sizeof(BatchShared) + 64;
 }
 
@@ -462,7 +536,7 @@ int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, siz
   int nmax = 0, tabmax = 0;
   for (int a = 0; a < bp.num_active; ++a) {
     nmax = max(nmax, bp.lrows[a] * bp.lcols[a]);
-    tabmax = max(tabmax, bp.lrows[a] + bp.lcols[a]);
+    tabmax = max(tabmax, table_doubles(bp.lrows[a], bp.lcols[a]));
   }
   nmax = (nmax + 7) & ~7;
   tabmax = (tabmax + 1) & ~1;

@@ -120,7 +120,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     const int n = lr * lc;
     if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
     nmax = std::max(nmax, n);
-    tabmax = std::max(tabmax, lr + lc);
+    tabmax = std::max(tabmax, 2 * (lr + lc) + 4 * lc + 8 * lr);   // kernels_batch.cu table_doubles()
     bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
     bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
     bp->px_offset[a + 1] = bp->px_offset[a] + n;

@@ -41,7 +41,7 @@ int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8
 int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
                        const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log,
                        int32_t* log_counts, unsigned int* next_pair /* device counter, zero before the launch */);
-size_t batch_align_smem_bytes(int max_level_pixels, int max_rows_plus_cols);
+size_t batch_align_smem_bytes(int max_level_pixels, int max_table_doubles);
 cudaError_t batch_align_prepare(size_t smem_bytes);
 
 }  // namespace phovo
