@@ -79,12 +79,13 @@ class ClockSampler:
             try:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
                 reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                # power is a slow query: every 8th sample is enough for the maximum
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if len(self.samples) % 8 == 0 else 0.0
                 self.samples.append((sm, reasons, power))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def stop(self):
         self.stop_flag = True
@@ -115,7 +116,16 @@ def algorithmic_bytes(cfg, iters, rows, cols):
     return total_iter_bytes, setup
 
 
-def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False):
+DEPTH_SCALE = 1. / 5000.   # raw u16 sensor units -> metres (TUM convention, VisualOdometry.cpp:163)
+
+
+def quantise_depth(d_metres):
+    """metres -> raw u16 sensor units, the format both reference apps read from disk."""
+    import numpy as np
+    return np.clip(np.rint(d_metres * 5000.), 0, 65535).astype(np.uint16)
+
+
+def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False, depth="u16"):
     """The CPU arm: the oracle port of the reference's analytic path, `threads` independent
     single-threaded alignments at a time (the reference itself is single-threaded, OpenMP off)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -124,8 +134,12 @@ def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False):
     oracle_py.build()
     distinct = min(pairs, 32)          # rendering on the host is slow; the sample repeats 32 distinct pairs
     g0, d0, g1, _ = phovo.synth.make_batch(distinct, ROWS, COLS, K=K, seed0=0)
+    raw = quantise_depth(d0) if depth == "u16" else None
+    if raw is not None:
+        d0 = raw.astype(np.float64) * DEPTH_SCALE      # what the apps hand to SetSourceFrame (cv::Mat_<double>)
     reps = (pairs + distinct - 1) // distinct
     g0, d0, g1 = (np.tile(a, (reps, 1, 1))[:pairs] for a in (g0, d0, g1))
+    raw = np.tile(raw, (reps, 1, 1))[:pairs] if raw is not None else None
     cfg = oracle_py.Config.from_buffer_copy(bytes(phovo.configs.to_config(CONFIG, phovo.capi)))
     times, opt_times = [], []
     for s in range(warmup + steps):
@@ -135,7 +149,7 @@ def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False):
             opt_times.append(opt)
     wall = float(np.mean(times))
     return {"value": pairs / wall, "ms_per_step": wall * 1e3, "optimize_only_pairs_per_core_s": pairs / float(np.mean(opt_times)),
-            "states": st, "iters": it, "inputs": (g0, d0, g1)}
+            "states": st, "iters": it, "inputs": (g0, d0, g1), "raw_depth": raw}
 
 
 def main():
@@ -147,6 +161,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0: 2 per host thread, >= 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", default="u16", choices=["u16", "f32"],
+                    help="depth format at the boundary: raw u16 sensor units x 1/5000 m (what the reference apps read, default) or f32 metres")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -162,12 +178,12 @@ def main():
         if rank != 0:
             return 0
         pairs = args.cpu_pairs or max(64, 2 * host_threads)
-        r = cpu_reference(phovo, K, pairs, host_threads, args.steps, max(args.warmup, 1))
+        r = cpu_reference(phovo, K, pairs, host_threads, args.steps, max(args.warmup, 1), depth=args.depth)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "batched independent 640x480 pairs, %s, bounded sample" % CONFIG,
-                           "pairs_per_step": pairs, "rows": ROWS, "cols": COLS},
+                           "pairs_per_step": pairs, "rows": ROWS, "cols": COLS, "depth_dtype": args.depth},
                 "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": host_threads, "kind": "port",
                                  "sample": "%d pairs per step, %d threads x single-threaded alignments (SetSourceFrame+SetTargetFrame+Optimize), faithful cost structure (materialised Nx6 Jacobian, per-pass setZero)" % (pairs, host_threads)},
                 "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -191,13 +207,18 @@ def main():
 
     # ---- synthetic inputs (not timed): P pairs per rank, generated on the GPU, then mirrored to pinned host memory
     g0, d0, g1, xis = phovo.synth.render_batch_torch(P, ROWS, COLS, K, dev, seed0=rank * P)
+    depth_scale = 1.0
+    if args.depth == "u16":
+        # raw sensor units (values < 32768: the int16 tensor carries the same bits as u16)
+        d0 = torch.clamp(torch.round(d0.to(torch.float64) * 5000.), 0, 32767).to(torch.int16)
+        depth_scale = DEPTH_SCALE
     states = torch.zeros((P, 6), dtype=torch.float64, device=dev)
     iters = torch.zeros((P, phovo.MAXL), dtype=torch.int32, device=dev)
     gathered = torch.zeros((world * P, 6), dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize(dev)
 
     def step():
-        odo.BatchAlignDevice(g0, d0, g1, states, iters)
+        odo.BatchAlignDevice(g0, d0, g1, states, iters, depth_scale=depth_scale)
         if world > 1:
             dist.all_gather_into_tensor(gathered, states)     # the final pose gather
 
@@ -226,7 +247,7 @@ def main():
     launches = odo.LaunchCount() - launches0
     # per-kernel CUDA-event times (recorded inside the library on the same stream), one more step
     for _ in range(3):
-        odo.BatchAlignDevice(g0, d0, g1, states, iters)
+        odo.BatchAlignDevice(g0, d0, g1, states, iters, depth_scale=depth_scale)
         a, b = odo.BatchKernelTimes()
         pyr_ms.append(a); align_ms.append(b)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -243,14 +264,14 @@ def main():
     hg1 = torch.empty(g1.shape, dtype=g1.dtype, pin_memory=True); hg1.copy_(g1)
     torch.cuda.synchronize(dev)
     for _ in range(2):
-        st_e2e, it_e2e = odo.BatchAlign(hg0, hd0, hg1)
+        st_e2e, it_e2e = odo.BatchAlign(hg0, hd0, hg1, depth_scale=depth_scale)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
-        st_e2e, it_e2e = odo.BatchAlign(hg0, hd0, hg1)
+        st_e2e, it_e2e = odo.BatchAlign(hg0, hd0, hg1, depth_scale=depth_scale)
     e1.record(stream)
     barrier()
     wall_e2e = time.perf_counter() - t0
@@ -306,10 +327,13 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         pairs = args.cpu_pairs or max(64, 2 * host_threads)
-        r = cpu_reference(phovo, K, pairs, host_threads, 1, 0)
+        r = cpu_reference(phovo, K, pairs, host_threads, 1, 0, depth=args.depth)
         # same inputs through the GPU: iteration counts and poses must agree with the CPU port
         cg0, cd0, cg1 = r["inputs"]
-        st_chk, it_chk = odo.BatchAlign(cg0, cd0.astype(np.float32), cg1)
+        if args.depth == "u16":
+            st_chk, it_chk = odo.BatchAlign(cg0, r["raw_depth"], cg1, depth_scale=DEPTH_SCALE)
+        else:
+            st_chk, it_chk = odo.BatchAlign(cg0, cd0.astype(np.float32), cg1)
         iters_equal = bool(np.array_equal(it_chk, r["iters"]))
         pose_err = float(np.max(np.abs(st_chk - r["states"])))
         cpu = {"value": r["value"], "unit": "pairs/s", "cores": host_threads, "kind": "port",
@@ -320,7 +344,7 @@ def main():
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "batched independent 640x480 RGB-D pairs, %s (BASELINE configs[3]), %d pairs per GPU per step" % (CONFIG, P),
-                       "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "f32", "parallelism": "pairs sharded x%d, final pose all_gather" % world,
+                       "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "u16 raw x 1/5000 m" if args.depth == "u16" else "f32 metres", "parallelism": "pairs sharded x%d, final pose all_gather" % world,
                        "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (h2d / 1e9),
                        "mean_iterations_per_pair": {str(l): float(it_host[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0}},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
