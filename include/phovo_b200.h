@@ -222,6 +222,19 @@ int phovo_shard_begin_level(phovo_ctx* ctx, int level);          /* resets the i
 int phovo_shard_partial(phovo_ctx* ctx);                         /* K3a + K3b + local reduce -> buffer */
 int phovo_shard_step(phovo_ctx* ctx, int* done);                 /* solve + update + termination test */
 int phovo_shard_finish(phovo_ctx* ctx);                          /* read back state + stats */
+/* Fused exchange over NVLink peer memory (one process per GPU): every rank allocates an exchange
+ * area and exports its CUDA IPC handle (64 bytes); after importing every peer's handle,
+ * phovo_shard_partial_exchange() replaces phovo_shard_partial + the collective: the kernel that
+ * reduces the per-block partials stores this rank's 32 sums straight into every peer's area
+ * (st.global over NVLink), releases a flag, waits for the peers' flags and sums the `world` slots
+ * in rank order -- a one-shot all-reduce in the epilogue of the local reduction, bitwise identical
+ * on every rank.  A peer that never arrives makes the wait time out (error flag, PHOVO_E_CUDA
+ * from phovo_shard_step) instead of hanging the GPU. */
+#define PHOVO_IPC_HANDLE_BYTES 64
+#define PHOVO_SHARD_MAX_WORLD 8
+int phovo_shard_peer_export(phovo_ctx* ctx, void* handle_out /* PHOVO_IPC_HANDLE_BYTES */);
+int phovo_shard_peer_import(phovo_ctx* ctx, int peer_rank, const void* handle);
+int phovo_shard_partial_exchange(phovo_ctx* ctx);
 
 #ifdef __cplusplus
 }

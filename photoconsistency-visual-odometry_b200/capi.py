@@ -104,6 +104,9 @@ SIGNATURES = {
     "phovo_shard_partial": (C.c_int, [_vp]),
     "phovo_shard_step": (C.c_int, [_vp, _ip]),
     "phovo_shard_finish": (C.c_int, [_vp]),
+    "phovo_shard_peer_export": (C.c_int, [_vp, _vp]),
+    "phovo_shard_peer_import": (C.c_int, [_vp, C.c_int, _vp]),
+    "phovo_shard_partial_exchange": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -229,6 +229,51 @@ __global__ void __launch_bounds__(1024) k_reduce_to_buffer(const PoseDev* pose, 
   if (threadIdx.x < 32) buffer[threadIdx.x] = threadIdx.x < PHOVO_NACC ? totals[threadIdx.x] : 0.;
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused local reduction + one-shot all-reduce over NVLink peer memory (row-sharded single pair).
+// 1024 threads: warps 0..28 reduce the per-block partials (one value each, fixed order); then
+// thread (w, v) = (tid / 32, tid % 32), w < world, stores value v into peer w's slot
+// [parity][rank][v]; thread w*32 releases peer w's flag[rank] = epoch after a system-scope fence;
+// thread w < world acquires the local flag[w] >= epoch (bounded spin); finally thread v < 32 sums the
+// slots in rank order.  Two slot parities: a peer can be at most one exchange ahead.
+__global__ void __launch_bounds__(1024) k_reduce_exchange(const PoseDev* pose, const double* __restrict__ partials, int grid,
+                                                          double* __restrict__ buffer, ShardExchange* const* __restrict__ peers,
+                                                          int rank, int world, unsigned long long epoch) {
+  __shared__ double totals[32];
+  reduce_partials(partials, grid, totals);
+  const int w = threadIdx.x >> 5, v = threadIdx.x & 31;
+  const int parity = (int)(epoch & 1ull);
+  if (w < world) {
+    ShardExchange* peer = peers[w];
+    peer->slots[parity][rank][v] = v < PHOVO_NACC ? totals[v] : 0.;
+    __threadfence_system();
+    __syncwarp();
+    if (v == 0) st_release_sys(&peer->flags[rank], epoch);
+  }
+  ShardExchange* mine = peers[rank];
+  if (threadIdx.x < world) {
+    long long spins = 0;
+    while (ld_acquire_sys(&mine->flags[threadIdx.x]) < epoch) {
+      if (++spins > (1ll << 22)) { mine->error = 1; break; }   // seconds: a peer never arrived
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0.;
+    for (int r = 0; r < world; ++r) s += mine->slots[parity][r][threadIdx.x];
+    buffer[threadIdx.x] = s;
+  }
+}
+
 __global__ void k_solve_from_buffer(LevelParams L, PoseDev* pose, const double* buffer, phovo_iter_stats* log) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (pose->done) return;
@@ -307,6 +352,12 @@ int launch_reduce_only(cudaStream_t stream, const LevelParams& L, const PoseDev*
 
 int launch_reduce_to_buffer(cudaStream_t stream, const double* partials, int grid, double* buffer) {
   k_reduce_to_buffer<<<1, 1024, 0, stream>>>(nullptr, partials, grid, buffer);
+  return 1;
+}
+
+int launch_reduce_exchange(cudaStream_t stream, const PoseDev* pose, const double* partials, int grid, double* buffer,
+                           ShardExchange* const* peers_dev, int rank, int world, unsigned long long epoch) {
+  k_reduce_exchange<<<1, 1024, 0, stream>>>(pose, partials, grid, buffer, peers_dev, rank, world, epoch);
   return 1;
 }
 

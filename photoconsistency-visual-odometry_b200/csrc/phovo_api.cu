@@ -269,6 +269,9 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   cudaFree(ctx->stage_gray[0]); cudaFree(ctx->stage_gray[1]); cudaFree(ctx->stage_depth);
   cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_eval);
   cudaFree(ctx->dump_res); cudaFree(ctx->dump_jac);
+  for (int r = 0; r < 8; ++r)
+    if (ctx->xchg_opened[r]) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+  cudaFree(ctx->xchg_own); cudaFree(ctx->xchg_peers_dev);
   cudaFreeHost(ctx->h_pose); cudaFreeHost(ctx->h_log); cudaFreeHost(ctx->h_state_in); cudaFreeHost(ctx->h_eval);
   cudaEventDestroy(ctx->ev_copy);
   for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev_time[i]);
@@ -923,6 +926,61 @@ extern "C" int phovo_shard_partial(phovo_ctx* ctx) {
   return PHOVO_OK;
 }
 
+extern "C" int phovo_shard_peer_export(phovo_ctx* ctx, void* handle_out) {
+  if (!ctx || !handle_out) return PHOVO_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == PHOVO_IPC_HANDLE_BYTES, "IPC handle size");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xchg_own) {
+    CK(cudaMalloc((void**)&ctx->xchg_own, sizeof(ShardExchange)));
+    CK(cudaMemset(ctx->xchg_own, 0, sizeof(ShardExchange)));
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->xchg_own));
+  memcpy(handle_out, &h, sizeof(h));
+  ctx->xchg_peer[ctx->shard_rank] = ctx->xchg_own;
+  ctx->xchg_table_dirty = true;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_shard_peer_import(phovo_ctx* ctx, int peer_rank, const void* handle) {
+  if (!ctx || !handle || peer_rank < 0 || peer_rank >= PHOVO_SHARD_MAX_WORLD) return PHOVO_E_INVALID;
+  if (peer_rank == ctx->shard_rank) return PHOVO_OK;   // own area: no IPC round trip
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->xchg_opened[peer_rank]) { cudaIpcCloseMemHandle(ctx->xchg_peer[peer_rank]); ctx->xchg_opened[peer_rank] = false; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->xchg_peer[peer_rank] = (ShardExchange*)p;
+  ctx->xchg_opened[peer_rank] = true;
+  ctx->xchg_table_dirty = true;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_shard_partial_exchange(phovo_ctx* ctx) {
+  if (!ctx || ctx->shard_level < 0) return PHOVO_E_INVALID;
+  if (ctx->shard_world > PHOVO_SHARD_MAX_WORLD) return ctx->fail(PHOVO_E_UNSUPPORTED, "peer exchange supports up to 8 ranks");
+  for (int r = 0; r < ctx->shard_world; ++r)
+    if (!ctx->xchg_peer[r]) return ctx->fail(PHOVO_E_INVALID, "peer exchange areas are not all imported (phovo_shard_peer_export / _import)");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xchg_peers_dev) CK(cudaMalloc((void**)&ctx->xchg_peers_dev, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD));
+  if (ctx->xchg_table_dirty) {
+    CK(cudaMemcpyAsync(ctx->xchg_peers_dev, ctx->xchg_peer, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->xchg_table_dirty = false;
+  }
+  const LevelParams L = ctx->level_params(ctx->shard_level);
+  const LevelPtrs P = ctx->level_ptrs(ctx->shard_level);
+  int grid = 0;
+  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, nullptr, nullptr, false);
+  ctx->xchg_epoch += 1;
+  ctx->launches += launch_reduce_exchange(ctx->stream, ctx->d_pose, ctx->partials, grid, ctx->d_shard, ctx->xchg_peers_dev,
+                                          ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch);
+  CK(cudaGetLastError());
+  return PHOVO_OK;
+}
+
 extern "C" int phovo_shard_step(phovo_ctx* ctx, int* done) {
   if (!ctx || ctx->shard_level < 0) return PHOVO_E_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -940,5 +998,11 @@ extern "C" int phovo_shard_step(phovo_ctx* ctx, int* done) {
 extern "C" int phovo_shard_finish(phovo_ctx* ctx) {
   if (!ctx) return PHOVO_E_INVALID;
   CK(cudaSetDevice(ctx->device));
-  return read_back(ctx);
+  int rc = read_back(ctx);
+  if (ctx->xchg_own) {
+    int err = 0;
+    CK(cudaMemcpy(&err, &ctx->xchg_own->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return ctx->fail(PHOVO_E_CUDA, "peer exchange timed out waiting for another rank");
+  }
+  return rc;
 }

@@ -61,6 +61,13 @@ struct phovo_ctx {
   // row sharding
   int shard_rank = 0, shard_world = 1, shard_level = -1;
   double* d_shard = nullptr;
+  // fused peer-store exchange: own area (cudaMalloc, IPC-exported), peers' areas (IPC-opened)
+  phovo::ShardExchange* xchg_own = nullptr;
+  phovo::ShardExchange* xchg_peer[8] = {nullptr};
+  bool xchg_opened[8] = {false};
+  phovo::ShardExchange** xchg_peers_dev = nullptr;   // device copy of xchg_peer[]
+  bool xchg_table_dirty = true;
+  unsigned long long xchg_epoch = 0;
 
   // bookkeeping
   cudaEvent_t ev_copy = nullptr; cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -51,5 +51,18 @@ int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev*
                              phovo_iter_stats* log);
 int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
 
+// Exchange area of the fused peer-store all-reduce (one per rank, IPC-shared with the peers).
+struct ShardExchange {
+  double slots[2][8][32];              // [epoch parity][writer rank][value]
+  unsigned long long flags[8];         // flags[w] = last epoch rank w has delivered here
+  int error;                           // set when a wait timed out
+  int pad;
+};
+// totals of the local partials -> st.global into every peer's slots -> release flags -> wait for the
+// peers -> sum the `world` slots in rank order into `buffer` (32 doubles).
+int launch_reduce_exchange(cudaStream_t stream, const PoseDev* pose, const double* partials, int grid, double* buffer,
+                           ShardExchange* const* peers_dev /* device array [world] */, int rank, int world,
+                           unsigned long long epoch);
+
 }  // namespace phovo
 #endif

@@ -268,3 +268,15 @@ class CPhotoconsistencyOdometryCuda:
 
     def ShardFinish(self):
         self._check(self._L.phovo_shard_finish(self._h))
+
+    def ShardPeerExport(self):
+        """64-byte CUDA IPC handle of this rank's exchange area (bytes)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._L.phovo_shard_peer_export(self._h, buf))
+        return buf.raw
+
+    def ShardPeerImport(self, peer_rank, handle):
+        self._check(self._L.phovo_shard_peer_import(self._h, int(peer_rank), C.c_char_p(bytes(handle))))
+
+    def ShardPartialExchange(self):
+        self._check(self._L.phovo_shard_partial_exchange(self._h))
