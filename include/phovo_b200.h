@@ -202,6 +202,10 @@ int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows, int cols,
 int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable);
 int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int index, phovo_iter_stats* out);
 int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);
+/* test hooks of the batch kernel (results must not change): bit 0 = every pixel takes the exact
+ * reference warp instead of the estimate-then-verify shortcut; bit 1 = use the generic
+ * thread->pixel bookkeeping even when the CTA width is a multiple of the level width */
+int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags);
 int phovo_synchronize(phovo_ctx* ctx);
 /* device time (CUDA events on the context stream) of the two kernels of the last
  * phovo_batch_align_device call: pyramid (K1b) and align (K3-batch); blocks until they finished */

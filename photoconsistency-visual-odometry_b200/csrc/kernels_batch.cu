@@ -227,11 +227,11 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
 }
 
 // Per-level / per-iteration lookup tables in shared memory (doubles).  `cols`/`rows` of the level.
-//   exact  : cx[c] = fl(c - ox), ry[r] = fl(r - oy)            the reference's own roundings (AN:282-287), phase A
-//   ray    : cxi[c] = cx[c] * inv_fx, ryi[r] = ry[r] * inv_fy  back-projected ray (px/d, py/d), phase B and table builds
+//   exact  : cx[c] = fl(c - ox), ry[r] = fl(r - oy)            the reference's own roundings (AN:282-287)
+//   ray    : cxi[c] = cx[c] * inv_fx, ryi[r] = ry[r] * inv_fy  back-projected ray (px/d, py/d)
 //   colA/B : {R00 cxi, R10 cxi}, {R20 cxi, -cp cxi}            per ITERATION: the column part of R*(ray) and of dZ'/dpitch
-//   row    : {R01 ryi + R02, R11 ryi + R12, R21 ryi + R22, -(sp sr ryi + sp cr), R22 ryi - R21, R02 ryi - R01, R12 ryi - R11, 0}
-// so that in phase B  q = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
+//   row    : {R01 ryi + R02, R11 ryi + R12}, {R21 ryi + R22, -(sp sr ryi + sp cr)}, {R22 ryi - R21, R02 ryi - R01}, {R12 ryi - R11, 0}
+// so that  R p = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
 struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
@@ -241,27 +241,29 @@ __host__ __device__ inline int table_doubles(int rows, int cols) { return 2 * (r
 
 struct WarpA { int tj, ti; bool ok; };
 
-// Phase A of one pixel: AN:279-303 in fp64 with the reference's operation order and no FMA
-// contraction.  Straight-line code: no branches, so two pixels interleave in one basic block.
-__device__ __forceinline__ WarpA warp_exact(const Pose& T, double cx, double ry, double d, double fx, double fy, double ox, double oy,
-                                            double inv_fx, double inv_fy, double min_depth, double max_depth, int rows, int cols) {
+// The reference's warp of one pixel, AN:279-303: fp64, its operation order, no FMA contraction,
+// correctly rounded reciprocal, C round().  Used for the (rare) pixels whose cheap estimate falls
+// within 2^-17 px of a rounding boundary, and for everything when bp.exact_always is set.
+__device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double ry, double d, double fx, double fy, double ox, double oy,
+                                         double inv_fx, double inv_fy, int rows, int cols) {
+  Pose T;
+  pose_load(pose, T);
   const double px = __dmul_rn(__dmul_rn(cx, d), inv_fx);
   const double py = __dmul_rn(__dmul_rn(ry, d), inv_fy);
   const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R00, px), __dmul_rn(T.R01, py)), __dmul_rn(T.R02, d)), T.x);
   const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R10, px), __dmul_rn(T.R11, py)), __dmul_rn(T.R12, d)), T.y);
   const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.R20, px), __dmul_rn(T.R21, py)), __dmul_rn(T.R22, d)), T.z);
+  WarpA w;
+  const double az = fabs(Z);
+  // |Z| outside the normal range (incl. NaN / 0, where the reference's int cast is undefined) is out of bounds
+  if (!((az > 1e-300) & (az < 1e300))) { w.tj = -1; w.ti = -1; w.ok = false; return w; }
   const double iz = rcp_rn_normal(Z);                                       // AN:294 `1./Z`
   const double tc = __dadd_rn(__dmul_rn(__dmul_rn(X, fx), iz), ox);
   const double tr = __dadd_rn(__dmul_rn(__dmul_rn(Y, fy), iz), oy);
   // C round(): half away from zero == trunc(x + copysign(0.5, x)) with the add rounded toward zero
-  WarpA w;
   w.tj = __double2int_rz(__dadd_rz(tc, copysign(0.5, tc)));
   w.ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));
-  const double az = fabs(Z);
-  // strict depth bounds (AN:279-280); |Z| outside the normal range (incl. NaN / 0, where the
-  // reference's int cast is undefined) is out of bounds; saturated casts fail the range test
-  w.ok = (min_depth < d) & (d < max_depth) & (az > 1e-300) & (az < 1e300) &
-         ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);
+  w.ok = ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);   // saturated casts fail the range test
   return w;
 }
 
@@ -269,36 +271,226 @@ __device__ __forceinline__ void smem_red_max(unsigned addr, unsigned v) {
   asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-struct IterConst {          // per-iteration scalars phase B needs besides the tables
+struct IterConst {          // per-iteration scalars besides the tables
   double x, y, z, cy, sy, rho;
+  double fxs, fys, oxs, oys;   // fx 2^20, fy 2^20, (ox + 0.5) 2^20, (oy + 0.5) 2^20  (phase A fixed point)
 };
+
+struct ColRegs { double2 a, b; double cxi; };   // column entries of the tables for one pixel
+
+constexpr int kFracBits = 20;                 // fixed-point fraction bits of the estimated target coordinate
+constexpr unsigned kFracOne = 1u << kFracBits;
+
+// Phase A of one pixel, fast path.  Estimates the warped coordinate from the per-iteration tables
+// (error < 1e-9 px: ~15 roundings of 2^-53 on coordinates below 2^13) in 2^-20 px fixed point, as
+// floor(t + 0.5).  If the fraction is at least `guard` units (default 8 = 2^-17 px) away from both
+// ends the rounded pixel is certain and equals the reference's round(); otherwise `uncertain` is
+// set and the caller runs warp_exact.  Straight-line: two pixels interleave in one basic block.
+__device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double d,
+                                               int rows, int cols, unsigned guard, bool& uncertain) {
+  const double M0 = col.a.x + r0.x, M1 = col.a.y + r0.y, M2 = col.b.x + r1.x;
+  const double X = fma(d, M0, K.x), Y = fma(d, M1, K.y), Z = fma(d, M2, K.z);
+  const double iz = rcp_1ulp(Z);
+  const long long lx = __double2ll_rd(fma(X * K.fxs, iz, K.oxs));
+  const long long ly = __double2ll_rd(fma(Y * K.fys, iz, K.oys));
+  const unsigned fx_ = (unsigned)lx & (kFracOne - 1u), fy_ = (unsigned)ly & (kFracOne - 1u);
+  // exponent of Z must be ordinary, otherwise the estimate means nothing (0, denormal, huge, inf, NaN)
+  const unsigned ez = ((unsigned)__double2hiint(Z) >> 20) & 0x7ffu;
+  uncertain = (fx_ - guard > kFracOne - 2u * guard) | (fy_ - guard > kFracOne - 2u * guard) | (ez - 64u > 1900u);
+  const long long qx = lx >> kFracBits, qy = ly >> kFracBits;
+  WarpA w;
+  w.tj = (int)qx; w.ti = (int)qy;
+  w.ok = ((unsigned long long)qx < (unsigned long long)cols) & ((unsigned long long)qy < (unsigned long long)rows);
+  return w;
+}
 
 // Phase B of one pixel: J' = J / (gk fx) and the integer residual numerator; the common factors
 // are applied once per iteration to the reduced sums.  Everything is computed unconditionally on
 // sanitised operands and masked, so that two pixels interleave without branches.
 template <int MODE>
-__device__ __forceinline__ void jacobian_row(const IterConst& K, const Tables& tb, int r, int c, double d, bool valid, unsigned gw,
-                                             double J[6]) {
+__device__ __forceinline__ void jacobian_row(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double2 r2, double2 r3,
+                                             double d, bool valid, unsigned gw, double J[6]) {
   const double ds = valid ? d : 1.0;
-  const double2 ca = tb.colA[c], cb = tb.colB[c];
-  const double2 r0 = tb.row[4 * r + 0], r1 = tb.row[4 * r + 1], r2 = tb.row[4 * r + 2], r3 = tb.row[4 * r + 3];
-  const double q0 = ds * (ca.x + r0.x), q1 = ds * (ca.y + r0.y), q2 = ds * (cb.x + r1.x);
+  const double q0 = ds * (col.a.x + r0.x), q1 = ds * (col.a.y + r0.y), q2 = ds * (col.b.x + r1.x);
   const double Zs = q2 + K.z;
   const double iz = rcp_1ulp(valid ? Zs : 1.0);
   // a' = Gx1[i] / Z', b' = Gy1[i] (fy/fx) / Z'   (gradients at the SOURCE index, AN:346-347)
   const double ga = valid ? (double)(short)(gw & 0xffffu) * iz : 0.;
   const double gb = valid ? (double)((int)gw >> 16) * (iz * K.rho) : 0.;
   // closed form of AN:243-342, gradient folded in
-  const double A = MODE == 0 ? fma(ds * tb.cxi[c], K.x, q0) : q0 + K.x;   // AN:253 bug-compatible / Maxima-exact
+  const double A = MODE == 0 ? fma(ds * col.cxi, K.x, q0) : q0 + K.x;   // AN:253 bug-compatible / Maxima-exact
   const double B = q1 + K.y;
   J[0] = ga;
   J[1] = gb;
   J[2] = -(fma(ga, A, gb * B) * iz);
   J[3] = fma(gb, q0, -(ga * q1));
-  const double Zp = ds * (cb.y + r1.y);
+  const double Zp = ds * (col.b.y + r1.y);
   J[4] = fma(q2, fma(ga, K.cy, gb * K.sy), Zp * J[2]);
   const double Zr = ds * r2.x, t5a = ds * r2.y, t5b = ds * r3.x;
   J[5] = fma(ga, t5a, fma(gb, t5b, Zr * J[2]));
+}
+
+struct LevelCtx {
+  int rows, cols, n, a, pair;
+  const double* gD0; const unsigned short* gI0;
+  unsigned* sWin; const unsigned* sG; const unsigned short* sI1; double* sRed;
+  unsigned sWinAddr;
+  Tables tb;
+};
+
+// The Gauss-Newton loop of one level of one pair (AN:504-561).  COLFIX: the CTA width is a multiple
+// of the level width, so a thread's pixels t, t+BT, ... all lie in ONE column: the column entries
+// of the tables live in registers and only the row advances.  The thread -> pixel mapping is the
+// same linear one in both variants, so results are bitwise identical.
+template <int MODE, bool COLFIX>
+__device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rows = L.rows, cols = L.cols, n = L.n, a = L.a;
+  const Tables& tb = L.tb;
+  const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
+  const double min_depth = bp.min_depth, max_depth = bp.max_depth;
+  const int max_iters = bp.max_iters[a];
+  const unsigned guard = 8u;                     // 2^-17 px
+  const bool force_exact = bp.exact_always != 0;   // test hook: every pixel takes the exact path
+  // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT
+  const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
+  const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
+  const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
+  // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
+  const double gkfx = bp.grad_k[a] * fx;
+  const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
+  IterConst K;
+  K.rho = fy / fx;
+  K.fxs = fx * (double)kFracOne; K.fys = fy * (double)kFracOne;
+  K.oxs = (ox + 0.5) * (double)kFracOne; K.oys = (oy + 0.5) * (double)kFracOne;
+  const double my_cxi = COLFIX ? tb.cxi[c0_first] : 0., my_cx = COLFIX ? tb.cx[c0_first] : 0.;
+
+  for (int it = 0; it < max_iters; ++it) {
+    Pose T;
+    pose_load(&sh->pose, T);
+    K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy;
+    // ---- per-iteration tables ----
+    for (int k = tid; k < (COLFIX ? 0 : cols) + rows; k += BT) {
+      if (!COLFIX && k < cols) {
+        const double v = tb.cxi[k];
+        tb.colA[k] = make_double2(T.R00 * v, T.R10 * v);
+        tb.colB[k] = make_double2(T.R20 * v, -(T.cp * v));
+      } else {
+        const int r = COLFIX ? k : k - cols;
+        const double v = tb.ryi[r];
+        tb.row[4 * r + 0] = make_double2(fma(T.R01, v, T.R02), fma(T.R11, v, T.R12));
+        tb.row[4 * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
+        tb.row[4 * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
+        tb.row[4 * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
+      }
+    }
+    ColRegs mycol;
+    mycol.a = make_double2(T.R00 * my_cxi, T.R10 * my_cxi);
+    mycol.b = make_double2(T.R20 * my_cxi, -(T.cp * my_cxi));
+    mycol.cxi = my_cxi;
+    __syncthreads();
+    // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
+    unsigned long long valid = 0ull;
+    {
+      int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first, k = 0;
+      int i = tid;
+      // register prefetch: pixels of this trip (p*), of the next trip (q*), loads for the one after (f*)
+      double p0 = i < n ? __ldg(L.gD0 + i) : 0., p1 = i + BT < n ? __ldg(L.gD0 + i + BT) : 0.;
+      double q0 = i + 2 * BT < n ? __ldg(L.gD0 + i + 2 * BT) : 0., q1 = i + 3 * BT < n ? __ldg(L.gD0 + i + 3 * BT) : 0.;
+      unsigned u0 = i < n ? (unsigned)__ldg(L.gI0 + i) : 0u, u1 = i + BT < n ? (unsigned)__ldg(L.gI0 + i + BT) : 0u;
+      unsigned v0 = i + 2 * BT < n ? (unsigned)__ldg(L.gI0 + i + 2 * BT) : 0u, v1 = i + 3 * BT < n ? (unsigned)__ldg(L.gI0 + i + 3 * BT) : 0u;
+      for (; i < n; i += 2 * BT, k += 2) {
+        double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
+        if (i + 4 * BT < n) { f0 = __ldg(L.gD0 + i + 4 * BT); w0 = (unsigned)__ldg(L.gI0 + i + 4 * BT); }
+        if (i + 5 * BT < n) { f1 = __ldg(L.gD0 + i + 5 * BT); w1 = (unsigned)__ldg(L.gI0 + i + 5 * BT); }
+        const bool in1 = i + BT < n;
+        const int rr1 = in1 ? r1 : 0, cc1 = in1 ? c1 : 0;
+        ColRegs ca0 = mycol, ca1 = mycol;
+        if (!COLFIX) {
+          ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0];
+          ca1.a = tb.colA[cc1]; ca1.b = tb.colB[cc1];
+        }
+        bool unc0, unc1;
+        WarpA a0 = warp_estimate(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], p0, rows, cols, guard, unc0);
+        WarpA a1 = warp_estimate(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], p1, rows, cols, guard, unc1);
+        const bool dep0 = (min_depth < p0) & (p0 < max_depth);                 // strict bounds, AN:279-280
+        const bool dep1 = (min_depth < p1) & (p1 < max_depth) & in1;
+        if (dep0 & (unc0 | force_exact)) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+        if (dep1 & (unc1 | force_exact)) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[cc1], tb.ry[rr1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+        const bool ok0 = a0.ok & dep0, ok1 = a1.ok & dep1;
+        if (ok0) smem_red_max(L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);
+        if (ok1) smem_red_max(L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
+        valid |= ((unsigned long long)ok0 << k) | ((unsigned long long)ok1 << (k + 1));
+        if (COLFIX) { r0 += dr2; r1 += dr2; }
+        else {
+          c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
+          c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
+        }
+        p0 = q0; p1 = q1; q0 = f0; q1 = f1; u0 = v0; u1 = v1; v0 = w0; v1 = w1;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
+    double acc[28];
+#pragma unroll
+    for (int v = 0; v < 28; ++v) acc[v] = 0.;
+    {
+      int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
+      unsigned long long vm = valid;
+      int i = tid;
+      double p0 = i < n ? __ldg(L.gD0 + i) : 0., p1 = i + BT < n ? __ldg(L.gD0 + i + BT) : 0.;
+      for (; i < n; i += 2 * BT) {
+        double f0 = 0., f1 = 0.;
+        if (i + 2 * BT < n) f0 = __ldg(L.gD0 + i + 2 * BT);
+        if (i + 3 * BT < n) f1 = __ldg(L.gD0 + i + 3 * BT);
+        const bool in1 = i + BT < n;
+        const int j1 = in1 ? i + BT : i;
+        const int rr1 = in1 ? r1 : 0, cc1 = in1 ? c1 : 0;
+        const unsigned wa = L.sWin[i], wb = in1 ? L.sWin[j1] : 0u;
+        L.sWin[i] = 0u;
+        if (in1) L.sWin[j1] = 0u;
+        const int ra = wa ? (int)L.sI1[i] - (int)(wa & 0xffffu) : 0;
+        const int rb = wb ? (int)L.sI1[j1] - (int)(wb & 0xffffu) : 0;
+        const double resa = (double)ra, resb = (double)rb;
+        ColRegs ca0 = mycol, ca1 = mycol;
+        if (!COLFIX) {
+          ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0]; ca0.cxi = MODE == 0 ? tb.cxi[c0] : 0.;
+          ca1.a = tb.colA[cc1]; ca1.b = tb.colB[cc1]; ca1.cxi = MODE == 0 ? tb.cxi[cc1] : 0.;
+        }
+        double Ja[6], Jb[6];
+        jacobian_row<MODE>(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], tb.row[4 * r0 + 2], tb.row[4 * r0 + 3], p0, (vm & 1ull) != 0, L.sG[i], Ja);
+        jacobian_row<MODE>(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], tb.row[4 * rr1 + 2], tb.row[4 * rr1 + 3], p1, (vm & 2ull) != 0, L.sG[j1], Jb);
+        acc[27] = fma(resa, resa, acc[27]);
+        accumulate_row(acc, Ja, resa);
+        acc[27] = fma(resb, resb, acc[27]);
+        accumulate_row(acc, Jb, resb);
+        vm >>= 2;
+        if (COLFIX) { r0 += dr2; r1 += dr2; }
+        else {
+          c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
+          c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
+        }
+        p0 = f0; p1 = f1;
+      }
+    }
+    // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
+    {
+      double x[32];
+#pragma unroll
+      for (int v = 0; v < 28; ++v) x[v] = acc[v];
+      x[28] = (double)__popcll(valid); x[29] = 0.; x[30] = 0.; x[31] = 0.;
+      L.sRed[wid * 32 + lane] = warp_transpose_sum(x, lane);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      double tot = 0.;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) tot += L.sRed[w * 32 + lane];
+      warp_gn_step(tot * scale, lane, bp, a, it, L.pair, sh, log);
+    }
+    __syncthreads();
+    if (sh->done) break;
+  }
 }
 
 // K3-batch.  Persistent CTAs fetch pairs from a global counter (iteration counts differ between
@@ -326,8 +518,7 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
   double* sTab = (double*)(sI1 + nmax);
   double* sRed = sTab + tabmax;
   BatchShared* sh = (BatchShared*)(sRed + NW * 32);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
+  const int tid = threadIdx.x;
 
   for (;;) {
     __syncthreads();   // the previous pair's outputs have been read from shared memory
@@ -350,15 +541,19 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
     const uint8_t* rec = store + (size_t)pair * bp.record_bytes;
 
     for (int a = 0; a < bp.num_active; ++a) {
+      LevelCtx L;
       const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
-      const double* __restrict__ gD0 = (const double*)(rec + bp.off_D0[a]);
-      const unsigned short* __restrict__ gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
-      Tables tb;
+      L.rows = rows; L.cols = cols; L.n = n; L.a = a; L.pair = pair;
+      L.gD0 = (const double*)(rec + bp.off_D0[a]);
+      L.gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
+      L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
+      L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
+      Tables& tb = L.tb;
       tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
       tb.cx = (double*)(tb.row + 4 * rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
-      const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
       {
         // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
+        const double ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
         const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
         uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
         const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
@@ -369,15 +564,10 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
       }
       if (tid == 0) { sh->done = 0; sh->iteration = 0; }
       __syncthreads();
-      // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT: both (r, c) pairs
-      // advance by the fixed step of 2*BT pixels -- no division in the loops
-      const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
-      const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
-      const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
       {
         // Scharr numerators of I1 (AN:181-187), reflect-101: |gx|,|gy| <= 16 * 1020 fits s16
         const int dr = BT / cols, dc = BT - dr * cols;
-        int r = r0_first, c = c0_first;
+        int r = tid / cols, c = tid - r * cols;
         for (int i = tid; i < n; i += BT) {
           const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
           const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
@@ -390,113 +580,9 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
           if (c >= cols) { c -= cols; ++r; }
         }
       }
-      __syncthreads();
-
-      const double min_depth = bp.min_depth, max_depth = bp.max_depth;
-      const int max_iters = bp.max_iters[a];
-      // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
-      const double gkfx = bp.grad_k[a] * fx;
-      const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
-
-      for (int it = 0; it < max_iters; ++it) {
-        Pose T;
-        pose_load(&sh->pose, T);
-        // ---- per-iteration tables for phase B (read after the barrier that ends phase A) ----
-        for (int k = tid; k < cols + rows; k += BT) {
-          if (k < cols) {
-            const double v = tb.cxi[k];
-            tb.colA[k] = make_double2(T.R00 * v, T.R10 * v);
-            tb.colB[k] = make_double2(T.R20 * v, -(T.cp * v));
-          } else {
-            const int r = k - cols;
-            const double v = tb.ryi[r];
-            tb.row[4 * r + 0] = make_double2(fma(T.R01, v, T.R02), fma(T.R11, v, T.R12));
-            tb.row[4 * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
-            tb.row[4 * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
-            tb.row[4 * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
-          }
-        }
-        // ---- phase A: warp every source pixel and bid for its target slot ----
-        unsigned long long valid = 0ull;
-        {
-          int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first, k = 0;
-          int i = tid;
-          // register prefetch: pixels of this trip (p*), of the next trip (q*), loads for the one after (f*)
-          double p0 = i < n ? __ldg(gD0 + i) : 0., p1 = i + BT < n ? __ldg(gD0 + i + BT) : 0.;
-          double q0 = i + 2 * BT < n ? __ldg(gD0 + i + 2 * BT) : 0., q1 = i + 3 * BT < n ? __ldg(gD0 + i + 3 * BT) : 0.;
-          unsigned u0 = i < n ? (unsigned)__ldg(gI0 + i) : 0u, u1 = i + BT < n ? (unsigned)__ldg(gI0 + i + BT) : 0u;
-          unsigned v0 = i + 2 * BT < n ? (unsigned)__ldg(gI0 + i + 2 * BT) : 0u, v1 = i + 3 * BT < n ? (unsigned)__ldg(gI0 + i + 3 * BT) : 0u;
-          for (; i < n; i += 2 * BT, k += 2) {
-            double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
-            if (i + 4 * BT < n) { f0 = __ldg(gD0 + i + 4 * BT); w0 = (unsigned)__ldg(gI0 + i + 4 * BT); }
-            if (i + 5 * BT < n) { f1 = __ldg(gD0 + i + 5 * BT); w1 = (unsigned)__ldg(gI0 + i + 5 * BT); }
-            const bool in1 = i + BT < n;
-            const WarpA a0 = warp_exact(T, tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, min_depth, max_depth, rows, cols);
-            const WarpA a1 = warp_exact(T, tb.cx[in1 ? c1 : 0], tb.ry[in1 ? r1 : 0], p1, fx, fy, ox, oy, inv_fx, inv_fy, min_depth, max_depth, rows, cols);
-            const bool ok1 = a1.ok & in1;
-            if (a0.ok) smem_red_max(sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);        // AN:358
-            if (ok1) smem_red_max(sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
-            valid |= ((unsigned long long)a0.ok << k) | ((unsigned long long)ok1 << (k + 1));
-            c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
-            c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
-            p0 = q0; p1 = q1; q0 = f0; q1 = f1; u0 = v0; u1 = v1; v0 = w0; v1 = w1;
-          }
-        }
-        __syncthreads();
-        // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
-        double acc[28];
-#pragma unroll
-        for (int v = 0; v < 28; ++v) acc[v] = 0.;
-        {
-          IterConst K;
-          K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy; K.rho = fy / fx;
-          int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
-          unsigned long long vm = valid;
-          int i = tid;
-          double p0 = i < n ? __ldg(gD0 + i) : 0., p1 = i + BT < n ? __ldg(gD0 + i + BT) : 0.;
-          for (; i < n; i += 2 * BT) {
-            double f0 = 0., f1 = 0.;
-            if (i + 2 * BT < n) f0 = __ldg(gD0 + i + 2 * BT);
-            if (i + 3 * BT < n) f1 = __ldg(gD0 + i + 3 * BT);
-            const bool in1 = i + BT < n;
-            const int j1 = in1 ? i + BT : i;
-            const unsigned wa = sWin[i], wb = in1 ? sWin[j1] : 0u;
-            sWin[i] = 0u;
-            if (in1) sWin[j1] = 0u;
-            const int ra = wa ? (int)sI1[i] - (int)(wa & 0xffffu) : 0;
-            const int rb = wb ? (int)sI1[j1] - (int)(wb & 0xffffu) : 0;
-            const double resa = (double)ra, resb = (double)rb;
-            double Ja[6], Jb[6];
-            jacobian_row<MODE>(K, tb, r0, c0, p0, (vm & 1ull) != 0, sG[i], Ja);
-            jacobian_row<MODE>(K, tb, in1 ? r1 : 0, in1 ? c1 : 0, p1, (vm & 2ull) != 0, sG[j1], Jb);
-            acc[27] = fma(resa, resa, acc[27]);
-            accumulate_row(acc, Ja, resa);
-            acc[27] = fma(resb, resb, acc[27]);
-            accumulate_row(acc, Jb, resb);
-            vm >>= 2;
-            c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
-            c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
-            p0 = f0; p1 = f1;
-          }
-        }
-        // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
-        {
-          double x[32];
-#pragma unroll
-          for (int v = 0; v < 28; ++v) x[v] = acc[v];
-          x[28] = (double)__popcll(valid); x[29] = 0.; x[30] = 0.; x[31] = 0.;
-          sRed[wid * 32 + lane] = warp_transpose_sum(x, lane);
-        }
-        __syncthreads();
-        if (wid == 0) {
-          double tot = 0.;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) tot += sRed[w * 32 + lane];
-          warp_gn_step(tot * scale, lane, bp, a, it, pair, sh, log);
-        }
-        __syncthreads();
-        if (sh->done) break;
-      }
+      // (the first barrier inside gn_level orders these writes before the pixel loops)
+      if (BT % cols == 0 && !bp.force_generic) gn_level<MODE, true>(bp, L, sh, log);
+      else gn_level<MODE, false>(bp, L, sh, log);
       if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + bp.level[a]] = sh->iteration;
     }
     __syncthreads();

@@ -29,6 +29,7 @@ struct phovo_batch_state {
   std::vector<phovo_iter_stats> h_log; std::vector<int32_t> h_log_counts;
   int log_per_pair = 0; int last_pairs = 0; bool log_fetched = false;
   bool record_stats = false;
+  int debug_flags = 0;
   // staging for host inputs: two slots
   uint8_t* stage_g0[2] = {nullptr, nullptr}; uint8_t* stage_g1[2] = {nullptr, nullptr}; char* stage_d[2] = {nullptr, nullptr};
   size_t stage_cap_g[2] = {0, 0}, stage_cap_g1[2] = {0, 0}, stage_cap_d[2] = {0, 0};
@@ -107,6 +108,8 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   memset(bp, 0, sizeof(*bp));
   bp->num_pairs = num_pairs; bp->rows = rows; bp->cols = cols;
   bp->mode = ctx->cfg.mode; bp->log_cap = log_cap;
+  bp->exact_always = ctx->batch ? (ctx->batch->debug_flags & 1) : 0;
+  bp->force_generic = ctx->batch ? ((ctx->batch->debug_flags >> 1) & 1) : 0;
   bp->min_depth = ctx->cfg.min_depth; bp->max_depth = ctx->cfg.max_depth;
   int a = 0, nmax = 0, tabmax = 0;
   unsigned long long off = 0;
@@ -191,6 +194,14 @@ extern "C" int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable) {
   phovo_batch_state* b; int rc = get_state(ctx, &b);
   if (rc) return rc;
   b->record_stats = enable != 0;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags) {
+  if (!ctx) return PHOVO_E_INVALID;
+  phovo_batch_state* b; int rc = get_state(ctx, &b);
+  if (rc) return rc;
+  b->debug_flags = flags;
   return PHOVO_OK;
 }
 

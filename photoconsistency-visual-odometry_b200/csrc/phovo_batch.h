@@ -9,7 +9,7 @@
 
 namespace phovo {
 
-constexpr int kBatchThreads = 384;          // 12 warps, up to 168 registers per thread
+constexpr int kBatchThreads = 480;          // 15 warps, 128 registers per thread; 480 is a multiple of the level widths 160 / 80 / 40 / 20 (640x480) and 240 / 120 / 60 (8K, 960-wide)
 constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + tables + scratch must fit 227 KB (checked exactly
                                             // by the host); also <= 64 * kBatchThreads (validity mask) and < 65535
 
@@ -19,6 +19,8 @@ struct BatchParams {
   int num_active;                       // active levels, coarse -> fine
   int mode;
   int log_cap;                          // per-pair stats slots (0: do not record)
+  int exact_always;                     // test hook: every pixel takes the exact warp (no estimate shortcut)
+  int force_generic;                    // test hook: generic (r, c) bookkeeping even when BT % cols == 0
   int level[PHOVO_MAX_LEVELS];          // pyramid level index of active level a
   int lrows[PHOVO_MAX_LEVELS], lcols[PHOVO_MAX_LEVELS];
   int max_iters[PHOVO_MAX_LEVELS];

@@ -226,6 +226,10 @@ class CPhotoconsistencyOdometryCuda:
     def BatchSetRecordStats(self, enable):
         self._check(self._L.phovo_batch_set_record_stats(self._h, int(enable)))
 
+    def BatchSetDebugFlags(self, flags):
+        """bit 0: exact warp for every pixel; bit 1: generic pixel bookkeeping (results must not change)."""
+        self._check(self._L.phovo_batch_set_debug_flags(self._h, int(flags)))
+
     def BatchIterationStats(self, pair):
         out = []
         for i in range(self._L.phovo_batch_num_iter_stats(self._h, pair)):

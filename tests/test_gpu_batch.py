@@ -98,6 +98,44 @@ def test_batch_odd_size_and_u16_depth(phovo, oracle):
         assert_pose_close(st[p], ost[p])
 
 
+@pytest.mark.parametrize("shape,cfg_name", [((480, 640), "config_4_level_optimization_analytic"),
+                                            ((93, 141), "test_3_level_all_active"),
+                                            ((120, 160), "test_3_level_all_active")])
+def test_batch_shortcuts_do_not_change_results(phovo, shape, cfg_name):
+    """The estimate-then-verify warp and the column-fixed bookkeeping are pure optimisations: with
+    either switched off (exact reference warp for EVERY pixel / generic bookkeeping) states,
+    iteration counts and every logged normal equation are bitwise the same."""
+    K = phovo.synth.K_FRAME_ALIGNMENT.copy()
+    K[:2] *= shape[1] / 640.
+    P = 4
+    g0, d0, g1, _ = phovo.synth.make_batch(P, shape[0], shape[1], K=K, seed0=400)
+    cfg = phovo.configs.to_config(cfg_name, phovo.capi)
+    if shape == (120, 160):
+        cfg.max_num_iterations[0] = 0        # 120x160 = 19 200 px fits; keep level 0 out to stay small
+    odo = make_odo(phovo, cfg, K)
+    odo.BatchSetRecordStats(True)
+    runs = []
+    for flags in (0, 1, 2, 3):
+        odo.BatchSetDebugFlags(flags)
+        try:
+            st, it = odo.BatchAlign(g0, d0.astype(np.float32), g1)
+        except phovo.PhovoError as e:
+            assert e.code == phovo.capi.E_UNSUPPORTED
+            pytest.skip("level does not fit the batch kernel")
+        logs = [odo.BatchIterationStats(p) for p in range(P)]
+        runs.append((st, it, logs))
+    odo.BatchSetDebugFlags(0)
+    st0, it0, logs0 = runs[0]
+    assert it0.sum() > 0
+    for st, it, logs in runs[1:]:
+        assert np.array_equal(st, st0) and np.array_equal(it, it0)
+        for la, lb in zip(logs, logs0):
+            assert len(la) == len(lb)
+            for a, b in zip(la, lb):
+                assert a["num_valid"] == b["num_valid"]
+                assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"])
+
+
 def test_batch_unsupported_configurations_fail_loudly(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)
