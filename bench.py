@@ -281,7 +281,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * P * e2e_steps / (float(te.item()) * 1e-3)
     assert np.array_equal(st_e2e, st_host), "host-buffer path and device-resident path disagree"
-    h2d = P * (2 * ROWS * COLS + ROWS * COLS * d0.element_size())
+    h2d_full = P * (2 * ROWS * COLS + ROWS * COLS * d0.element_size())
+    h2d = odo.BatchLastH2DBytes()          # counted by the library from the copies it issued
     d2h = P * (6 * 8 + phovo.MAXL * 4)
 
     if rank != 0:
@@ -345,7 +346,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "batched independent 640x480 RGB-D pairs, %s (BASELINE configs[3]), %d pairs per GPU per step" % (CONFIG, P),
                        "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "u16 raw x 1/5000 m" if args.depth == "u16" else "f32 metres", "parallelism": "pairs sharded x%d, final pose all_gather" % world,
-                       "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (h2d / 1e9),
+                       "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (h2d_full / 1e9),
+                       "e2e_upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe" % (h2d, h2d_full),
                        "mean_iterations_per_pair": {str(l): float(it_host[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0}},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te.item()) / e2e_steps, "steps": e2e_steps},

@@ -206,6 +206,10 @@ int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);
  * reference warp instead of the estimate-then-verify shortcut; bit 1 = use the generic
  * thread->pixel bookkeeping even when the CTA width is a multiple of the level width */
 int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags);
+/* bytes the last phovo_batch_align call copied host -> device.  Host batches are uploaded without
+ * the source rows no active pyramid level reads (the levels are point-decimated from the original
+ * image, AN:132), so this can be less than the size of the inputs. */
+int phovo_batch_get_last_h2d_bytes(const phovo_ctx* ctx, unsigned long long* bytes);
 int phovo_synchronize(phovo_ctx* ctx);
 /* device time (CUDA events on the context stream) of the two kernels of the last
  * phovo_batch_align_device call: pyramid (K1b) and align (K3-batch); blocks until they finished */

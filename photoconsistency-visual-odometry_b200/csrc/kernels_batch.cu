@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
   const int level = bp.level[a];
   const double scale = (double)(1 << level);
   const size_t pair = blockIdx.y;
-  const size_t frame = (size_t)bp.rows * bp.cols;
+  // staged host inputs may carry only the source rows the active levels read (see phovo_batch.cu):
+  // row y of a frame then lives at compact row (y / period) * keep + (y % period - keep_begin)
+  const int period = bp.src_period;
+  const size_t frame = period ? (size_t)(bp.rows / period) * bp.src_keep * bp.cols : (size_t)bp.rows * bp.cols;
   const uint8_t* G0 = gray0 + pair * frame;
   const uint8_t* G1 = gray1 + pair * frame;
   const DT* D = depth0 + pair * frame;
@@ -68,10 +71,16 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
   linear_axis(y, scale, bp.rows, false, sy, fy);
   const int y0 = min(max(sy, 0), bp.rows - 1), y1 = min(max(sy + 1, 0), bp.rows - 1);
   const bool two = sx + 1 < bp.cols;
-  const size_t o00 = (size_t)y0 * bp.cols + sx, o10 = (size_t)y1 * bp.cols + sx;
+  const int z0 = period ? (y0 / period) * bp.src_keep + (y0 % period - bp.src_keep_begin) : y0;
+  const int z1 = period ? (y1 / period) * bp.src_keep + (y1 % period - bp.src_keep_begin) : y1;
+  const size_t o00 = (size_t)z0 * bp.cols + sx, o10 = (size_t)z1 * bp.cols + sx;
   unsigned s0, s1;
   double dv;
-  if (two) {
+  if (level == 0) {  // the image itself: one tap with weight one (value = 4 v / 1020 = v / 255)
+    s0 = 4u * (unsigned)__ldg(G0 + o00);
+    s1 = 4u * (unsigned)__ldg(G1 + o00);
+    dv = depth_at<DT>(D + o00, depth_scale);
+  } else if (two) {
     s0 = (unsigned)__ldg(G0 + o00) + __ldg(G0 + o00 + 1) + __ldg(G0 + o10) + __ldg(G0 + o10 + 1);
     s1 = (unsigned)__ldg(G1 + o00) + __ldg(G1 + o00 + 1) + __ldg(G1 + o10) + __ldg(G1 + o10 + 1);
     const double a0 = (double)(1.f - fx), a1 = (double)fx;
@@ -278,30 +287,36 @@ struct IterConst {          // per-iteration scalars besides the tables
 
 struct ColRegs { double2 a, b; double cxi; };   // column entries of the tables for one pixel
 
-constexpr int kFracBits = 20;                 // fixed-point fraction bits of the estimated target coordinate
+constexpr int kFracBits = 14;                 // fixed-point fraction bits of the estimated target coordinate
 constexpr unsigned kFracOne = 1u << kFracBits;
 
 // Phase A of one pixel, fast path.  Estimates the warped coordinate from the per-iteration tables
-// (error < 1e-9 px: ~15 roundings of 2^-53 on coordinates below 2^13) in 2^-20 px fixed point, as
-// floor(t + 0.5).  If the fraction is at least `guard` units (default 8 = 2^-17 px) away from both
-// ends the rounded pixel is certain and equals the reference's round(); otherwise `uncertain` is
-// set and the caller runs warp_exact.  Straight-line: two pixels interleave in one basic block.
+// (error < 1e-9 px: ~15 roundings of 2^-53 on coordinates below 2^16) as floor((t + 0.5) 2^14) in a
+// 32-bit integer.  If the 14-bit fraction is neither 0 nor 2^14 - 1 the estimate is at least
+// 2^-14 px away from a rounding boundary, so the rounded pixel is certain and equals the
+// reference's round() (also for t in (-0.5, 0), which round() maps to -0 -> column 0); otherwise
+// `uncertain` is set and the caller runs warp_exact.  Saturated conversions (|t| >= 2^17, inf) land
+// out of bounds, NaN converts to 0 and is therefore uncertain.  Straight-line code.
 __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double d,
-                                               int rows, int cols, unsigned guard, bool& uncertain) {
+                                               int rows, int cols, bool& uncertain) {
   const double M0 = col.a.x + r0.x, M1 = col.a.y + r0.y, M2 = col.b.x + r1.x;
   const double X = fma(d, M0, K.x), Y = fma(d, M1, K.y), Z = fma(d, M2, K.z);
   const double iz = rcp_1ulp(Z);
-  const long long lx = __double2ll_rd(fma(X * K.fxs, iz, K.oxs));
-  const long long ly = __double2ll_rd(fma(Y * K.fys, iz, K.oys));
+  const int lx = __double2int_rd(fma(X * K.fxs, iz, K.oxs));
+  const int ly = __double2int_rd(fma(Y * K.fys, iz, K.oys));
   const unsigned fx_ = (unsigned)lx & (kFracOne - 1u), fy_ = (unsigned)ly & (kFracOne - 1u);
   // exponent of Z must be ordinary, otherwise the estimate means nothing (0, denormal, huge, inf, NaN)
   const unsigned ez = ((unsigned)__double2hiint(Z) >> 20) & 0x7ffu;
-  uncertain = (fx_ - guard > kFracOne - 2u * guard) | (fy_ - guard > kFracOne - 2u * guard) | (ez - 64u > 1900u);
-  const long long qx = lx >> kFracBits, qy = ly >> kFracBits;
+  uncertain = (fx_ - 1u >= kFracOne - 2u) | (fy_ - 1u >= kFracOne - 2u) | (ez - 64u > 1900u);
   WarpA w;
-  w.tj = (int)qx; w.ti = (int)qy;
-  w.ok = ((unsigned long long)qx < (unsigned long long)cols) & ((unsigned long long)qy < (unsigned long long)rows);
+  w.tj = lx >> kFracBits; w.ti = ly >> kFracBits;
+  w.ok = ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);
   return w;
+}
+
+// predicated shared-memory max: no branch, so the surrounding block stays straight-line
+__device__ __forceinline__ void smem_red_max_if(bool p, unsigned addr, unsigned v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.max.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((unsigned)p) : "memory");
 }
 
 // Phase B of one pixel: J' = J / (gk fx) and the integer residual numerator; the common factors
@@ -310,13 +325,15 @@ __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs
 template <int MODE>
 __device__ __forceinline__ void jacobian_row(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double2 r2, double2 r3,
                                              double d, bool valid, unsigned gw, double J[6]) {
-  const double ds = valid ? d : 1.0;
+  // an invalid pixel contributes a zero row: depth and 1/Z' are forced to 0 (the raw values may be
+  // 0, inf or NaN), everything downstream is then finite and multiplied by zero
+  const double ds = valid ? d : 0.;
   const double q0 = ds * (col.a.x + r0.x), q1 = ds * (col.a.y + r0.y), q2 = ds * (col.b.x + r1.x);
-  const double Zs = q2 + K.z;
-  const double iz = rcp_1ulp(valid ? Zs : 1.0);
+  const double izr = rcp_1ulp(q2 + K.z);
+  const double iz = valid ? izr : 0.;
   // a' = Gx1[i] / Z', b' = Gy1[i] (fy/fx) / Z'   (gradients at the SOURCE index, AN:346-347)
-  const double ga = valid ? (double)(short)(gw & 0xffffu) * iz : 0.;
-  const double gb = valid ? (double)((int)gw >> 16) * (iz * K.rho) : 0.;
+  const double ga = (double)(short)(gw & 0xffffu) * iz;
+  const double gb = (double)((int)gw >> 16) * (iz * K.rho);
   // closed form of AN:243-342, gradient folded in
   const double A = MODE == 0 ? fma(ds * col.cxi, K.x, q0) : q0 + K.x;   // AN:253 bug-compatible / Maxima-exact
   const double B = q1 + K.y;
@@ -350,7 +367,6 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
   const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
   const double min_depth = bp.min_depth, max_depth = bp.max_depth;
   const int max_iters = bp.max_iters[a];
-  const unsigned guard = 8u;                     // 2^-17 px
   const bool force_exact = bp.exact_always != 0;   // test hook: every pixel takes the exact path
   // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT
   const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
@@ -363,6 +379,7 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
   K.rho = fy / fx;
   K.fxs = fx * (double)kFracOne; K.fys = fy * (double)kFracOne;
   K.oxs = (ox + 0.5) * (double)kFracOne; K.oys = (oy + 0.5) * (double)kFracOne;
+  const int trips = (n - tid + 2 * BT - 1) / (2 * BT);   // loop trips of this thread (0 if tid >= n)
   const double my_cxi = COLFIX ? tb.cxi[c0_first] : 0., my_cx = COLFIX ? tb.cx[c0_first] : 0.;
 
   for (int it = 0; it < max_iters; ++it) {
@@ -392,17 +409,16 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
     // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
     unsigned long long valid = 0ull;
     {
-      int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first, k = 0;
+      int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
       int i = tid;
-      // register prefetch: pixels of this trip (p*), of the next trip (q*), loads for the one after (f*)
+      // register prefetch: the loads of the next trip are issued at the top of the current one
       double p0 = i < n ? __ldg(L.gD0 + i) : 0., p1 = i + BT < n ? __ldg(L.gD0 + i + BT) : 0.;
-      double q0 = i + 2 * BT < n ? __ldg(L.gD0 + i + 2 * BT) : 0., q1 = i + 3 * BT < n ? __ldg(L.gD0 + i + 3 * BT) : 0.;
       unsigned u0 = i < n ? (unsigned)__ldg(L.gI0 + i) : 0u, u1 = i + BT < n ? (unsigned)__ldg(L.gI0 + i + BT) : 0u;
-      unsigned v0 = i + 2 * BT < n ? (unsigned)__ldg(L.gI0 + i + 2 * BT) : 0u, v1 = i + 3 * BT < n ? (unsigned)__ldg(L.gI0 + i + 3 * BT) : 0u;
-      for (; i < n; i += 2 * BT, k += 2) {
+      unsigned vhi = 0u, vlo = 0u;     // validity bits enter at the top and shift down: bit k of `valid` = pixel k
+      for (; i < n; i += 2 * BT) {
         double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
-        if (i + 4 * BT < n) { f0 = __ldg(L.gD0 + i + 4 * BT); w0 = (unsigned)__ldg(L.gI0 + i + 4 * BT); }
-        if (i + 5 * BT < n) { f1 = __ldg(L.gD0 + i + 5 * BT); w1 = (unsigned)__ldg(L.gI0 + i + 5 * BT); }
+        if (i + 2 * BT < n) { f0 = __ldg(L.gD0 + i + 2 * BT); w0 = (unsigned)__ldg(L.gI0 + i + 2 * BT); }
+        if (i + 3 * BT < n) { f1 = __ldg(L.gD0 + i + 3 * BT); w1 = (unsigned)__ldg(L.gI0 + i + 3 * BT); }
         const bool in1 = i + BT < n;
         const int rr1 = in1 ? r1 : 0, cc1 = in1 ? c1 : 0;
         ColRegs ca0 = mycol, ca1 = mycol;
@@ -411,23 +427,29 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
           ca1.a = tb.colA[cc1]; ca1.b = tb.colB[cc1];
         }
         bool unc0, unc1;
-        WarpA a0 = warp_estimate(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], p0, rows, cols, guard, unc0);
-        WarpA a1 = warp_estimate(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], p1, rows, cols, guard, unc1);
+        WarpA a0 = warp_estimate(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], p0, rows, cols, unc0);
+        WarpA a1 = warp_estimate(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], p1, rows, cols, unc1);
         const bool dep0 = (min_depth < p0) & (p0 < max_depth);                 // strict bounds, AN:279-280
         const bool dep1 = (min_depth < p1) & (p1 < max_depth) & in1;
-        if (dep0 & (unc0 | force_exact)) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
-        if (dep1 & (unc1 | force_exact)) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[cc1], tb.ry[rr1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+        const bool ex0 = dep0 & (unc0 | force_exact), ex1 = dep1 & (unc1 | force_exact);
+        if (ex0 | ex1) {                                                       // rare: ~2e-4 of the pixels
+          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[cc1], tb.ry[rr1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+        }
         const bool ok0 = a0.ok & dep0, ok1 = a1.ok & dep1;
-        if (ok0) smem_red_max(L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);
-        if (ok1) smem_red_max(L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
-        valid |= ((unsigned long long)ok0 << k) | ((unsigned long long)ok1 << (k + 1));
+        smem_red_max_if(ok0, L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);
+        smem_red_max_if(ok1, L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
+        vlo = __funnelshift_r(vlo, vhi, 2);
+        vhi = (vhi >> 2) | ((unsigned)ok0 << 30) | ((unsigned)ok1 << 31);
         if (COLFIX) { r0 += dr2; r1 += dr2; }
         else {
           c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
         }
-        p0 = q0; p1 = q1; q0 = f0; q1 = f1; u0 = v0; u1 = v1; v0 = w0; v1 = w1;
+        p0 = f0; p1 = f1; u0 = w0; u1 = w1;
       }
+      valid = ((unsigned long long)vhi << 32) | vlo;
+      valid = trips > 0 ? valid >> (64 - 2 * trips) : 0ull;
     }
     __syncthreads();
     // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----

@@ -30,6 +30,7 @@ struct phovo_batch_state {
   int log_per_pair = 0; int last_pairs = 0; bool log_fetched = false;
   bool record_stats = false;
   int debug_flags = 0;
+  unsigned long long last_h2d_bytes = 0;
   // staging for host inputs: two slots
   uint8_t* stage_g0[2] = {nullptr, nullptr}; uint8_t* stage_g1[2] = {nullptr, nullptr}; char* stage_d[2] = {nullptr, nullptr};
   size_t stage_cap_g[2] = {0, 0}, stage_cap_g1[2] = {0, 0}, stage_cap_d[2] = {0, 0};
@@ -115,7 +116,6 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   unsigned long long off = 0;
   for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
     if (ctx->cfg.max_num_iterations[level] <= 0) continue;
-    if (level == 0) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: level 0 does not fit in shared memory; use the per-pair API");
     if (ctx->cfg.blur_filter_size[level] > 1) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: blurFilterSize > 0 is only supported by the per-pair API");
     int lr, lc;
     level_size(rows, cols, level, &lr, &lc);
@@ -147,6 +147,34 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   return PHOVO_OK;
 }
 
+// Which source rows do the active levels read?  Level l >= 1 of an image whose height is a
+// multiple of 2^l reads rows 2^l y + 2^(l-1) - 1 and 2^l y + 2^(l-1) only (central 2x2 taps of
+// cv::resize at an exact power-of-two factor, AN:132).  If, within the period 2^lmax, the rows read
+// form one contiguous run [begin, begin + keep), a host batch is uploaded with one strided 2-D copy
+// that skips the other rows (640x480, levels 2+3: rows 1..6 of every 8, 25 % less PCIe traffic).
+static void row_compaction(const phovo_ctx* ctx, int rows, int* period, int* begin, int* keep) {
+  *period = 0; *begin = 0; *keep = 0;
+  int lmax = 0;
+  for (int l = 0; l < ctx->cfg.num_levels; ++l) {
+    if (ctx->cfg.max_num_iterations[l] <= 0) continue;
+    if (l == 0) return;                       // level 0 reads every row
+    lmax = std::max(lmax, l);
+  }
+  if (lmax == 0 || lmax > 6) return;
+  const int P = 1 << lmax;
+  if (rows % P != 0) return;                  // border taps would break the pattern
+  std::vector<char> need(P, 0);
+  for (int l = 1; l <= lmax; ++l) {
+    if (ctx->cfg.max_num_iterations[l] <= 0) continue;
+    for (int y = 0; y < P >> l; ++y) { need[(y << l) + (1 << (l - 1)) - 1] = 1; need[(y << l) + (1 << (l - 1))] = 1; }
+  }
+  int first = 0; while (first < P && !need[first]) ++first;
+  int last = P - 1; while (last >= 0 && !need[last]) --last;
+  if (first > last || (first == 0 && last == P - 1)) return;   // nothing to skip
+  for (int r = first; r <= last; ++r) if (!need[r]) return;     // holes inside the run: keep it simple, copy everything
+  *period = P; *begin = first; *keep = last - first + 1;
+}
+
 static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& bp, size_t smem, cudaStream_t stream,
                       const uint8_t* g0, const void* d0, int depth_type, double depth_scale, const uint8_t* g1,
                       uint8_t* store, const double* init, double* states, int32_t* iters,
@@ -172,6 +200,12 @@ static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& b
   CK(cudaEventRecord(b->ev_k[2], stream));
   b->timed = true;
   CK(cudaGetLastError());
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_get_last_h2d_bytes(const phovo_ctx* ctx, unsigned long long* bytes) {
+  if (!ctx || !bytes || !ctx->batch) return PHOVO_E_INVALID;
+  *bytes = ctx->batch->last_h2d_bytes;
   return PHOVO_OK;
 }
 
@@ -287,17 +321,32 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
       CK(ensure(&b->stage_d[s], &b->stage_cap_d[s], frame * chunk * delt));
     }
     CK(cudaMemsetAsync(b->iters, 0, sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)num_pairs, ctx->stream));
+    int period, keep_begin, keep;
+    row_compaction(ctx, rows, &period, &keep_begin, &keep);
+    b->last_h2d_bytes = 0;
     int slot = 0, used[2] = {0, 0};
     for (int p0 = 0; p0 < num_pairs; p0 += chunk, slot ^= 1) {
       const int np = std::min(chunk, num_pairs - p0);
       if (used[slot]) CK(cudaStreamWaitEvent(b->copy_stream, b->ev_consumed[slot], 0));
-      CK(cudaMemcpyAsync(b->stage_g0[slot], gray0 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
-      CK(cudaMemcpyAsync(b->stage_g1[slot], gray1 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
-      CK(cudaMemcpyAsync(b->stage_d[slot], (const char*)depth0 + (size_t)p0 * frame * delt, frame * np * delt, cudaMemcpyHostToDevice, b->copy_stream));
+      if (period) {
+        // one strided copy per image stack: `keep` of every `period` rows, frames are back to back
+        const size_t groups = (size_t)(rows / period) * np;
+        const size_t gw = (size_t)keep * cols, gp = (size_t)period * cols, go = (size_t)keep_begin * cols;
+        CK(cudaMemcpy2DAsync(b->stage_g0[slot], gw, gray0 + (size_t)p0 * frame + go, gp, gw, groups, cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaMemcpy2DAsync(b->stage_g1[slot], gw, gray1 + (size_t)p0 * frame + go, gp, gw, groups, cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaMemcpy2DAsync(b->stage_d[slot], gw * delt, (const char*)depth0 + ((size_t)p0 * frame + go) * delt, gp * delt, gw * delt, groups, cudaMemcpyHostToDevice, b->copy_stream));
+        b->last_h2d_bytes += groups * gw * (2 + delt);
+      } else {
+        CK(cudaMemcpyAsync(b->stage_g0[slot], gray0 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaMemcpyAsync(b->stage_g1[slot], gray1 + (size_t)p0 * frame, frame * np, cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaMemcpyAsync(b->stage_d[slot], (const char*)depth0 + (size_t)p0 * frame * delt, frame * np * delt, cudaMemcpyHostToDevice, b->copy_stream));
+        b->last_h2d_bytes += (size_t)frame * np * (2 + delt);
+      }
       CK(cudaEventRecord(b->ev_copied[slot], b->copy_stream));
       CK(cudaStreamWaitEvent(ctx->stream, b->ev_copied[slot], 0));
       BatchParams cp = bp;
       cp.num_pairs = np;
+      cp.src_period = period; cp.src_keep_begin = keep_begin; cp.src_keep = keep;
       rc = run_device(ctx, b, cp, smem, ctx->stream, b->stage_g0[slot], b->stage_d[slot], depth_type, depth_scale, b->stage_g1[slot],
                       b->store + (size_t)p0 * bp.record_bytes, d_init ? d_init + (size_t)p0 * 6 : nullptr,
                       b->states + (size_t)p0 * 6, b->iters + (size_t)p0 * PHOVO_MAX_LEVELS,

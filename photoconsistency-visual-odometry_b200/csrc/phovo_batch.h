@@ -21,6 +21,7 @@ struct BatchParams {
   int log_cap;                          // per-pair stats slots (0: do not record)
   int exact_always;                     // test hook: every pixel takes the exact warp (no estimate shortcut)
   int force_generic;                    // test hook: generic (r, c) bookkeeping even when BT % cols == 0
+  int src_period, src_keep_begin, src_keep;   // row compaction of staged inputs (src_period 0: dense frames)
   int level[PHOVO_MAX_LEVELS];          // pyramid level index of active level a
   int lrows[PHOVO_MAX_LEVELS], lcols[PHOVO_MAX_LEVELS];
   int max_iters[PHOVO_MAX_LEVELS];

@@ -226,6 +226,12 @@ class CPhotoconsistencyOdometryCuda:
     def BatchSetRecordStats(self, enable):
         self._check(self._L.phovo_batch_set_record_stats(self._h, int(enable)))
 
+    def BatchLastH2DBytes(self):
+        """Bytes the last BatchAlign call with host inputs copied to the device."""
+        n = C.c_uint64()
+        self._check(self._L.phovo_batch_get_last_h2d_bytes(self._h, C.byref(n)))
+        return int(n.value)
+
     def BatchSetDebugFlags(self, flags):
         """bit 0: exact warp for every pixel; bit 1: generic pixel bookkeeping (results must not change)."""
         self._check(self._L.phovo_batch_set_debug_flags(self._h, int(flags)))
