@@ -156,49 +156,51 @@ __device__ __forceinline__ double warp_transpose_sum(double (&x)[32], int lane) 
   return x[0];
 }
 
-// Gauss-Newton step in ONE warp (AN:538-549 + AN:376-392).  Lane L enters with total[L]
-// ([0..20] upper triangle of J^T J, [21..26] J^T r, [27] sum r^2, [28] count).  Rows of the 6x6
-// system live in lanes 0..5; the symmetric positive definite system is eliminated without
-// pivoting (LDL^T, i.e. the Cholesky solve the north star asks for; the reference's
-// Eigen inverse() is a pivoted LU -- same solution to ~cond*2^-53) with one reciprocal per
-// pivot; substitution is column oriented so the dependent chain is 6 x (shuffle + fma).
-// Then state update, sincos on three lanes, rotation, termination flag.  Lane 0 publishes.
+// Gauss-Newton step by ONE warp (AN:538-549 + AN:376-392).  Lane L enters with total[L]
+// ([0..20] upper triangle of J^T J, [21..26] J^T r, [27] sum r^2, [28] count).  The totals go through
+// shared memory and EVERY lane solves the full 6x6 system redundantly in registers: the symmetric
+// positive definite system is eliminated without pivoting (LDL^T, i.e. the Cholesky solve the north
+// star asks for; the reference's Eigen inverse() is a pivoted LU -- same solution to ~cond*2^-53)
+// with one correctly rounded reciprocal per pivot.  No shuffles on the critical path: a serial
+// chain of ~50 dependent fp64 operations instead of ~100 shuffle round trips.  Then state update,
+// sincos on three lanes, rotation, termination flag.  Lane 0 publishes.
 __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchParams& bp, int a, int it, int pair,
                                              BatchShared* sh, phovo_iter_stats* log) {
   const unsigned FULL = 0xffffffffu;
   sh->totals[lane] = tot;
-  const int row = lane < 6 ? lane : 5;
-  double A[6], g;
+  __syncwarp();
+  double A[6][6], g[6];
+  {
+    int k = 0;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int lo = row < j ? row : j, hi = row < j ? j : row;
-    A[j] = __shfl_sync(FULL, tot, lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo));
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) { A[i][j] = sh->totals[k]; ++k; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = sh->totals[21 + i];
   }
-  g = __shfl_sync(FULL, tot, 21 + row);
   double n2 = 0.;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { const double gk = __shfl_sync(FULL, tot, 21 + k); n2 = fma(gk, gk, n2); }
-  double rinv[6];
+  for (int k = 0; k < 6; ++k) n2 = fma(g[k], g[k], n2);
+  // LDL^T on the upper triangle: after step k row k holds the pivot row; rows below are updated
+  double rinv[6], x[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double pk = __shfl_sync(FULL, A[k], k);
-    double prow[6];
+    rinv[k] = rcp_rn_normal(A[k][k]);
 #pragma unroll
-    for (int j = k + 1; j < 6; ++j) prow[j] = __shfl_sync(FULL, A[j], k);
-    const double pg = __shfl_sync(FULL, g, k);
-    rinv[k] = 1.0 / pk;
-    if (lane > k) {
-      const double m = A[k] * rinv[k];
+    for (int i = k + 1; i < 6; ++i) {
+      const double m = A[k][i] * rinv[k];          // A[i][k] == A[k][i] by symmetry
 #pragma unroll
-      for (int j = k + 1; j < 6; ++j) A[j] = fma(-m, prow[j], A[j]);
-      g = fma(-m, pg, g);
+      for (int j = i; j < 6; ++j) A[i][j] = fma(-m, A[k][j], A[i][j]);
+      g[i] = fma(-m, g[k], g[i]);
     }
   }
-  double x[6];
 #pragma unroll
   for (int k = 5; k >= 0; --k) {
-    x[k] = __shfl_sync(FULL, g, k) * rinv[k];
-    if (lane < k) g = fma(-A[k], x[k], g);
+    double sacc = g[k];
+#pragma unroll
+    for (int j = k + 1; j < 6; ++j) sacc = fma(-A[k][j], x[j], sacc);
+    x[k] = sacc * rinv[k];
   }
   const double lambda = bp.lambda[a];
   double s_in[6], s_out[6];
@@ -505,10 +507,10 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
     }
     __syncthreads();
     if (wid == 0) {
-      double tot = 0.;
+      double t0 = 0., t1 = 0.;   // two interleaved chains, fixed order
 #pragma unroll
-      for (int w = 0; w < NW; ++w) tot += L.sRed[w * 32 + lane];
-      warp_gn_step(tot * scale, lane, bp, a, it, L.pair, sh, log);
+      for (int w = 0; w < NW; w += 2) { t0 += L.sRed[w * 32 + lane]; if (w + 1 < NW) t1 += L.sRed[(w + 1) * 32 + lane]; }
+      warp_gn_step((t0 + t1) * scale, lane, bp, a, it, L.pair, sh, log);
     }
     __syncthreads();
     if (sh->done) break;
