@@ -24,7 +24,6 @@
 namespace phovo {
 namespace {
 
-constexpr int BT = kBatchThreads;
 
 __device__ __forceinline__ void linear_axis(int d, double scale, int ssize, bool is_x, int& s0, float& w1) {
   float f = (float)(((double)d + 0.5) * scale - 0.5);
@@ -101,8 +100,8 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // K3-batch building blocks
 // ---------------------------------------------------------------------------------------------
-constexpr int NW = BT / 32;
-static_assert(kBatchMaxLevelPixels <= 64 * BT, "per-thread validity mask is 64 bits");
+static_assert(kBatchMaxLevelPixels <= 64 * kBatchThreads, "per-thread validity mask is 64 bits");
+static_assert(kBatchSmallLevelPixels <= 64 * kBatchThreadsSmall, "per-thread validity mask is 64 bits");
 static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 in 16 bits");
 
 struct BatchShared {
@@ -361,8 +360,9 @@ struct LevelCtx {
 // of the level width, so a thread's pixels t, t+BT, ... all lie in ONE column: the column entries
 // of the tables live in registers and only the row advances.  The thread -> pixel mapping is the
 // same linear one in both variants, so results are bitwise identical.
-template <int MODE, bool COLFIX>
+template <int MODE, bool COLFIX, int BT>
 __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
+  constexpr int NW = BT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rows = L.rows, cols = L.cols, n = L.n, a = L.a;
   const Tables& tb = L.tb;
@@ -517,8 +517,12 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
   }
 }
 
-// K3-batch.  Persistent CTAs fetch pairs from a global counter (iteration counts differ between
-// pairs, so static assignment leaves SMs idle at the tail).  Per level, resident in shared memory:
+// K3-batch, one launch per ACTIVE pyramid level (coarse to fine; the state of every pair travels
+// through `states` between launches).  Persistent CTAs fetch pairs from a global counter (iteration
+// counts differ between pairs, so static assignment leaves SMs idle at the tail).  A small level
+// runs as 3 CTAs of 160 threads per SM, so that the serial part of one pair's iteration (barriers,
+// the 6x6 solve) overlaps the pixel loops of two other pairs; a level that needs most of the
+// shared memory runs as 1 CTA of 480 threads.  Resident in shared memory for the level:
 //   sWin u32[n]  winner word per TARGET slot: (source index + 1) << 16 | I0 tap sum of that source;
 //                a native 32-bit shared atomicMax keeps the largest source index == the reference's
 //                raster-order last-writer-wins (AN:358) and carries the winner's intensity along
@@ -526,21 +530,25 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
 //                computed once per level from the resident I1 tap sums (AN:165-189)
 //   sI1  u16[n]  I1 tap sums (value = sum / 1020)
 //   tables       see struct Tables
-// D0 (fp64) and I0 (u16) are streamed from the pair's record (L2) with register prefetch two trips
-// ahead.  Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current
-// pose stays in a 64-bit register mask between the two phases of an iteration.
-template <int MODE>
-__global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ BatchParams bp, const uint8_t* __restrict__ store,
-                                                       const double* __restrict__ init_states, double* __restrict__ states,
-                                                       int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
-                                                       int32_t* __restrict__ log_counts, int nmax, int tabmax,
-                                                       unsigned int* __restrict__ next_pair) {
+// D0 (fp64) and I0 (u16) are streamed from the pair's record (L2) with register prefetch.
+// Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current pose
+// stays in a 64-bit register mask between the two phases of an iteration.  The thread -> pixel
+// mapping is a pure function of the level size, so results do not depend on grid, batch or GPU.
+template <int MODE, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ BatchParams bp, const int a,
+                                                          const uint8_t* __restrict__ store,
+                                                          const double* __restrict__ init_states, double* __restrict__ states,
+                                                          int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
+                                                          int32_t* __restrict__ log_counts, unsigned int* __restrict__ next_pair) {
+  constexpr int NW = BT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
+  const int nal = (n + 7) & ~7;
   unsigned* sWin = (unsigned*)smem_raw;
-  unsigned* sG = sWin + nmax;
-  unsigned short* sI1 = (unsigned short*)(sG + nmax);
-  double* sTab = (double*)(sI1 + nmax);
-  double* sRed = sTab + tabmax;
+  unsigned* sG = sWin + nal;
+  unsigned short* sI1 = (unsigned short*)(sG + nal);
+  double* sTab = (double*)(sI1 + nal);
+  double* sRed = sTab + ((table_doubles(rows, cols) + 1) & ~1);
   BatchShared* sh = (BatchShared*)(sRed + NW * 32);
   const int tid = threadIdx.x;
 
@@ -551,12 +559,14 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
       sh->pair = pair;
       if (pair < bp.num_pairs) {
         double s[6];
-        for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)pair * 6 + k] : 0.;
+        const double* src = a == 0 ? init_states : states;     // the first level starts from the caller's state
+        for (int k = 0; k < 6; ++k) s[k] = src ? src[(size_t)pair * 6 + k] : 0.;
         Pose P;
         pose_from_state(s, P);
         for (int k = 0; k < 6; ++k) sh->pose.state[k] = s[k];
         pose_store(P, &sh->pose);
-        sh->pose.log_count = 0;
+        sh->pose.log_count = (a == 0 || !log_counts) ? 0 : log_counts[pair];
+        sh->done = 0; sh->iteration = 0;
       }
     }
     __syncthreads();
@@ -564,52 +574,48 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
     if (pair >= bp.num_pairs) break;
     const uint8_t* rec = store + (size_t)pair * bp.record_bytes;
 
-    for (int a = 0; a < bp.num_active; ++a) {
-      LevelCtx L;
-      const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
-      L.rows = rows; L.cols = cols; L.n = n; L.a = a; L.pair = pair;
-      L.gD0 = (const double*)(rec + bp.off_D0[a]);
-      L.gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
-      L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
-      L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
-      Tables& tb = L.tb;
-      tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
-      tb.cx = (double*)(tb.row + 4 * rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
-      {
-        // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
-        const double ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
-        const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
-        uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
-        const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
-        for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
-        for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
-        for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
-      }
-      if (tid == 0) { sh->done = 0; sh->iteration = 0; }
-      __syncthreads();
-      {
-        // Scharr numerators of I1 (AN:181-187), reflect-101: |gx|,|gy| <= 16 * 1020 fits s16
-        const int dr = BT / cols, dc = BT - dr * cols;
-        int r = tid / cols, c = tid - r * cols;
-        for (int i = tid; i < n; i += BT) {
-          const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
-          const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
-          const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
-          const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
-          const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
-          const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
-          sG[i] = ((unsigned)gxn & 0xffffu) | ((unsigned)gyn << 16);
-          c += dc; r += dr;
-          if (c >= cols) { c -= cols; ++r; }
-        }
-      }
-      // (the first barrier inside gn_level orders these writes before the pixel loops)
-      if (BT % cols == 0 && !bp.force_generic) gn_level<MODE, true>(bp, L, sh, log);
-      else gn_level<MODE, false>(bp, L, sh, log);
-      if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + bp.level[a]] = sh->iteration;
+    LevelCtx L;
+    L.rows = rows; L.cols = cols; L.n = n; L.a = a; L.pair = pair;
+    L.gD0 = (const double*)(rec + bp.off_D0[a]);
+    L.gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
+    L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
+    L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
+    Tables& tb = L.tb;
+    tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
+    tb.cx = (double*)(tb.row + 4 * rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
+    {
+      // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
+      const double ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
+      const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
+      uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
+      const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
+      for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
+      for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);
+      for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
+      for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
     }
     __syncthreads();
+    {
+      // Scharr numerators of I1 (AN:181-187), reflect-101: |gx|,|gy| <= 16 * 1020 fits s16
+      const int dr = BT / cols, dc = BT - dr * cols;
+      int r = tid / cols, c = tid - r * cols;
+      for (int i = tid; i < n; i += BT) {
+        const int rm = r > 0 ? r - 1 : (rows > 1 ? 1 : 0), rp = r < rows - 1 ? r + 1 : (rows > 1 ? rows - 2 : 0);
+        const int cm = c > 0 ? c - 1 : (cols > 1 ? 1 : 0), cp = c < cols - 1 ? c + 1 : (cols > 1 ? cols - 2 : 0);
+        const unsigned short* Rm = sI1 + rm * cols; const unsigned short* R0 = sI1 + r * cols; const unsigned short* Rp = sI1 + rp * cols;
+        const int a00 = Rm[cm], a01 = Rm[c], a02 = Rm[cp], a10 = R0[cm], a12 = R0[cp], a20 = Rp[cm], a21 = Rp[c], a22 = Rp[cp];
+        const int gxn = 10 * (a12 - a10) + 3 * ((a22 - a20) + (a02 - a00));
+        const int gyn = (3 * a20 + 10 * a21 + 3 * a22) - (3 * a00 + 10 * a01 + 3 * a02);
+        sG[i] = ((unsigned)gxn & 0xffffu) | ((unsigned)gyn << 16);
+        c += dc; r += dr;
+        if (c >= cols) { c -= cols; ++r; }
+      }
+    }
+    // (the first barrier inside gn_level orders these writes before the pixel loops)
+    if (BT % cols == 0 && !bp.force_generic) gn_level<MODE, true, BT>(bp, L, sh, log);
+    else gn_level<MODE, false, BT>(bp, L, sh, log);
+    __syncthreads();
+    if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + bp.level[a]] = sh->iteration;
     if (tid < 6) states[(size_t)pair * 6 + tid] = sh->pose.state[tid];
     if (tid == 0 && log_counts) log_counts[pair] = sh->pose.log_count;
   }
@@ -617,16 +623,29 @@ __global__ void __launch_bounds__(BT, 1) k_batch_align(const __grid_constant__ B
 
 }  // namespace
 
-size_t batch_align_smem_bytes(int nmax, int tabmax) {
-  nmax = (nmax + 7) & ~7;
-  tabmax = (tabmax + 1) & ~1;   // doubles of lookup tables, see table_doubles()
-  return (size_t)nmax * 10 + (size_t)tabmax * sizeof(double) + (size_t)NW * 32 * sizeof(double) + sizeof(BatchShared) + 64;
+// dynamic shared memory of one CTA working on a level of rows x cols pixels with `threads` threads
+static size_t level_smem_bytes(int rows, int cols, int threads) {
+  const size_t nal = ((size_t)rows * cols + 7) & ~(size_t)7;
+  const size_t tab = ((size_t)table_doubles(rows, cols) + 1) & ~(size_t)1;
+  return nal * 10 + tab * sizeof(double) + (size_t)(threads / 32) * 32 * sizeof(double) + sizeof(BatchShared) + 64;
 }
 
-cudaError_t batch_align_prepare(size_t smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(k_batch_align<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_batch_align<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+// A small level runs as 3 CTAs of kBatchThreadsSmall per SM (each gets a third of the 227 KB).
+bool batch_level_is_small(int rows, int cols) {
+  return rows * cols <= kBatchSmallLevelPixels && level_smem_bytes(rows, cols, kBatchThreadsSmall) <= (size_t)(227 * 1024) / 3 - 1024;
+}
+
+size_t batch_level_smem_bytes(int rows, int cols) {
+  return level_smem_bytes(rows, cols, batch_level_is_small(rows, cols) ? kBatchThreadsSmall : kBatchThreads);
+}
+
+cudaError_t batch_align_prepare() {
+  cudaError_t e;
+  const int big = 227 * 1024, small = (227 * 1024) / 3 - 1024;
+  if ((e = cudaFuncSetAttribute(k_batch_level<0, kBatchThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_batch_level<1, kBatchThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_batch_level<0, kBatchThreadsSmall, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_batch_level<1, kBatchThreadsSmall, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
 }
 
 int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8_t* gray0, const void* depth0,
@@ -640,21 +659,27 @@ int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8
   return 1;
 }
 
-int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
+// One launch per active level, coarse to fine.  `next_pair` must hold one zeroed counter per level.
+int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count, const uint8_t* store,
                        const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log, int32_t* log_counts,
                        unsigned int* next_pair) {
-  int nmax = 0, tabmax = 0;
+  int launches = 0;
   for (int a = 0; a < bp.num_active; ++a) {
-    nmax = max(nmax, bp.lrows[a] * bp.lcols[a]);
-    tabmax = max(tabmax, table_doubles(bp.lrows[a], bp.lcols[a]));
+    const int rows = bp.lrows[a], cols = bp.lcols[a];
+    const size_t smem = batch_level_smem_bytes(rows, cols);
+    const bool fixed = bp.mode == PHOVO_MODE_ANALYTIC_FIXED;
+    if (batch_level_is_small(rows, cols)) {
+      const int grid = min(bp.num_pairs, 3 * sm_count);
+      if (fixed) k_batch_level<1, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+      else k_batch_level<0, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+    } else {
+      const int grid = min(bp.num_pairs, sm_count);
+      if (fixed) k_batch_level<1, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+      else k_batch_level<0, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+    }
+    ++launches;
   }
-  nmax = (nmax + 7) & ~7;
-  tabmax = (tabmax + 1) & ~1;
-  if (bp.mode == PHOVO_MODE_ANALYTIC_FIXED)
-    k_batch_align<1><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax, tabmax, next_pair);
-  else
-    k_batch_align<0><<<grid, BT, smem_bytes, stream>>>(bp, store, init_states, states, iters, log, log_counts, nmax, tabmax, next_pair);
-  return 1;
+  return launches;
 }
 
 }  // namespace phovo

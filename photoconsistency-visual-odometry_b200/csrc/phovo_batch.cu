@@ -83,7 +83,7 @@ static int get_state(phovo_ctx* ctx, phovo_batch_state** out) {
     CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->batch->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->batch->copy_stream, cudaStreamNonBlocking));
-    CK(cudaMalloc((void**)&ctx->batch->next_pair, sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&ctx->batch->next_pair, sizeof(unsigned int) * PHOVO_MAX_LEVELS));
     for (int s = 0; s < 2; ++s) {
       CK(cudaEventCreateWithFlags(&ctx->batch->ev_copied[s], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ctx->batch->ev_consumed[s], cudaEventDisableTiming));
@@ -112,7 +112,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   bp->exact_always = ctx->batch ? (ctx->batch->debug_flags & 1) : 0;
   bp->force_generic = ctx->batch ? ((ctx->batch->debug_flags >> 1) & 1) : 0;
   bp->min_depth = ctx->cfg.min_depth; bp->max_depth = ctx->cfg.max_depth;
-  int a = 0, nmax = 0, tabmax = 0;
+  int a = 0, nmax = 0;
   unsigned long long off = 0;
   for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
     if (ctx->cfg.max_num_iterations[level] <= 0) continue;
@@ -123,7 +123,6 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     const int n = lr * lc;
     if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
     nmax = std::max(nmax, n);
-    tabmax = std::max(tabmax, 2 * (lr + lc) + 4 * lc + 8 * lr);   // kernels_batch.cu table_doubles()
     bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
     bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
     bp->px_offset[a + 1] = bp->px_offset[a] + n;
@@ -142,8 +141,12 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   }
   bp->num_active = a;
   bp->record_bytes = off ? off : 16;
-  *smem_out = batch_align_smem_bytes(nmax, tabmax);
-  if (*smem_out > 227 * 1024) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget; use the per-pair API");
+  *smem_out = 0;
+  for (int k = 0; k < a; ++k) {
+    const size_t need = batch_level_smem_bytes(bp->lrows[k], bp->lcols[k]);
+    if (need > 227 * 1024) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget; use the per-pair API");
+    *smem_out = std::max(*smem_out, need);
+  }
   return PHOVO_OK;
 }
 
@@ -185,18 +188,17 @@ static int run_device(phovo_ctx* ctx, phovo_batch_state* b, const BatchParams& b
     else CK(cudaMemsetAsync(states, 0, sizeof(double) * 6 * (size_t)bp.num_pairs, stream));
     return PHOVO_OK;
   }
-  if (b->prepared_smem < smem) {
-    CK(batch_align_prepare(smem));
-    b->prepared_smem = smem;
+  if (!b->prepared_smem) {
+    CK(batch_align_prepare());
+    b->prepared_smem = 1;
   }
   const int src = depth_type == PHOVO_DEPTH_F64 ? SRC_F64 : depth_type == PHOVO_DEPTH_F32 ? SRC_F32 : SRC_U16;
   if (!b->ev_k[0]) for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&b->ev_k[i]));
   CK(cudaEventRecord(b->ev_k[0], stream));
   ctx->launches += launch_batch_pyramid(stream, bp, g0, d0, src, depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0, g1, store);
   CK(cudaEventRecord(b->ev_k[1], stream));
-  const int grid = std::min(bp.num_pairs, b->sm_count);   // one persistent CTA per SM
-  CK(cudaMemsetAsync(b->next_pair, 0, sizeof(unsigned int), stream));
-  ctx->launches += launch_batch_align(stream, bp, grid, smem, store, init, states, iters, log, log_counts, b->next_pair);
+  CK(cudaMemsetAsync(b->next_pair, 0, sizeof(unsigned int) * PHOVO_MAX_LEVELS, stream));
+  ctx->launches += launch_batch_align(stream, bp, b->sm_count, store, init, states, iters, log, log_counts, b->next_pair);
   CK(cudaEventRecord(b->ev_k[2], stream));
   b->timed = true;
   CK(cudaGetLastError());

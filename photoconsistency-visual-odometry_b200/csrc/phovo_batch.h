@@ -10,6 +10,8 @@
 namespace phovo {
 
 constexpr int kBatchThreads = 480;          // 15 warps, 128 registers per thread; 480 is a multiple of the level widths 160 / 80 / 40 / 20 (640x480) and 240 / 120 / 60 (8K, 960-wide)
+constexpr int kBatchThreadsSmall = 160;      // small levels: 3 CTAs of 5 warps per SM (160 is a multiple of 80 / 40 / 20)
+constexpr int kBatchSmallLevelPixels = 6400; // largest level that runs 3 CTAs per SM
 constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + tables + scratch must fit 227 KB (checked exactly
                                             // by the host); also <= 64 * kBatchThreads (validity mask) and < 65535
 
@@ -39,13 +41,15 @@ struct BatchParams {
 // one pass over the full-resolution inputs.  depth_type: SRC_F64 / SRC_F32 / SRC_U16.
 int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8_t* gray0, const void* depth0,
                          int depth_type, double depth_scale, const uint8_t* gray1, uint8_t* store);
-// K3-batch: persistent CTAs, one pair at a time per CTA, level images resident in shared memory,
-// whole coarse-to-fine Gauss-Newton loop on chip.
-int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int grid, size_t smem_bytes, const uint8_t* store,
+// K3-batch: persistent CTAs, one pair at a time per CTA, the level's images resident in shared
+// memory, the whole Gauss-Newton loop of the level on chip; one launch per active level.
+// Returns the number of launches.  `next_pair`: PHOVO_MAX_LEVELS zeroed device counters.
+int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count, const uint8_t* store,
                        const double* init_states, double* states, int32_t* iters, phovo_iter_stats* log,
-                       int32_t* log_counts, unsigned int* next_pair /* device counter, zero before the launch */);
-size_t batch_align_smem_bytes(int max_level_pixels, int max_table_doubles);
-cudaError_t batch_align_prepare(size_t smem_bytes);
+                       int32_t* log_counts, unsigned int* next_pair);
+size_t batch_level_smem_bytes(int rows, int cols);
+bool batch_level_is_small(int rows, int cols);
+cudaError_t batch_align_prepare();
 
 }  // namespace phovo
 #endif
