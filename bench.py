@@ -9,7 +9,7 @@ gradient-norm stop at 300), sharded by pair across the GPUs: every rank aligns `
   value   : pairs/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e     : pairs/s through the reference-facing C ABI with HOST (pinned) buffers: the H2D copy of
             every pair and the D2H read of the poses are inside the timed region
-  roofline: the dominant kernel (k_batch_align) -- algorithmic bytes per SURVEY 8(d)
+  roofline: the dominant kernel (k_batch_level, one launch per active level) -- algorithmic bytes per SURVEY 8(d)
             (20 B/px per executed GN iteration + 216 B of sums) / its CUDA-event time, against the
             measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the CPU oracle (faithful port of the reference's analytic path,
@@ -311,7 +311,7 @@ def main():
         fp64 = {"achieved": rate / 1e12, "peak": prof["fp64_peak_thread_inst_per_s"] / 1e12, "unit": "T fp64 thread-instructions/s",
                 "frac": rate / prof["fp64_peak_thread_inst_per_s"], "inst_per_px_iter": prof["fp64_thread_inst_per_px_iter"],
                 "source": "ncu op counters of %s / executed pixel-iterations; peak = %s" % (prof.get("tag"), prof.get("fp64_peak_source"))}
-    roofline = {"bound": "hbm", "kernel": "k_batch_align", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_batch_level (one launch per active pyramid level; figures are the sum over the level launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": (prof["dram_bytes_per_pair"] * P) if prof.get("dram_bytes_per_pair") else None,
                 "traffic_source": "ncu --set full dram__bytes_read+write of one launch (%s, %d pairs) scaled by pairs" % (prof.get("tag"), prof.get("profiled_pairs", 0)) if prof else None,

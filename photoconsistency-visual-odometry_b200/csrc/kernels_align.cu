@@ -175,7 +175,7 @@ __device__ void gn_step(const LevelParams& L, PoseDev* pose, const double* total
                         unsigned long long cond_handle) {
   double g[6], step[6], s_in[6], n2 = 0.;
   for (int k = 0; k < 6; ++k) { g[k] = totals[21 + k]; n2 = fma(g[k], g[k], n2); s_in[k] = pose->state[k]; }
-  solve6_lu(totals, g, step);
+  solve6_ldlt(totals, g, step);
   double s_out[6];
   for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];   // AN:539-540
   const double gnorm = sqrt(n2);

@@ -113,31 +113,6 @@ struct BatchShared {
   int pad;
 };
 
-// MUFU.RCP64H seed: 1/x to ~20 bits, low word zero.
-__device__ __forceinline__ double rcp_seed(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  return r;
-}
-// Correctly rounded 1/x for x in the normal range: the fast path nvcc itself emits for `1.0 / x`
-// (seed, two Newton steps folded into three FMAs, one residual correction), without the
-// exponent-range test and slow-path call -- the caller guarantees 1e-300 < |x| < 1e300.
-__device__ __forceinline__ double rcp_rn_normal(double x) {
-  const double r0 = rcp_seed(x);
-  double e = fma(-x, r0, 1.0);
-  e = fma(e, e, e);
-  const double r1 = fma(r0, e, r0);
-  const double e2 = fma(-x, r1, 1.0);
-  return fma(r1, e2, r1);
-}
-// 1/x to about one ulp (relative error ~ seed_error^3 = 2^-60 before rounding): Jacobian use only.
-__device__ __forceinline__ double rcp_1ulp(double x) {
-  const double r0 = rcp_seed(x);
-  double e = fma(-x, r0, 1.0);
-  e = fma(e, e, e);
-  return fma(r0, e, r0);
-}
-
 // Sum 32 values across the 32 lanes of a warp with 31 shuffle-adds (recursive halving): on return
 // lane L holds, in x[0], the warp-wide sum of the callers' x[L].  The order of the additions is a
 // pure function of the lane index, so the result is bitwise reproducible.
@@ -168,39 +143,10 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
   const unsigned FULL = 0xffffffffu;
   sh->totals[lane] = tot;
   __syncwarp();
-  double A[6][6], g[6];
-  {
-    int k = 0;
+  double x[6], n2 = 0.;
+  solve6_ldlt(sh->totals, sh->totals + 21, x);
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i; j < 6; ++j) { A[i][j] = sh->totals[k]; ++k; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) g[i] = sh->totals[21 + i];
-  }
-  double n2 = 0.;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) n2 = fma(g[k], g[k], n2);
-  // LDL^T on the upper triangle: after step k row k holds the pivot row; rows below are updated
-  double rinv[6], x[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    rinv[k] = rcp_rn_normal(A[k][k]);
-#pragma unroll
-    for (int i = k + 1; i < 6; ++i) {
-      const double m = A[k][i] * rinv[k];          // A[i][k] == A[k][i] by symmetry
-#pragma unroll
-      for (int j = i; j < 6; ++j) A[i][j] = fma(-m, A[k][j], A[i][j]);
-      g[i] = fma(-m, g[k], g[i]);
-    }
-  }
-#pragma unroll
-  for (int k = 5; k >= 0; --k) {
-    double sacc = g[k];
-#pragma unroll
-    for (int j = k + 1; j < 6; ++j) sacc = fma(-A[k][j], x[j], sacc);
-    x[k] = sacc * rinv[k];
-  }
+  for (int k = 0; k < 6; ++k) n2 = fma(sh->totals[21 + k], sh->totals[21 + k], n2);
   const double lambda = bp.lambda[a];
   double s_in[6], s_out[6];
 #pragma unroll

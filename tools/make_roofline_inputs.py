@@ -10,20 +10,27 @@ import csv, io, json, subprocess, sys
 
 def main(rep, log, peak, tag):
     raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
-    d = dict(zip(raw[0], raw[2])); u = dict(zip(raw[0], raw[1]))
+    u = dict(zip(raw[0], raw[1]))
+    launches = [dict(zip(raw[0], r)) for r in raw[2:]]       # one k_batch_level launch per active pyramid level
+    d = launches[0]
     line = json.loads([l for l in open(log) if l.startswith("{")][-1])
     pairs = line["config"]["pairs_per_gpu"]
     it = line["config"]["mean_iterations_per_pair"]
     rows, cols = line["config"]["rows"], line["config"]["cols"]
     px_iters = pairs * sum(v * round(rows * 0.5 ** int(l)) * round(cols * 0.5 ** int(l)) for l, v in it.items())
-    cycles = float(d["sm__cycles_elapsed.avg"])
-    fp64 = sum(float(d["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k]) for k in ("dfma", "dmul", "dadd")) * cycles
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    dram = sum(float(d["dram__bytes_%s.sum" % k]) * scale[u["dram__bytes_%s.sum" % k]] for k in ("read", "write"))
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    fp64 = dram = dur = 0.0
+    for L in launches:
+        cycles = float(L["sm__cycles_elapsed.avg"])
+        fp64 += sum(float(L["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k]) for k in ("dfma", "dmul", "dadd")) * cycles
+        dram += sum(float(L["dram__bytes_%s.sum" % k]) * scale[u["dram__bytes_%s.sum" % k]] for k in ("read", "write"))
+        dur += float(L["gpu__time_duration.sum"]) * tscale[u["gpu__time_duration.sum"]]
     best = max(json.loads(l)["dfma_per_s"] for l in open(peak) if l.startswith("{"))
-    out = {"tag": tag, "kernel": "k_batch_align", "profiled_pairs": pairs, "profiled_duration_ms": float(d["gpu__time_duration.sum"]),
+    out = {"tag": tag, "kernel": "k_batch_level (one launch per active level, summed)", "profiled_launches": len(launches),
+           "profiled_pairs": pairs, "profiled_duration_ms": dur,
            "dram_bytes_per_pair": dram / pairs, "fp64_thread_inst_per_px_iter": fp64 / px_iters,
-           "fp64_pipe_active_pct_of_active": float(d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]),
+           "fp64_pipe_active_pct_of_active_per_launch": [float(L["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]) for L in launches],
            "fp64_peak_thread_inst_per_s": best, "fp64_peak_source": "tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.jsonl), DFMA issue rate",
            "registers_per_thread": int(d["launch__registers_per_thread"])}
     print(json.dumps(out, indent=1))
