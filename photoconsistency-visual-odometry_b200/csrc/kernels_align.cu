@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(kBlock) k_winner(LevelParams L, LevelPtrs P, c
     const double d = __ldg(P.D0 + i);
     const int r = i / L.cols, c = i - r * L.cols;
     Warped w;
-    if (warp_pixel<CERES>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
+    const bool ok = warp_pixel<CERES>(L, T, r, c, d, w);
+    if (ok) atomicMax(P.winner + w.t, i);
+    if (!CERES) P.valid[i] = ok;
   }
 }
 
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
   for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
   const int n = L.rows * L.cols;
   const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;
+  const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
     const int r = i / L.cols, c = i - r * L.cols;
     const double d = __ldg(P.D0 + i);
@@ -140,13 +143,27 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
         acc[27] = fma(res, res, acc[27]);
       }
       if (DUMP && dump_res) dump_res[i] = res;
-      const bool ok = warp_pixel<false>(L, T, r, c, d, w);
-      if (!ok) continue;
-      double Ju[6], Jv[6], J[6];
-      projection_jacobian<MODE == 0>(L, T, w, d, Ju, Jv);
-      const double gx = __ldg(P.Gx + i), gy = __ldg(P.Gy + i);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J[k] = gx * Ju[k] + gy * Jv[k];   // AN:345-348
+      if (!P.valid[i]) continue;                      // K3a decided (exact reference arithmetic)
+      // From here on nothing decides an integer: FMA contraction and a 1-ulp reciprocal are fine.
+      const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+      const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+      const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+      const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+      const double iz = rcp_1ulp(q2 + T.z);
+      // a = Gx1[i] fx / Z', b = Gy1[i] fy / Z'  (gradients at the SOURCE index, AN:346-347); closed form
+      // of AN:243-342 with the gradient folded in
+      const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
+      const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
+      const double B = q1 + T.y;
+      double J[6];
+      J[0] = ga;
+      J[1] = gb;
+      J[2] = -(fma(ga, A, gb * B) * iz);
+      J[3] = fma(gb, q0, -(ga * q1));
+      const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+      J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
+      const double Zr = fma(T.R22, py, -(T.R21 * d));
+      J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
       accumulate_row(acc, J, res);
       acc[28] += 1.;
       if (DUMP && dump_jac) for (int k = 0; k < 6; ++k) dump_jac[(size_t)i * 6 + k] = J[k];

@@ -113,23 +113,6 @@ struct BatchShared {
   int pad;
 };
 
-// Sum 32 values across the 32 lanes of a warp with 31 shuffle-adds (recursive halving): on return
-// lane L holds, in x[0], the warp-wide sum of the callers' x[L].  The order of the additions is a
-// pure function of the lane index, so the result is bitwise reproducible.
-__device__ __forceinline__ double warp_transpose_sum(double (&x)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int j = 0; j < o; ++j) {
-      const double send = up ? x[j] : x[j + o];
-      const double keep = up ? x[j + o] : x[j];
-      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return x[0];
-}
-
 // Gauss-Newton step by ONE warp (AN:538-549 + AN:376-392).  Lane L enters with total[L]
 // ([0..20] upper triangle of J^T J, [21..26] J^T r, [27] sum r^2, [28] count).  The totals go through
 // shared memory and EVERY lane solves the full 6x6 system redundantly in registers: the symmetric

@@ -68,6 +68,7 @@ LevelPtrs phovo_ctx::level_ptrs(int level) const {
   LevelPtrs P;
   P.I0 = I0[level]; P.D0 = D0[level]; P.I1 = I1[level]; P.Gx = Gx[level]; P.Gy = Gy[level];
   P.winner = winner;
+  P.valid = valid;
   return P;
 }
 
@@ -129,6 +130,11 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
       launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap);
       ctx->launches += 1;
     }
+  }
+  {
+    unsigned char* before = ctx->valid;
+    CK(ensure(&ctx->valid, &ctx->valid_cap, max_px));
+    if (before != ctx->valid) changed = true;
   }
   for (int s = 0; s < 2; ++s) CK(ensure(&ctx->scratch64[s], &ctx->scratch_cap[s], max_px));
   {
@@ -265,7 +271,7 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
     cudaFree(ctx->I0[l]); cudaFree(ctx->D0[l]); cudaFree(ctx->I1[l]); cudaFree(ctx->Gx[l]); cudaFree(ctx->Gy[l]);
   }
-  cudaFree(ctx->winner); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
+  cudaFree(ctx->winner); cudaFree(ctx->valid); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
   cudaFree(ctx->stage_gray[0]); cudaFree(ctx->stage_gray[1]); cudaFree(ctx->stage_depth);
   cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_eval);
   cudaFree(ctx->dump_res); cudaFree(ctx->dump_jac);

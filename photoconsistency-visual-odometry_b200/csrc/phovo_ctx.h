@@ -37,6 +37,7 @@ struct phovo_ctx {
   double* Gy[PHOVO_MAX_LEVELS] = {nullptr};
   size_t lcap[PHOVO_MAX_LEVELS][5] = {{0}};
   int* winner = nullptr; size_t winner_cap = 0;           // one int per pixel of the largest active level
+  unsigned char* valid = nullptr; size_t valid_cap = 0;   // one flag per pixel (K3a -> K3b)
   double* scratch64[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};
   double* partials = nullptr; size_t partials_cap = 0;    // [grid][32] per-block normal-equation partials
   char* stage_gray[2] = {nullptr, nullptr}; size_t stage_gray_cap[2] = {0, 0};

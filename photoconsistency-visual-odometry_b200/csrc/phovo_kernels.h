@@ -29,6 +29,7 @@ int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int co
 struct LevelPtrs {
   const double* I0; const double* D0; const double* I1; const double* Gx; const double* Gy;
   int* winner;        // rows*cols ints, all -1 between iterations
+  unsigned char* valid;  // rows*cols flags written by K3a: pixel is depth-valid and lands in bounds under the current pose
 };
 
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);
