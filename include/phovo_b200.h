@@ -175,6 +175,15 @@ int phovo_set_stream(phovo_ctx* ctx, void* cuda_stream);
 /* 0: plain stream launches with host-side convergence polling; 1 (default): whole Optimize as one
  * CUDA graph with a conditional WHILE node per level (no host sync inside) */
 int phovo_set_use_graph(phovo_ctx* ctx, int enable);
+/* How phovo_optimize drives the iteration loop of a level (results agree to rounding; each path is
+ * bitwise reproducible run to run):
+ *   2 (default) one persistent cooperative kernel per level, grid-wide barriers between the phases
+ *   1           one CUDA graph for the whole Optimize with a conditional WHILE node per level
+ *   0           plain stream launches, the host polls the termination flag every 4 iterations
+ * phovo_set_use_graph(ctx, e) is shorthand for path e ? 1 : 0.  If a path is not available on the
+ * device the next one down is used (phovo_graph_error tells why). */
+int phovo_set_execution(phovo_ctx* ctx, int path);
+int phovo_last_optimize_path(const phovo_ctx* ctx);
 /* 1 if the last phovo_optimize ran as the CUDA graph (0: plain launches; see phovo_graph_error) */
 int phovo_last_optimize_used_graph(const phovo_ctx* ctx);
 const char* phovo_graph_error(const phovo_ctx* ctx);

@@ -86,6 +86,8 @@ SIGNATURES = {
     "phovo_set_stream": (C.c_int, [_vp, _vp]),
     "phovo_set_use_graph": (C.c_int, [_vp, C.c_int]),
     "phovo_last_optimize_used_graph": (C.c_int, [_vp]),
+    "phovo_set_execution": (C.c_int, [_vp, C.c_int]),
+    "phovo_last_optimize_path": (C.c_int, [_vp]),
     "phovo_graph_error": (C.c_char_p, [_vp]),
     "phovo_set_build_all_levels": (C.c_int, [_vp, C.c_int]),
     "phovo_batch_align": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,8 @@
 //
 // All kernels early-exit when pose->done is set, so an iteration enqueued after convergence is a
 // no-op; the integer atomicMax of K3a is order-independent, hence run-to-run reproducible.
+#include <cooperative_groups.h>
+
 #include "phovo_device.cuh"
 #include "phovo_kernels.h"
 
@@ -299,6 +301,135 @@ __global__ void k_solve_from_buffer(LevelParams L, PoseDev* pose, const double* 
   gn_step(L, pose, totals, log, 0ull);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent cooperative variant: ONE launch runs the whole Gauss-Newton loop of a level
+// (AN:504-561).  Per iteration: phase A (K3a) -> grid.sync -> phase B (K3b, per-block partials) ->
+// grid.sync -> every CTA sums ALL partials in the same fixed order and takes the same step
+// redundantly (no third barrier, no broadcast); CTA 0 publishes pose and log.  Data written by
+// other SMs inside the launch (winner, valid, partials) is read with ld.global.cg.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCoopBlock = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
+                                                               phovo_iter_stats* log) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
+  __shared__ double s_tot[32];
+  __shared__ PoseDev s_pose;
+  __shared__ int s_done;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_pose = *pose; s_done = 0; }
+  __syncthreads();
+  int log_count = s_pose.log_count;
+  const int log_capacity = s_pose.log_capacity;
+  const int n = L.rows * L.cols;
+  const int stride = gridDim.x * kCoopBlock;
+  int it = 0;
+  for (; it < L.max_iters; ++it) {
+    Pose T;
+    pose_load(&s_pose, T);
+    // ---- phase A: winner map + validity (exact reference arithmetic) ----
+    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+      const double d = __ldg(P.D0 + i);
+      const int r = i / L.cols, c = i - r * L.cols;
+      Warped w;
+      const bool ok = warp_pixel<false>(L, T, r, c, d, w);
+      if (ok) atomicMax(P.winner + w.t, i);
+      P.valid[i] = ok;
+    }
+    grid.sync();
+    // ---- phase B: residual + Jacobian + normal equations ----
+    double acc[PHOVO_NACC];
+#pragma unroll
+    for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+    const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
+    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+      const int win = __ldcg(P.winner + i);
+      P.winner[i] = -1;
+      double res = 0.;
+      if (win >= 0) {
+        res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
+        acc[27] = fma(res, res, acc[27]);
+      }
+      if (!__ldcg(P.valid + i)) continue;
+      const int r = i / L.cols, c = i - r * L.cols;
+      const double d = __ldg(P.D0 + i);
+      const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+      const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+      const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+      const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+      const double iz = rcp_1ulp(q2 + T.z);
+      const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
+      const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
+      const double B = q1 + T.y;
+      double J[6];
+      J[0] = ga;
+      J[1] = gb;
+      J[2] = -(fma(ga, A, gb * B) * iz);
+      J[3] = fma(gb, q0, -(ga * q1));
+      const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+      J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
+      const double Zr = fma(T.R22, py, -(T.R21 * d));
+      J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
+      accumulate_row(acc, J, res);
+      acc[28] += 1.;
+    }
+    {
+      const double total = block_reduce<kCoopBlock>(acc, smem);
+      if (tid < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + tid] = total;
+    }
+    grid.sync();
+    // ---- every CTA: fixed-order sum of all partials (group g of 8 takes blocks g, g+8, ...) ----
+    {
+      const int v = tid & 31, g = tid >> 5;
+      double s = 0.;
+      for (int b = g; b < (int)gridDim.x; b += kCoopBlock / 32) s += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
+      smem[g * PHOVO_ACC_STRIDE + v] = s;
+      __syncthreads();
+      if (tid < 32) {
+        double t = 0.;
+#pragma unroll
+        for (int k = 0; k < kCoopBlock / 32; ++k) t += smem[k * PHOVO_ACC_STRIDE + tid];
+        s_tot[tid] = t;
+      }
+      __syncthreads();
+    }
+    // ---- Gauss-Newton step + termination test (AN:538-549, 376-392), one thread per CTA ----
+    if (tid == 0) {
+      double g[6], step[6], s_in[6], s_out[6], n2 = 0.;
+      for (int k = 0; k < 6; ++k) { g[k] = s_tot[21 + k]; n2 = fma(g[k], g[k], n2); s_in[k] = s_pose.state[k]; }
+      solve6_ldlt(s_tot, g, step);
+      for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];
+      const double gnorm = sqrt(n2);
+      const int done = (it + 1 >= L.max_iters) || (gnorm < L.min_grad_norm);
+      if (blockIdx.x == 0 && log && log_count < log_capacity) {
+        phovo_iter_stats* e = log + log_count;
+        e->level = L.level; e->iteration = it; e->num_valid = (int)s_tot[28]; e->accepted = 1;
+        for (int k = 0; k < 21; ++k) e->H[k] = s_tot[k];
+        for (int k = 0; k < 6; ++k) { e->g[k] = g[k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
+        e->grad_norm = gnorm; e->cost = 0.5 * s_tot[27]; e->radius = 0.;
+      }
+      Pose Pn;
+      pose_from_state(s_out, Pn);
+      for (int k = 0; k < 6; ++k) s_pose.state[k] = s_out[k];
+      pose_store(Pn, &s_pose);
+      s_done = done;
+    }
+    log_count += 1;
+    __syncthreads();
+    if (s_done) { ++it; break; }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    s_pose.iteration = it;
+    s_pose.iters_per_level[L.level] = it;
+    s_pose.done = 1;
+    s_pose.log_count = log_count;
+    *pose = s_pose;
+  }
+}
+
 inline int grid_for(int n) {
   // one pixel per thread up to 8 CTAs per SM, then a fixed persistent grid (grid-stride loop);
   // the grid is a pure function of the level size, so the partial-sum order is reproducible.
@@ -353,6 +484,33 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
   }
   *grid_out = grid;
   return launches + 2;
+}
+
+static int g_coop_blocks_per_sm[2] = {-1, -1};
+
+// One cooperative launch for the whole iteration loop of a level.  Returns the number of launches
+// (1) or -1 if cooperative launch is not available (the caller falls back to the graph path).
+int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                      phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err) {
+  const int m = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
+  void* fn = m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
+  if (g_coop_blocks_per_sm[m] < 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kCoopBlock, 0) != cudaSuccess) nb = 0;
+    g_coop_blocks_per_sm[m] = nb;
+  }
+  if (g_coop_blocks_per_sm[m] < 1) { *err = cudaErrorCooperativeLaunchTooLarge; return -1; }
+  const int n = L.rows * L.cols;
+  int grid = (n + kCoopBlock - 1) / kCoopBlock;
+  const int cap = sm_count * (g_coop_blocks_per_sm[m] < 2 ? g_coop_blocks_per_sm[m] : 2);
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  LevelParams Lc = L; LevelPtrs Pc = P;
+  void* args[] = {&Lc, &Pc, &pose, &partials, &log};
+  *err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopBlock), args, 0, stream);
+  if (*err != cudaSuccess) return -1;
+  *grid_out = grid;
+  return 1;
 }
 
 int launch_reduce_solve(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* partials, int grid,

@@ -235,6 +235,11 @@ extern "C" int phovo_create(int device, phovo_ctx** out) {
   if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return PHOVO_E_CUDA; }
   phovo_ctx* ctx = new phovo_ctx();
   ctx->device = device;
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) ctx->coop_broken = true;
+  }
   phovo_internal_default_config(&ctx->cfg);
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -387,8 +392,18 @@ extern "C" int phovo_set_stream(phovo_ctx* ctx, void* cuda_stream) {
 extern "C" int phovo_set_use_graph(phovo_ctx* ctx, int enable) {
   if (!ctx) return PHOVO_E_INVALID;
   ctx->use_graph = enable != 0;
+  ctx->execution = enable ? 1 : 0;
   return PHOVO_OK;
 }
+
+extern "C" int phovo_set_execution(phovo_ctx* ctx, int path) {
+  if (!ctx || path < 0 || path > 2) return PHOVO_E_INVALID;
+  ctx->execution = path;
+  ctx->use_graph = path >= 1;
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_last_optimize_path(const phovo_ctx* ctx) { return ctx ? ctx->last_path : -1; }
 
 // ---------------------------------------------------------------------------------------------
 // frames
@@ -600,6 +615,31 @@ static int optimize_graph(phovo_ctx* ctx) {
   return PHOVO_OK;
 }
 
+// One cooperative persistent launch per active level: set-state, then for each level begin-level + loop kernel.
+static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
+  *unavailable = false;
+  ctx->launches += launch_set_state(ctx->stream, ctx->d_pose, nullptr, ctx->state, ctx->log_cap);
+  for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {   // AN:502-503
+    const int M = ctx->cfg.max_num_iterations[level];
+    if (M <= 0) continue;
+    const LevelParams L = ctx->level_params(level);
+    const LevelPtrs P = ctx->level_ptrs(level);
+    ctx->launches += launch_begin_level(ctx->stream, ctx->d_pose, M);
+    int grid = 0; cudaError_t e = cudaSuccess;
+    const int rc = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, ctx->sm_count, &grid, &e);
+    if (rc < 0) {
+      cudaGetLastError();
+      ctx->graph_error = std::string("cooperative launch unavailable: ") + cudaGetErrorString(e);
+      *unavailable = true;
+      CK(cudaStreamSynchronize(ctx->stream));
+      return PHOVO_OK;
+    }
+    ctx->launches += rc;
+  }
+  CK(cudaGetLastError());
+  return PHOVO_OK;
+}
+
 static int optimize_ceres(phovo_ctx* ctx);
 
 extern "C" int phovo_optimize(phovo_ctx* ctx) {
@@ -611,7 +651,15 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
   ctx->setup_timed = false;
   CK(cudaEventRecord(ctx->ev_time[2], ctx->stream));
   ctx->last_used_graph = 0;
+  ctx->last_path = 0;
   if (ctx->cfg.mode == PHOVO_MODE_CERES) return optimize_ceres(ctx);
+  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
+    bool unavailable = false;
+    rc = optimize_coop(ctx, &unavailable);
+    if (rc) return rc;
+    if (!unavailable) { ctx->last_path = 2; return read_back(ctx); }
+    ctx->coop_broken = true;   // remember and use the graph path from now on
+  }
   bool done = false;
   if (ctx->use_graph && !ctx->graph_broken) {
     rc = optimize_graph(ctx);
@@ -619,6 +667,7 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
       rc = read_back(ctx);
       if (rc == PHOVO_OK || rc == PHOVO_E_NUMERIC) {
         ctx->last_used_graph = 1;
+        ctx->last_path = 1;
         int iters = 0;
         for (int l = 0; l < ctx->cfg.num_levels; ++l) iters += ctx->h_pose->iters_per_level[l];
         ctx->launches += ctx->graph_launches_fixed + (int64_t)iters * ctx->graph_launches_per_iter;

@@ -51,6 +51,9 @@ int launch_reduce_to_buffer(cudaStream_t stream, const double* partials, int gri
 int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* buffer,
                              phovo_iter_stats* log);
 int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
+// persistent cooperative kernel: the whole iteration loop of one level in one launch (analytic modes)
+int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                      phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err);
 
 // Exchange area of the fused peer-store all-reduce (one per rank, IPC-shared with the peers).
 struct ShardExchange {

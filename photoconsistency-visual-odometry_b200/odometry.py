@@ -138,6 +138,13 @@ class CPhotoconsistencyOdometryCuda:
     def SetStream(self, cuda_stream):
         self._check(self._L.phovo_set_stream(self._h, cuda_stream))
 
+    def SetExecution(self, path):
+        """2 persistent cooperative kernel per level (default), 1 CUDA graph, 0 stream launches."""
+        self._check(self._L.phovo_set_execution(self._h, int(path)))
+
+    def LastPath(self):
+        return int(self._L.phovo_last_optimize_path(self._h))
+
     def UsedGraph(self):
         return bool(self._L.phovo_last_optimize_used_graph(self._h))
 

@@ -20,11 +20,14 @@ def conv_cfg(oracle, cfg):
     return oracle.Config.from_buffer_copy(bytes(cfg))
 
 
-def make_odo(phovo, cfg, K, graph=True, build_all=False):
+def make_odo(phovo, cfg, K, graph=None, build_all=False):
+    """graph=None: the library default (persistent cooperative kernel per level); True / False select
+    the CUDA-graph / plain-stream drivers of the iteration loop."""
     odo = phovo.CPhotoconsistencyOdometryCuda()
     odo.SetConfig(cfg)
     odo.SetIntrinsicMatrix(K)
-    odo.SetUseGraph(graph)
+    if graph is not None:
+        odo.SetUseGraph(graph)
     if build_all:
         odo.SetBuildAllLevels(True)
     return odo
@@ -155,6 +158,20 @@ def test_graph_and_stream_paths_are_bitwise_identical_and_reproducible(phovo):
     sgb, _ = run_gpu(odo_g, g0b, d0b, g1b)
     ssb, _ = run_gpu(odo_s, g0b, d0b, g1b)
     assert np.array_equal(sgb, ssb) and not np.array_equal(sgb, sg)
+    # the default driver: one persistent cooperative kernel per level.  Different partial-sum grouping,
+    # so equal to rounding (not bitwise) with the graph path, and bitwise reproducible run to run.
+    odo_p = make_odo(phovo, cfg, K)
+    sp, lp = run_gpu(odo_p, g0, d0, g1)
+    assert odo_p.LastPath() == 2, odo_p.GraphError()
+    assert len(lp) == len(lg) and np.max(np.abs(sp - sg)) < 1e-12
+    for a, b in zip(lp, lg):
+        assert a["num_valid"] == b["num_valid"]
+        assert np.max(np.abs(a["H"] - b["H"])) <= 1e-12 * np.max(np.abs(b["H"]))
+        assert np.max(np.abs(a["g"] - b["g"])) <= 1e-11 * np.max(np.abs(b["g"]))
+    for _ in range(3):
+        sp2, lp2 = run_gpu(odo_p, g0, d0, g1)
+        assert np.array_equal(sp, sp2)
+        assert all(np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"]) for a, b in zip(lp, lp2))
 
 
 @pytest.mark.parametrize("name", ["pair_96x128_ref", "pair_96x128_fixed", "pair_90x135_ref"])
