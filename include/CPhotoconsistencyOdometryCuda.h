@@ -163,6 +163,23 @@ public:
                                            size_t( depthImage.step ), 1.0 ), "phovo_promote_target_to_source" );
   }
 
+  /*!phovo::warpImage (CPhotoconsistencyOdometry.h:73-134) on the GPU: same arguments as the
+   * reference's free function; the apps call it after Optimize() to display the alignment.*/
+  void WarpImage( const IntensityImageType & intensityImage, const DepthImageType & depthImage,
+                  IntensityImageType & warpedIntensityImage, const Matrix44Type & Rt,
+                  const Matrix33Type & intrinsicMatrix, const int level = 0 )
+  {
+    double rt[16], K[9];
+    for( int i = 0; i < 4; i++ ) for( int j = 0; j < 4; j++ ) rt[ 4 * i + j ] = double( Rt( i, j ) );
+    for( int i = 0; i < 3; i++ ) for( int j = 0; j < 3; j++ ) K[ 3 * i + j ] = double( intrinsicMatrix( i, j ) );
+    warpedIntensityImage.create( intensityImage.rows, intensityImage.cols );
+    Check( phovo_warp_image( m_Ctx, reinterpret_cast< const uint8_t * >( intensityImage.data ), size_t( intensityImage.step ),
+                             depthImage.data, detail::DepthTypeOf< TCoordinate >::value, size_t( depthImage.step ), 1.0,
+                             intensityImage.rows, intensityImage.cols, rt, K, level,
+                             reinterpret_cast< uint8_t * >( warpedIntensityImage.data ), size_t( warpedIntensityImage.step ),
+                             0, 0, 0, 0 ), "phovo_warp_image" );
+  }
+
   /*!Executed Gauss-Newton iterations of the last Optimize() with their normal equations.*/
   std::vector< phovo_iter_stats > GetIterationStats() const
   {

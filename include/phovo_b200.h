@@ -156,6 +156,18 @@ int phovo_get_rt(const phovo_ctx* ctx, double rt[16]);               /* AN:572-5
 /* state -> 4x4, usable without a context (BASE:47-71) */
 void phovo_state_to_rt(const double state[6], double rt[16]);
 
+/* ---- diagnostics the apps compute after Optimize ----------------------------------------- */
+/* phovo::warpImage (BASE:73-134) + the cv::absdiff both apps show (FrameAlignment.cpp:107-110,
+ * VisualOdometry.cpp:247-252): forward-splat the source intensities through depth, Rt (row-major
+ * 4x4) and K / 2^level into `warped` (zero where nothing lands; truncating cast BASE:119-122,
+ * raster-order last writer wins); if `target` and `diff` are given also diff = |target - warped|.
+ * Host or device pointers; strides in bytes; depth as in phovo_set_source. */
+int phovo_warp_image(phovo_ctx* ctx, const uint8_t* gray, size_t gray_step,
+                     const void* depth, int depth_type, size_t depth_step, double depth_scale,
+                     int rows, int cols, const double rt[16], const double K[9], int level,
+                     uint8_t* warped, size_t warped_step,
+                     const uint8_t* target, size_t target_step, uint8_t* diff, size_t diff_step);
+
 /* ---- introspection (parity hooks; not in the reference) --------------------------------- */
 int phovo_num_iter_stats(const phovo_ctx* ctx);
 int phovo_get_iter_stats(const phovo_ctx* ctx, int index, phovo_iter_stats* out);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "phovo_get_state": (C.c_int, [_vp, _dp]),
     "phovo_get_rt": (C.c_int, [_vp, _dp]),
     "phovo_state_to_rt": (None, [_dp, _dp]),
+    "phovo_warp_image": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                   _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t]),
     "phovo_num_iter_stats": (C.c_int, [_vp]),
     "phovo_get_iter_stats": (C.c_int, [_vp, C.c_int, _stp]),
     "phovo_get_level_image": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _ip, _ip]),

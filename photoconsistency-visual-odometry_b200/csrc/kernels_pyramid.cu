@@ -177,4 +177,75 @@ int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int co
   return 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// phovo::warpImage, CPhotoconsistencyOdometry.h:73-134 (post-hoc visualisation of both apps)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct WarpImgParams { double R[12]; double fx, fy, ox, oy, inv_fx, inv_fy; };
+
+template <typename DT>
+__global__ void __launch_bounds__(256) k_warp_splat(const uint8_t* __restrict__ gray, size_t gray_step, const DT* __restrict__ depth,
+                                                    size_t depth_step, double depth_scale, int rows, int cols,
+                                                    const __grid_constant__ WarpImgParams W, unsigned long long* __restrict__ keys) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    const DT* drow = (const DT*)((const char*)depth + (size_t)r * depth_step);
+    double d = (double)drow[c];
+    if (sizeof(DT) == 2) d = __dmul_rn(d, depth_scale);
+    if (!(d > 0.)) continue;                                                           // BASE:106
+    // BASE:109-112, fp64, the reference's operation order, no FMA contraction
+    const double px = __dmul_rn(__dmul_rn(__dsub_rn((double)c, W.ox), d), W.inv_fx);
+    const double py = __dmul_rn(__dmul_rn(__dsub_rn((double)r, W.oy), d), W.inv_fy);
+    // Eigen 4x4 * 4x1 (BASE:115): sum over k = 0..3 in order, the homogeneous 1 multiplies the translation
+    const double X = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(W.R[0], px), __dmul_rn(W.R[1], py)), __dmul_rn(W.R[2], d)), W.R[3]);
+    const double Y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(W.R[4], px), __dmul_rn(W.R[5], py)), __dmul_rn(W.R[6], d)), W.R[7]);
+    const double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(W.R[8], px), __dmul_rn(W.R[9], py)), __dmul_rn(W.R[10], d)), W.R[11]);
+    const double tc = __dadd_rn(__ddiv_rn(__dmul_rn(X, W.fx), Z), W.ox);               // BASE:118-121: true division
+    const double tr = __dadd_rn(__ddiv_rn(__dmul_rn(Y, W.fy), Z), W.oy);
+    // static_cast<int>: truncation toward zero; NaN / out-of-range (undefined in the reference) -> skipped
+    if (!(tc > -1. && tc < (double)cols && tr > -1. && tr < (double)rows)) continue;
+    const int tj = (int)tc, ti = (int)tr;
+    const unsigned long long key = ((unsigned long long)(i + 1) << 8) | gray[(size_t)r * gray_step + c];
+    atomicMax(keys + (size_t)ti * cols + tj, key);                                     // raster-order last writer wins
+  }
+}
+
+__global__ void __launch_bounds__(256) k_warp_resolve(const unsigned long long* __restrict__ keys, int rows, int cols,
+                                                      uint8_t* __restrict__ warped, size_t warped_step,
+                                                      const uint8_t* __restrict__ target, size_t target_step,
+                                                      uint8_t* __restrict__ diff, size_t diff_step) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    const unsigned long long k = keys[i];
+    const int v = k ? (int)(k & 0xffull) : 0;                                          // BASE:98 zeros()
+    warped[(size_t)r * warped_step + c] = (uint8_t)v;
+    if (diff) { const int t = target[(size_t)r * target_step + c]; diff[(size_t)r * diff_step + c] = (uint8_t)(t > v ? t - v : v - t); }
+  }
+}
+}  // namespace
+
+int launch_warp_image(cudaStream_t stream, const uint8_t* gray, size_t gray_step, const void* depth, int depth_type,
+                      size_t depth_step, double depth_scale, int rows, int cols, const double rt[16],
+                      double fx, double fy, double ox, double oy, unsigned long long* keys,
+                      uint8_t* warped, size_t warped_step, const uint8_t* target, size_t target_step,
+                      uint8_t* diff, size_t diff_step) {
+  WarpImgParams W;
+  for (int k = 0; k < 12; ++k) W.R[k] = rt[k];
+  W.fx = fx; W.fy = fy; W.ox = ox; W.oy = oy;
+  W.inv_fx = 1.f / fx; W.inv_fy = 1.f / fy;          // BASE:91-92
+  const size_t n = (size_t)rows * cols;
+  cudaMemsetAsync(keys, 0, n * sizeof(unsigned long long), stream);
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  switch (depth_type) {
+    case SRC_F32: k_warp_splat<float><<<blocks, 256, 0, stream>>>(gray, gray_step, (const float*)depth, depth_step, depth_scale, rows, cols, W, keys); break;
+    case SRC_U16: k_warp_splat<uint16_t><<<blocks, 256, 0, stream>>>(gray, gray_step, (const uint16_t*)depth, depth_step, depth_scale, rows, cols, W, keys); break;
+    default:      k_warp_splat<double><<<blocks, 256, 0, stream>>>(gray, gray_step, (const double*)depth, depth_step, depth_scale, rows, cols, W, keys); break;
+  }
+  k_warp_resolve<<<blocks, 256, 0, stream>>>(keys, rows, cols, warped, warped_step, target, target_step, diff, diff_step);
+  return 2;
+}
+
 }  // namespace phovo

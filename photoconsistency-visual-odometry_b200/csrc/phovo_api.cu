@@ -280,6 +280,7 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   cudaFree(ctx->stage_gray[0]); cudaFree(ctx->stage_gray[1]); cudaFree(ctx->stage_depth);
   cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_eval);
   cudaFree(ctx->dump_res); cudaFree(ctx->dump_jac);
+  cudaFree(ctx->warp_keys); for (int k = 0; k < 3; ++k) cudaFree(ctx->warp_io[k]);
   for (int r = 0; r < 8; ++r)
     if (ctx->xchg_opened[r]) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
   cudaFree(ctx->xchg_own); cudaFree(ctx->xchg_peers_dev);
@@ -726,6 +727,46 @@ extern "C" void phovo_state_to_rt(const double s[6], double P[16]) {
 extern "C" int phovo_get_rt(const phovo_ctx* ctx, double rt[16]) {
   if (!ctx || !rt) return PHOVO_E_INVALID;
   phovo_state_to_rt(ctx->state, rt);
+  return PHOVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics: phovo::warpImage + absdiff (BASE:73-134; apps :107-110 / :247-252)
+// ---------------------------------------------------------------------------------------------
+extern "C" int phovo_warp_image(phovo_ctx* ctx, const uint8_t* gray, size_t gray_step, const void* depth, int depth_type,
+                                size_t depth_step, double depth_scale, int rows, int cols, const double rt[16],
+                                const double K[9], int level, uint8_t* warped, size_t warped_step,
+                                const uint8_t* target, size_t target_step, uint8_t* diff, size_t diff_step) {
+  if (!ctx || !gray || !depth || !rt || !K || !warped) return PHOVO_E_INVALID;
+  if (rows < 1 || cols < 1 || level < 0 || level > 30) return ctx->fail(PHOVO_E_INVALID, "bad image size or level");
+  if (src_type_of_depth(depth_type) < 0) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
+  if ((diff != nullptr) != (target != nullptr)) return ctx->fail(PHOVO_E_INVALID, "target and diff must be given together");
+  if (gray_step < (size_t)cols || warped_step < (size_t)cols || depth_step < (size_t)cols * depth_elt(depth_type) ||
+      (diff && (target_step < (size_t)cols || diff_step < (size_t)cols)))
+    return ctx->fail(PHOVO_E_INVALID, "row stride smaller than a row");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)rows * cols;
+  CK(ensure(&ctx->warp_keys, &ctx->warp_keys_cap, n));
+  const void* dg; size_t dgs; const void* dd; size_t dds; int rc;
+  if ((rc = stage_image(ctx, gray, gray_step, 1, rows, cols, &ctx->stage_gray[0], &ctx->stage_gray_cap[0], &dg, &dgs))) return rc;
+  if ((rc = stage_image(ctx, depth, depth_step, depth_elt(depth_type), rows, cols, &ctx->stage_depth, &ctx->stage_depth_cap, &dd, &dds))) return rc;
+  const void* dt = nullptr; size_t dts = 0;
+  if (target && (rc = stage_image(ctx, target, target_step, 1, rows, cols, &ctx->warp_io[1], &ctx->warp_io_cap[1], &dt, &dts))) return rc;
+  ctx->h2d_pending = false;
+  // outputs: write in place for device callers, through a dense device buffer for host callers
+  uint8_t* dw = warped; size_t dws = warped_step; uint8_t* ddf = diff; size_t ddfs = diff_step;
+  const bool w_host = !is_device_pointer(warped), d_host = diff && !is_device_pointer(diff);
+  if (w_host) { CK(ensure(&ctx->warp_io[0], &ctx->warp_io_cap[0], n)); dw = (uint8_t*)ctx->warp_io[0]; dws = cols; }
+  if (d_host) { CK(ensure(&ctx->warp_io[2], &ctx->warp_io_cap[2], n)); ddf = (uint8_t*)ctx->warp_io[2]; ddfs = cols; }
+  const double p = pow(2, level);                                   // BASE:89-94: K / 2^level
+  ctx->launches += launch_warp_image(ctx->stream, (const uint8_t*)dg, dgs, dd, src_type_of_depth(depth_type), dds,
+                                     depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0, rows, cols, rt,
+                                     K[0] / p, K[4] / p, K[2] / p, K[5] / p, ctx->warp_keys, dw, dws,
+                                     (const uint8_t*)dt, dts, ddf, ddfs);
+  CK(cudaGetLastError());
+  if (w_host) CK(cudaMemcpy2DAsync(warped, warped_step, dw, dws, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_host) CK(cudaMemcpy2DAsync(diff, diff_step, ddf, ddfs, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return PHOVO_OK;
 }
 

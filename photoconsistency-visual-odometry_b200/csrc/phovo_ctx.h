@@ -44,6 +44,9 @@ struct phovo_ctx {
   char* stage_depth = nullptr; size_t stage_depth_cap = 0;
   double* dump_res = nullptr; size_t dump_res_cap = 0;
   double* dump_jac = nullptr; size_t dump_jac_cap = 0;
+  // phovo_warp_image scratch
+  unsigned long long* warp_keys = nullptr; size_t warp_keys_cap = 0;
+  char* warp_io[3] = {nullptr, nullptr, nullptr}; size_t warp_io_cap[3] = {0, 0, 0};   // device copies of warped / target / diff for host callers
 
   // solver state
   double state[6] = {0};

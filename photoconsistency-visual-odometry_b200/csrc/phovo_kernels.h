@@ -25,6 +25,14 @@ int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows
 int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
                         double* Gx, double* Gy);
 
+// phovo::warpImage (BASE:73-134): splat keys (source index << 8 | intensity) with a 64-bit atomicMax,
+// then resolve to u8 (+ optional |target - warped|).  `keys` has rows*cols entries, zeroed here.
+int launch_warp_image(cudaStream_t stream, const uint8_t* gray, size_t gray_step, const void* depth, int depth_type,
+                      size_t depth_step, double depth_scale, int rows, int cols, const double rt[16],
+                      double fx, double fy, double ox, double oy, unsigned long long* keys,
+                      uint8_t* warped, size_t warped_step, const uint8_t* target, size_t target_step,
+                      uint8_t* diff, size_t diff_step);
+
 // ---- alignment (kernels_align.cu) ------------------------------------------------------------
 struct LevelPtrs {
   const double* I0; const double* D0; const double* I1; const double* Gx; const double* Gy;

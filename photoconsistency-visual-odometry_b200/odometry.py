@@ -117,6 +117,26 @@ class CPhotoconsistencyOdometryCuda:
         self._check(self._L.phovo_get_rt(self._h, m.ctypes.data_as(capi._dp)))
         return m.reshape(4, 4)
 
+    # -- diagnostics of the apps (phovo::warpImage, CPhotoconsistencyOdometry.h:73-134) ------
+    def WarpImage(self, intensityImage, depthImage, Rt, intrinsicMatrix, level=0, targetImage=None, depth_scale=1.0):
+        """Returns the warped source image (u8); with `targetImage` also |target - warped| as the
+        apps display it (FrameAlignment.cpp:107-110).  numpy inputs."""
+        g, gstep, gptr, shape = self._gray_args(np.ascontiguousarray(intensityImage))
+        d, dtype, dstep, dptr = self._depth_args(np.ascontiguousarray(depthImage), depth_scale)
+        rt = np.ascontiguousarray(Rt, dtype=np.float64).reshape(16)
+        K = np.ascontiguousarray(intrinsicMatrix, dtype=np.float64).reshape(9)
+        warped = np.zeros(shape, np.uint8)
+        diff = tgt = None
+        if targetImage is not None:
+            tgt = np.ascontiguousarray(targetImage, dtype=np.uint8)
+            diff = np.zeros(shape, np.uint8)
+        self._check(self._L.phovo_warp_image(self._h, gptr, gstep, dptr, dtype, dstep, float(depth_scale), shape[0], shape[1],
+                                             rt.ctypes.data_as(capi._dp), K.ctypes.data_as(capi._dp), int(level),
+                                             warped.ctypes.data, warped.strides[0],
+                                             None if tgt is None else tgt.ctypes.data, 0 if tgt is None else tgt.strides[0],
+                                             None if diff is None else diff.ctypes.data, 0 if diff is None else diff.strides[0]))
+        return warped if diff is None else (warped, diff)
+
     # -- extensions (not in the reference) --------------------------------------------------
     def SetConfig(self, cfg):
         self._check(self._L.phovo_set_config(self._h, C.byref(cfg)))

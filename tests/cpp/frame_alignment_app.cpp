@@ -127,6 +127,17 @@ int main( int argc, char ** argv )
       for( int i = 0; i < 4; i++ ) for( int j = 0; j < 4; j++ ) std::cout << " " << Rt( i, j );
       std::cout << std::endl;
       std::cout << "iterations " << photoconsistencyOdometry.GetIterationStats().size() << std::endl;
+      // FrameAlignment.cpp:106-110: warp the source with the result and compare with the target
+      IntensityImageType warpedImage;
+      photoconsistencyOdometry.WarpImage( imgGray0, imgDepth0, warpedImage, Rt, intrinsicMatrix );
+      unsigned long long sumAbsDiff = 0, written = 0;
+      for( int r = 0; r < rows; r++ )
+        for( int c = 0; c < cols; c++ )
+        {
+          const int w = warpedImage( r, c ), t = imgGray1( r, c );
+          if( w ) { written++; sumAbsDiff += (unsigned long long)( w > t ? w - t : t - w ); }
+        }
+      std::cout << "warped " << written << " " << sumAbsDiff << std::endl;
       return 0;
     }
     if( mode == "vo" )

@@ -44,5 +44,19 @@ def main():
         print(name, len(iters), "iterations", s)
 
 
+def warp_golden():
+    """phovo::warpImage (CPhotoconsistencyOdometry.h:73-134) run from the reference source."""
+    K = np.array([[131.25, 0., 79.5], [0., 131.25, 59.5], [0., 0., 1.]])
+    g0, d0, g1, xi = phovo.synth.make_pair(120, 160, K=K, seed=35)
+    rt = phovo.state_to_rt(np.array([0.03, -0.02, 0.05, 0.02, -0.015, 0.01]))
+    out = {"gray0": g0, "depth0": d0.astype(np.float32), "gray1": g1, "K": K, "rt": rt}
+    for level in (0, 1):
+        Kl = K.copy(); Kl[:2] /= 2 ** level      # the reference divides K by 2^level inside warpImage; level 0 here, scaled K for level 1
+        out["warped_l%d" % level] = ref_py.warp_image(g0, d0, rt, Kl)
+    np.savez_compressed(os.path.join(HERE, "ref_warp_image_120x160.npz"), **out)
+    print("ref_warp_image_120x160", int((out["warped_l0"] > 0).sum()), "pixels written")
+
+
 if __name__ == "__main__":
+    warp_golden()
     main()

@@ -60,6 +60,12 @@ def test_frame_alignment_app_matches_oracle(phovo, oracle, tmp_path):
     assert_pose_close(state, o.state(), "C++ adapter")
     assert np.max(np.abs(state - o.state())) < 1e-10
     assert np.max(np.abs(Rt - o.rt())) < 1e-10
+    # the app's warpImage step through the adapter: same image as the Python binding produces
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    w = odo.WarpImage(g0, d0.astype(np.float64), Rt, K)
+    mask = w > 0
+    assert int(out["warped"][0]) == int(mask.sum())
+    assert int(out["warped"][1]) == int(np.abs(w.astype(np.int64) - g1.astype(np.int64))[mask].sum())
 
 
 @pytest.mark.gpu

@@ -20,7 +20,7 @@ import pytest
 from helpers import GOLDEN, REL_NORMAL_EQ, assert_pose_close, g_rel_err, h_rel_err
 from test_gpu_parity import conv_cfg, make_odo
 
-REF_FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+REF_FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_pair_*.npz")))
 IDX = [(a, b) for a in range(6) for b in range(a, 6)]
 
 
