@@ -164,3 +164,30 @@ def test_batch_unsupported_configurations_fail_loudly(phovo):
     odo.SetConfig(cfg)
     st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((1, 6), 0.01))
     assert np.array_equal(st, np.full((1, 6), 0.01)) and not it.any()
+
+
+def test_batch_at_scale_matches_general_path(phovo):
+    """Size-independent property at a BASELINE-sized workload: every pair of a 296-pair 640x480
+    batch (two full waves of persistent CTAs, dynamic scheduling, both kernel variants) gets the
+    pose and iteration counts the per-pair general path computes for it, and a second run is
+    bitwise identical."""
+    import torch
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    P = 296
+    g0, d0, g1, _ = phovo.synth.render_batch_torch(P, 480, 640, K, torch.device("cuda", 0), seed0=900)
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    odo = make_odo(phovo, cfg, K)
+    st, it = odo.BatchAlign(g0, d0, g1)
+    st2, it2 = odo.BatchAlign(g0, d0, g1)
+    assert np.array_equal(st, st2) and np.array_equal(it, it2)
+    assert np.isfinite(st).all() and it[:, 2].min() >= 1 and it[:, 3].min() >= 1 and it[:, 3].max() <= 50
+    worst = 0.
+    for p in range(0, P, 7):
+        odo.SetSourceFrame(g0[p], d0[p])
+        odo.SetTargetFrame(g1[p])
+        odo.SetInitialStateVector(np.zeros(6))
+        odo.Optimize()
+        log = odo.IterationStats()
+        assert [sum(1 for e in log if e["level"] == l) for l in (2, 3)] == [int(it[p, 2]), int(it[p, 3])], p
+        worst = max(worst, float(np.max(np.abs(odo.GetOptimalStateVector() - st[p]))))
+    assert worst < 1e-9, worst

@@ -431,6 +431,27 @@ def test_ceres_mode_residual_jacobian_and_lm(phovo, oracle):
     assert np.max(np.abs(s - o.state())) < 1e-10
 
 
+def test_ceres_config_5_level_640x480(phovo, oracle):
+    """BASELINE configs[2]: config_5_level_optimization_ceres on a 640x480 pair -- levels 0 and 1 ARE
+    optimised here (307 200 / 76 800 px).  GPU residual evaluation + restated LM against the oracle's:
+    same accept/reject sequence, costs and final pose.  (The LM itself is a restatement of Ceres'
+    documented algorithm: parity with the real Ceres trajectory is unpinned)"""
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    g0, d0, g1, _ = phovo.synth.make_pair(480, 640, K=K, seed=13)
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
+    odo = make_odo(phovo, cfg, K)
+    s, log = run_gpu(odo, g0, d0, g1)
+    o = run_oracle(oracle, cfg, K, g0, d0, g1)
+    olog = o.iter_stats()
+    assert len(log) > 0
+    assert [(e["level"], e["iteration"], e["accepted"]) for e in log] == [(e["level"], e["iteration"], e["accepted"]) for e in olog]
+    for a, b in zip(log, olog):
+        assert a["num_valid"] == b["num_valid"]
+        assert abs(a["cost"] - b["cost"]) < 1e-9 * b["cost"]
+    assert_pose_close(s, o.state(), "ceres config 5")
+    assert np.max(np.abs(s - o.state())) < 1e-9
+
+
 def test_error_paths(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_pair(60, 80, seed=1)
