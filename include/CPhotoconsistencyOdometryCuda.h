@@ -58,7 +58,8 @@ public:
 
   /*!mode: PHOVO_MODE_ANALYTIC_REF reproduces CPhotoconsistencyOdometryAnalytic bit-for-bit in
    * semantics (including AN:253); PHOVO_MODE_ANALYTIC_FIXED uses the Maxima-exact Jacobian;
-   * PHOVO_MODE_CERES evaluates the CPhotoconsistencyOdometryCeres residual.*/
+   * PHOVO_MODE_CERES evaluates the CPhotoconsistencyOdometryCeres residual; PHOVO_MODE_BIOBJECTIVE is
+   * CPhotoconsistencyOdometryBiObjective (photometric + depth rows).*/
   explicit CPhotoconsistencyOdometryCuda( int device = 0, int mode = PHOVO_MODE_ANALYTIC_REF ) : m_Ctx( 0 )
   {
     static_assert( sizeof( TPixel ) == 1, "intensity images must be 8-bit" );
@@ -104,12 +105,18 @@ public:
                              intensityImage.rows, intensityImage.cols ), "phovo_set_source" );
   }
 
-  /*!Sets the target (Intensity+Depth) frame (AN:479-491; the reference ignores the depth image).*/
+  /*!Sets the target (Intensity+Depth) frame (AN:479-491). The analytic and Ceres solvers ignore the
+   * depth image like the reference does; the photometric + depth solver (PHOVO_MODE_BIOBJECTIVE,
+   * CPhotoconsistencyOdometryBiObjective.h:567-579) uses it.*/
   void SetTargetFrame( const IntensityImageType & intensityImage,
-                       const DepthImageType & /*depthImage*/ )
+                       const DepthImageType & depthImage )
   {
     Check( phovo_set_target( m_Ctx, reinterpret_cast< const uint8_t * >( intensityImage.data ), size_t( intensityImage.step ),
                              intensityImage.rows, intensityImage.cols ), "phovo_set_target" );
+    phovo_config cfg; Check( phovo_get_config( m_Ctx, &cfg ), "phovo_get_config" );
+    if( cfg.mode == PHOVO_MODE_BIOBJECTIVE )
+      Check( phovo_set_target_depth( m_Ctx, depthImage.data, detail::DepthTypeOf< TCoordinate >::value,
+                                     size_t( depthImage.step ), 1.0 ), "phovo_set_target_depth" );
   }
 
   /*!Initializes the state vector to a certain value (AN:494-497): x, y, z, yaw, pitch, roll.*/

@@ -47,6 +47,8 @@ extern "C" {
 #define PHOVO_MODE_ANALYTIC_REF   0 /* bug-compatible with AN:253 (temp11 = cos*cos + x), default */
 #define PHOVO_MODE_ANALYTIC_FIXED 1 /* Maxima-exact Jacobian (phovo/Maxima/derivatives_photoconsistency.wxm) */
 #define PHOVO_MODE_CERES          2 /* CE:156-269 residual (bilinear, truncation scatter) + restated LM */
+#define PHOVO_MODE_BIOBJECTIVE    3 /* CPhotoconsistencyOdometryBiObjective.h:242-452: photometric + depth rows,
+                                       including its row aliasing (depth rows at 2*i collide with intensity rows at i) */
 
 /* depth element types accepted at the boundary */
 #define PHOVO_DEPTH_F64 0 /* cv::Mat_<double>, what both reference apps pass */
@@ -142,6 +144,11 @@ int phovo_set_source(phovo_ctx* ctx, const uint8_t* gray, size_t gray_step,
 /* SetTargetFrame (AN:479-491): the reference ignores the target depth (only .type(), AN:484);
  * builds the I1 pyramid and the Scharr gradient pyramids (AN:165-189). */
 int phovo_set_target(phovo_ctx* ctx, const uint8_t* gray, size_t gray_step, int rows, int cols);
+/* Target depth (metres), needed by PHOVO_MODE_BIOBJECTIVE only -- the analytic and Ceres solvers ignore
+ * it like the reference does.  Call after phovo_set_target with the same frame size: builds the target
+ * depth pyramid, the Scharr pyramids of depth / max_depth and the per-level gain mean(I1)/mean(D1)
+ * (CPhotoconsistencyOdometryBiObjective.h:213-239, 299, 567-579). */
+int phovo_set_target_depth(phovo_ctx* ctx, const void* depth, int depth_type, size_t depth_step, double depth_scale);
 /* VO loop helper (apps/PhotoconsistencyVisualOdometry/PhotoconsistencyVisualOdometry.cpp:222-223,256):
  * the previous target's intensity pyramid becomes the source intensity pyramid on the device;
  * only the depth of that frame has to be supplied. */

@@ -46,6 +46,17 @@ def lib():
         L.ref_num_iterations.argtypes = [vp]
         L.ref_get_iteration.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, dp]
         L.ref_warp_image.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, vp]
+        L.refbi_create.restype = vp
+        L.refbi_destroy.argtypes = [vp]
+        L.refbi_read_config.argtypes = [vp, C.c_char_p]
+        L.refbi_set_intrinsics.argtypes = [vp, dp]
+        L.refbi_set_source.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.refbi_set_target.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.refbi_set_initial_state.argtypes = [vp, dp]
+        L.refbi_optimize.argtypes = [vp]
+        L.refbi_get_state.argtypes = [vp, dp]
+        L.refbi_num_iterations.argtypes = [vp]
+        L.refbi_get_iteration.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, dp]
         _lib = L
     return _lib
 
@@ -91,6 +102,44 @@ class Reference:
             self.L.ref_get_iteration(self.h, i, C.byref(n), _dp(H), _dp(g))
             iters.append(dict(n=n.value, H=H.reshape(6, 6), g=g))
         return s, rt.reshape(4, 4), iters
+
+
+class ReferenceBiObjective:
+    """The reference's photometric + depth solver (CPhotoconsistencyOdometryBiObjective.h), driven like
+    the apps drive it; the target frame's depth IS used here."""
+
+    def __init__(self, config_yaml, K):
+        self.L = lib()
+        self.h = self.L.refbi_create()
+        self.L.refbi_read_config(self.h, os.fsencode(config_yaml))
+        self.K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        self.L.refbi_set_intrinsics(self.h, _dp(self.K))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refbi_destroy(self.h)
+            self.h = None
+
+    def align(self, gray0, depth0, gray1, depth1, state0=None):
+        g0 = np.ascontiguousarray(gray0, dtype=np.uint8)
+        d0 = np.ascontiguousarray(depth0, dtype=np.float64)
+        g1 = np.ascontiguousarray(gray1, dtype=np.uint8)
+        d1 = np.ascontiguousarray(depth1, dtype=np.float64)
+        r, c = g0.shape
+        self.L.refbi_set_source(self.h, g0.ctypes.data, d0.ctypes.data, r, c)
+        self.L.refbi_set_target(self.h, g1.ctypes.data, d1.ctypes.data, r, c)
+        s0 = np.zeros(6) if state0 is None else np.ascontiguousarray(state0, dtype=np.float64)
+        self.L.refbi_set_initial_state(self.h, _dp(s0))
+        self.L.refbi_optimize(self.h)
+        s = np.zeros(6)
+        self.L.refbi_get_state(self.h, _dp(s))
+        iters = []
+        for i in range(self.L.refbi_num_iterations(self.h)):
+            n = C.c_int()
+            H, g = np.zeros(36), np.zeros(6)
+            self.L.refbi_get_iteration(self.h, i, C.byref(n), _dp(H), _dp(g))
+            iters.append(dict(n=n.value, H=H.reshape(6, 6), g=g))
+        return s, iters
 
 
 def warp_image(gray, depth, rt, K):

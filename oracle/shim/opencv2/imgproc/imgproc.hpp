@@ -107,6 +107,18 @@ inline void Scharr( const Mat_< double > & src, Mat_< double > & dst, int /*ddep
   dst = out;
 }
 
+// cv::mean of a single-channel image: only .val[0] is used by the reference (BiObjective.h:299)
+struct Scalar { double val[4]; };
+inline Scalar mean( const Mat_< double > & src )
+{
+  Scalar s; s.val[0] = s.val[1] = s.val[2] = s.val[3] = 0.;
+  const size_t n = size_t( src.rows ) * size_t( src.cols );
+  double acc = 0.;
+  for( size_t k = 0; k < n; k++ ) acc += src( int( k ) );
+  s.val[0] = n ? acc / double( n ) : 0.;
+  return s;
+}
+
 template< class T >
 inline void absdiff( const Mat_< T > &, const Mat_< T > &, Mat_< T > & ) {}
 template< class T >

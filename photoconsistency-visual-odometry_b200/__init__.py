@@ -13,7 +13,7 @@ synth.py (deterministic synthetic RGB-D scene), build.py (in-tree nvcc build).
 """
 from . import capi, configs, sharded, synth  # noqa: F401
 from .capi import (Config, IterStats, PhovoError, MODE_ANALYTIC_REF, MODE_ANALYTIC_FIXED,  # noqa: F401
-                   MODE_CERES, DEPTH_F64, DEPTH_F32, DEPTH_U16, MAXL, default_config,
+                   MODE_CERES, MODE_BIOBJECTIVE, DEPTH_F64, DEPTH_F32, DEPTH_U16, MAXL, default_config,
                    parse_config_yaml, state_to_rt)
 from .odometry import CPhotoconsistencyOdometryCuda  # noqa: F401
 from .build import build  # noqa: F401

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libphovo_b200.so")
 MAXL = 10
 
 OK, E_INVALID, E_CUDA, E_CONFIG, E_NOMEM, E_UNSUPPORTED, E_NUMERIC = 0, -1, -2, -3, -4, -5, -6
-MODE_ANALYTIC_REF, MODE_ANALYTIC_FIXED, MODE_CERES = 0, 1, 2
+MODE_ANALYTIC_REF, MODE_ANALYTIC_FIXED, MODE_CERES, MODE_BIOBJECTIVE = 0, 1, 2, 3
 DEPTH_F64, DEPTH_F32, DEPTH_U16 = 0, 1, 2
 
 
@@ -71,6 +71,7 @@ SIGNATURES = {
     "phovo_set_source": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int]),
     "phovo_set_target": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
     "phovo_promote_target_to_source": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_double]),
+    "phovo_set_target_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_double]),
     "phovo_set_initial_state": (C.c_int, [_vp, _dp]),
     "phovo_optimize": (C.c_int, [_vp]),
     "phovo_get_state": (C.c_int, [_vp, _dp]),

@@ -175,6 +175,100 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq(LevelParams L, LevelPtrs P
   if (threadIdx.x < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + threadIdx.x] = total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Photometric + depth solver (CPhotoconsistencyOdometryBiObjective.h:242-452), PHOVO_MODE_BIOBJECTIVE.
+//
+// The reference stacks 2N rows.  Source pixel i (raster order = time i) writes, in this order:
+//   jacobians row i      = intensity Jacobian          residuals slot t(i)     = I1[t] - I0[i]
+//   jacobians row 2 i    = depth Jacobian              residuals slot 2 t(i)   = gain (D1[t] - D0[i])
+// so depth rows of pixel i collide with intensity rows of pixel 2i and later writers win
+// (BiObjective.h:422-442).  Gather form, bit-for-bit in semantics:
+//   Jacobian row k = intensity row of pixel k      if k < N, k > 0 and pixel k valid   (time k beats time k/2)
+//                  = depth row of pixel k/2        else if k even and pixel k/2 valid   (row 0: depth is written last)
+//                  = 0                             otherwise
+//   residual slot s = the write with the largest (time, kind) among intensity writes with t(i) = s
+//                     and depth writes with 2 t(i) = s  ->  atomicMax of the key 2 i + kind + 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_winner_bi(LevelParams L, LevelPtrs P, const PoseDev* __restrict__ pose) {
+  if (pose->done) return;
+  Pose T;
+  pose_load(pose, T);
+  const int n = L.rows * L.cols;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const double d = __ldg(P.D0 + i);
+    const int r = i / L.cols, c = i - r * L.cols;
+    Warped w;
+    const bool ok = warp_pixel<false>(L, T, r, c, d, w);       // same validity rule as the analytic solver (:279-303)
+    if (ok) {
+      atomicMax(P.winner + w.t, 2 * i + 1);                     // intensity residual (:433)
+      atomicMax(P.winner + 2 * w.t, 2 * i + 2);                 // depth residual (:444-445), written after it
+    }
+    P.valid[i] = ok;
+  }
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kBlock) k_normal_eq_bi(LevelParams L, LevelPtrs P, const PoseDev* __restrict__ pose,
+                                                         double* __restrict__ partials,
+                                                         double* __restrict__ dump_res, double* __restrict__ dump_jac) {
+  __shared__ double smem[(kBlock / 32) * PHOVO_ACC_STRIDE];
+  if (pose->done) return;
+  Pose T;
+  pose_load(pose, T);
+  const double gain = __ldg(P.gain);
+  double acc[PHOVO_NACC];
+#pragma unroll
+  for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+  const int n = L.rows * L.cols;
+  const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
+  for (int k = blockIdx.x * kBlock + threadIdx.x; k < 2 * n; k += gridDim.x * kBlock) {
+    const int wkey = P.winner[k];
+    P.winner[k] = -1;
+    double res = 0.;
+    if (wkey > 0) {
+      const int src = (wkey - 1) >> 1;
+      if (((wkey - 1) & 1) == 0) res = __ldg(P.I1 + k) - __ldg(P.I0 + src);                     // slot k = t
+      else res = gain * (__ldg(P.D1 + (k >> 1)) - __ldg(P.D0 + src));                           // slot k = 2 t
+      acc[27] = fma(res, res, acc[27]);
+    }
+    if (DUMP && dump_res) dump_res[k] = res;
+    int p = -1; bool depth_row = false;
+    if (k > 0 && k < n && P.valid[k]) p = k;
+    else if ((k & 1) == 0 && P.valid[k >> 1]) { p = k >> 1; depth_row = true; }
+    if (k < n && P.valid[k]) acc[28] += 1.;
+    if (p < 0) continue;
+    const int r = p / L.cols, c = p - r * L.cols;
+    const double d = __ldg(P.D0 + p);
+    const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+    const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+    const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+    const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+    const double X = q0 + T.x, Y = q1 + T.y;
+    const double iz = 1.0 / (q2 + T.z);
+    // d(R p)/d(yaw, pitch, roll), BiObjective.h:364-377 in closed form
+    const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+    const double dp0 = T.cy * q2, dp1 = T.sy * q2;
+    const double dr0 = fma(T.R02, py, -(T.R01 * d)), dr1 = fma(T.R12, py, -(T.R11 * d)), dr2 = fma(T.R22, py, -(T.R21 * d));
+    // v = gradient * projection Jacobian (:380-400), then v * jacobianRt
+    const double gx = depth_row ? __ldg(P.GxD + p) : __ldg(P.Gx + p), gy = depth_row ? __ldg(P.GyD + p) : __ldg(P.Gy + p);
+    const double v0 = gx * L.fx * iz, v1 = gy * L.fy * iz;
+    const double v2 = -(fma(gx * L.fx, X, gy * L.fy * Y) * iz * iz);
+    double J[6];
+    J[0] = v0; J[1] = v1; J[2] = v2;
+    J[3] = fma(v1, q0, -(v0 * q1));
+    J[4] = fma(v0, dp0, fma(v1, dp1, v2 * Zp));
+    J[5] = fma(v0, dr0, fma(v1, dr1, v2 * dr2));
+    if (depth_row) {   // gain * (v * jacobianRt - jacobianRt_z), :404-414
+      J[0] = gain * J[0]; J[1] = gain * J[1]; J[2] = gain * (J[2] - 1.);
+      J[3] = gain * J[3]; J[4] = gain * (J[4] - Zp); J[5] = gain * (J[5] - dr2);
+    }
+    accumulate_row(acc, J, res);
+    if (DUMP && dump_jac) for (int a = 0; a < 6; ++a) dump_jac[(size_t)k * 6 + a] = J[a];
+  }
+  const double total = block_reduce<kBlock>(acc, smem);
+  if (threadIdx.x < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + threadIdx.x] = total;
+}
+
 // Sum partials[0..grid) for each of the PHOVO_NACC values in a fixed order: warp v owns value v,
 // lane l adds blocks l, l+32, ... in order, then a fixed butterfly over lanes.  Needs 32 warps.
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int grid, double* totals /* smem[32] */) {
@@ -465,6 +559,14 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
   const int grid = grid_for(n);
   int launches = 0;
   if (clear_winner_first) launches += launch_fill_i32(stream, P.winner, -1, (size_t)n);
+  if (L.mode == PHOVO_MODE_BIOBJECTIVE) {
+    k_winner_bi<<<grid, kBlock, 0, stream>>>(L, P, pose);
+    const int grid2 = grid_for(2 * n);
+    if (dump_res || dump_jac) k_normal_eq_bi<true><<<grid2, kBlock, 0, stream>>>(L, P, pose, partials, dump_res, dump_jac);
+    else k_normal_eq_bi<false><<<grid2, kBlock, 0, stream>>>(L, P, pose, partials, nullptr, nullptr);
+    *grid_out = grid2;
+    return launches + 2;
+  }
   if (L.mode == PHOVO_MODE_CERES) k_winner<true><<<grid, kBlock, 0, stream>>>(L, P, pose);
   else k_winner<false><<<grid, kBlock, 0, stream>>>(L, P, pose);
   const bool dump = dump_res || dump_jac;

@@ -179,6 +179,38 @@ int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int co
 
 
 // ---------------------------------------------------------------------------------------------
+// helpers of the photometric + depth solver (BiObjective.h:213-239, 299)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_scale(const double* __restrict__ src, double alpha, double* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = __dmul_rn(src[i], alpha);
+}
+// one CTA, fixed order: thread t sums elements t, t+1024, ...; then a fixed tree over the threads
+__global__ void __launch_bounds__(1024) k_mean_ratio(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* out) {
+  __shared__ double sa[1024], sb[1024];
+  double x = 0., y = 0.;
+  for (size_t i = threadIdx.x; i < n; i += 1024) { x += a[i]; y += b[i]; }
+  sa[threadIdx.x] = x; sb[threadIdx.x] = y;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (sa[0] / (double)n) / (sb[0] / (double)n);   // cv::mean(I).val[0] / cv::mean(D).val[0]
+}
+}  // namespace
+
+int launch_scale(cudaStream_t stream, const double* src, double alpha, double* dst, size_t n) {
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  k_scale<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(src, alpha, dst, n);
+  return 1;
+}
+int launch_mean_ratio(cudaStream_t stream, const double* a, const double* b, size_t n, double* out) {
+  k_mean_ratio<<<1, 1024, 0, stream>>>(a, b, n, out);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // phovo::warpImage, CPhotoconsistencyOdometry.h:73-134 (post-hoc visualisation of both apps)
 // ---------------------------------------------------------------------------------------------
 namespace {

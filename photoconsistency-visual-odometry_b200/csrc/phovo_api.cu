@@ -69,6 +69,7 @@ LevelPtrs phovo_ctx::level_ptrs(int level) const {
   P.I0 = I0[level]; P.D0 = D0[level]; P.I1 = I1[level]; P.Gx = Gx[level]; P.Gy = Gy[level];
   P.winner = winner;
   P.valid = valid;
+  P.D1 = D1[level]; P.GxD = GxD[level]; P.GyD = GyD[level]; P.gain = d_gain ? d_gain + level : nullptr;
   return P;
 }
 
@@ -124,7 +125,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
   if (max_px == 0) max_px = 1;
   {
     int* before = ctx->winner;
-    CK(ensure(&ctx->winner, &ctx->winner_cap, max_px));
+    CK(ensure(&ctx->winner, &ctx->winner_cap, 2 * max_px));   // the photometric + depth solver stacks 2N rows
     if (before != ctx->winner) {
       changed = true;
       launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap);
@@ -276,6 +277,8 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
     cudaFree(ctx->I0[l]); cudaFree(ctx->D0[l]); cudaFree(ctx->I1[l]); cudaFree(ctx->Gx[l]); cudaFree(ctx->Gy[l]);
   }
+  for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) { cudaFree(ctx->D1[l]); cudaFree(ctx->GxD[l]); cudaFree(ctx->GyD[l]); }
+  cudaFree(ctx->d_gain);
   cudaFree(ctx->winner); cudaFree(ctx->valid); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
   cudaFree(ctx->stage_gray[0]); cudaFree(ctx->stage_gray[1]); cudaFree(ctx->stage_depth);
   cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_eval);
@@ -303,7 +306,7 @@ extern "C" int phovo_config_default(phovo_config* cfg) {
 
 static int validate_config(phovo_ctx* ctx, const phovo_config* cfg) {
   if (cfg->num_levels < 1 || cfg->num_levels > PHOVO_MAX_LEVELS) return ctx->fail(PHOVO_E_INVALID, "num_levels must be in [1, PHOVO_MAX_LEVELS]");
-  if (cfg->mode < 0 || cfg->mode > 2) return ctx->fail(PHOVO_E_INVALID, "unknown mode");
+  if (cfg->mode < 0 || cfg->mode > 3) return ctx->fail(PHOVO_E_INVALID, "unknown mode");
   long total = 0;
   for (int l = 0; l < cfg->num_levels; ++l) {
     const int k = cfg->blur_filter_size[l];
@@ -350,7 +353,7 @@ extern "C" int phovo_load_config_yaml(phovo_ctx* ctx, const char* path) {
 }
 
 extern "C" int phovo_set_mode(phovo_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 2) return PHOVO_E_INVALID;
+  if (!ctx || mode < 0 || mode > 3) return PHOVO_E_INVALID;
   if (ctx->cfg.mode != mode) {
     ctx->cfg.mode = mode;
     ctx->invalidate_graph();
@@ -445,6 +448,39 @@ extern "C" int phovo_set_target(phovo_ctx* ctx, const uint8_t* gray, size_t gray
   if ((rc = build_intensity(ctx, dg, dgs, true))) return rc;
   CK(cudaEventRecord(ctx->ev_time[1], ctx->stream));
   ctx->have_tgt = true;
+  ctx->have_tgt_depth = false;
+  return wait_uploads(ctx);
+}
+
+extern "C" int phovo_set_target_depth(phovo_ctx* ctx, const void* depth, int depth_type, size_t depth_step, double depth_scale) {
+  if (!ctx || !depth) return PHOVO_E_INVALID;
+  if (!ctx->have_tgt) return ctx->fail(PHOVO_E_INVALID, "SetTargetFrame must be called before the target depth is set");
+  if (src_type_of_depth(depth_type) < 0) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
+  if (depth_step < (size_t)ctx->cols * depth_elt(depth_type)) return ctx->fail(PHOVO_E_INVALID, "row stride smaller than a row");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_gain) CK(cudaMalloc((void**)&ctx->d_gain, sizeof(double) * PHOVO_MAX_LEVELS));
+  const void* dd; size_t dds; int rc;
+  if ((rc = stage_image(ctx, depth, depth_step, depth_elt(depth_type), ctx->rows, ctx->cols, &ctx->stage_depth, &ctx->stage_depth_cap, &dd, &dds))) return rc;
+  if ((rc = finish_uploads(ctx))) return rc;
+  for (int l = 0; l < ctx->cfg.num_levels; ++l) {
+    if (!ctx->level_active(l)) continue;
+    const int r = ctx->lrows[l], c = ctx->lcols[l];
+    const size_t n = (size_t)r * c;
+    double** arrs[3] = {&ctx->D1[l], &ctx->GxD[l], &ctx->GyD[l]};
+    for (int a = 0; a < 3; ++a) {
+      double* before = *arrs[a];
+      CK(ensure(arrs[a], &ctx->bcap[l][a], n));
+      if (before != *arrs[a]) ctx->invalidate_graph();
+    }
+    // BiObjective.h:574 (depth pyramid, no blur), :224-237 (Scharr of depth / m_MaxDepth), :299 (gain)
+    ctx->launches += launch_build_level(ctx->stream, dd, src_type_of_depth(depth_type), dds, depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0,
+                                        ctx->rows, ctx->cols, l, ctx->D1[l], r, c);
+    ctx->launches += launch_scale(ctx->stream, ctx->D1[l], 1. / ctx->cfg.max_depth, ctx->scratch64[0], n);
+    ctx->launches += launch_scharr_store(ctx->stream, ctx->scratch64[0], r, c, ctx->cfg.grad_scale[l], ctx->GxD[l], ctx->GyD[l]);
+    ctx->launches += launch_mean_ratio(ctx->stream, ctx->I1[l], ctx->D1[l], n, ctx->d_gain + l);
+  }
+  CK(cudaGetLastError());
+  ctx->have_tgt_depth = true;
   return wait_uploads(ctx);
 }
 
@@ -482,6 +518,8 @@ extern "C" int phovo_set_initial_state(phovo_ctx* ctx, const double state[6]) {
 static int ready_to_solve(phovo_ctx* ctx) {
   if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
   if (!ctx->have_src || !ctx->have_tgt) return ctx->fail(PHOVO_E_INVALID, "source and target frames must be set before Optimize");
+  if (ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE && !ctx->have_tgt_depth)
+    return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth (phovo_set_target_depth)");
   return PHOVO_OK;
 }
 
@@ -654,7 +692,7 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
   ctx->last_used_graph = 0;
   ctx->last_path = 0;
   if (ctx->cfg.mode == PHOVO_MODE_CERES) return optimize_ceres(ctx);
-  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
+  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1 && ctx->cfg.mode != PHOVO_MODE_BIOBJECTIVE) {
     bool unavailable = false;
     rc = optimize_coop(ctx, &unavailable);
     if (rc) return rc;
@@ -824,7 +862,7 @@ extern "C" int phovo_eval_residuals(phovo_ctx* ctx, int level, const double stat
   if (rc) return rc;
   if (level < 0 || level >= ctx->cfg.num_levels || !ctx->level_active(level)) return ctx->fail(PHOVO_E_INVALID, "level not built");
   CK(cudaSetDevice(ctx->device));
-  const size_t n = (size_t)ctx->lrows[level] * ctx->lcols[level];
+  const size_t n = (size_t)ctx->lrows[level] * ctx->lcols[level] * (ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : 1);
   CK(ensure(&ctx->dump_res, &ctx->dump_res_cap, n));
   CK(ensure(&ctx->dump_jac, &ctx->dump_jac_cap, n * 6));
   CK(cudaMemsetAsync(ctx->dump_res, 0, sizeof(double) * n, ctx->stream));

@@ -105,7 +105,8 @@ static void level_size(int rows, int cols, int level, int* orows, int* ocols) {
 static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, size_t* smem_out) {
   if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
   if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
-  if (ctx->cfg.mode == PHOVO_MODE_CERES) return ctx->fail(PHOVO_E_UNSUPPORTED, "the batch kernel implements the analytic solver only");
+  if (ctx->cfg.mode == PHOVO_MODE_CERES || ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE)
+    return ctx->fail(PHOVO_E_UNSUPPORTED, "the batch kernel implements the analytic solver only");
   memset(bp, 0, sizeof(*bp));
   bp->num_pairs = num_pairs; bp->rows = rows; bp->cols = cols;
   bp->mode = ctx->cfg.mode; bp->log_cap = log_cap;

@@ -36,6 +36,13 @@ struct phovo_ctx {
   double* Gx[PHOVO_MAX_LEVELS] = {nullptr};
   double* Gy[PHOVO_MAX_LEVELS] = {nullptr};
   size_t lcap[PHOVO_MAX_LEVELS][5] = {{0}};
+  // photometric + depth solver: target depth pyramid, Scharr of depth / max_depth, gain per level
+  double* D1[PHOVO_MAX_LEVELS] = {nullptr};
+  double* GxD[PHOVO_MAX_LEVELS] = {nullptr};
+  double* GyD[PHOVO_MAX_LEVELS] = {nullptr};
+  size_t bcap[PHOVO_MAX_LEVELS][3] = {{0}};
+  double* d_gain = nullptr;
+  bool have_tgt_depth = false;
   int* winner = nullptr; size_t winner_cap = 0;           // one int per pixel of the largest active level
   unsigned char* valid = nullptr; size_t valid_cap = 0;   // one flag per pixel (K3a -> K3b)
   double* scratch64[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};

@@ -21,6 +21,9 @@ int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_
                        double src_scale, int rows, int cols, int level, double* dst, int orows, int ocols);
 // K2b: cv::GaussianBlur(k x k, sigma) applied once, BORDER_REFLECT_101, fp64 in place via `tmp`.
 int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows, int cols, int ksize, double sigma);
+// dst = src * alpha (Mat::convertTo with a scale), and gain[0] = mean(a) / mean(b) in a fixed summation order
+int launch_scale(cudaStream_t stream, const double* src, double alpha, double* dst, size_t n);
+int launch_mean_ratio(cudaStream_t stream, const double* a, const double* b, size_t n, double* out);
 // K2: Scharr x/y (AN:181-187) from the fp64 level image, same evaluation order as cv::Scharr.
 int launch_scharr_store(cudaStream_t stream, const double* img, int rows, int cols, double scale,
                         double* Gx, double* Gy);
@@ -38,6 +41,8 @@ struct LevelPtrs {
   const double* I0; const double* D0; const double* I1; const double* Gx; const double* Gy;
   int* winner;        // rows*cols ints, all -1 between iterations
   unsigned char* valid;  // rows*cols flags written by K3a: pixel is depth-valid and lands in bounds under the current pose
+  // photometric + depth solver only (PHOVO_MODE_BIOBJECTIVE); winner then has 2*rows*cols slots
+  const double* D1; const double* GxD; const double* GyD; const double* gain;
 };
 
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);

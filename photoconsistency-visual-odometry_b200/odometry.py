@@ -96,9 +96,14 @@ class CPhotoconsistencyOdometryCuda:
         self._check(self._L.phovo_set_source(self._h, gptr, gstep, dptr, dtype, dstep, float(depth_scale),
                                              shape[0], shape[1]))
 
-    def SetTargetFrame(self, intensityImage, depthImage=None):      # AN:479-491 (depth ignored, AN:484)
+    def SetTargetFrame(self, intensityImage, depthImage=None, depth_scale=1.0):
+        """AN:479-491: the analytic and Ceres solvers ignore the target depth (AN:484); the photometric +
+        depth solver (MODE_BIOBJECTIVE, BiObjective.h:567-579) needs it."""
         g, gstep, gptr, shape = self._gray_args(intensityImage)
         self._check(self._L.phovo_set_target(self._h, gptr, gstep, shape[0], shape[1]))
+        if depthImage is not None and self.GetConfig().mode == capi.MODE_BIOBJECTIVE:
+            d, dtype, dstep, dptr = self._depth_args(depthImage, depth_scale)
+            self._check(self._L.phovo_set_target_depth(self._h, dptr, dtype, dstep, float(depth_scale)))
 
     def SetInitialStateVector(self, initialStateVector):            # AN:494-497
         s = np.ascontiguousarray(initialStateVector, dtype=np.float64).reshape(6)

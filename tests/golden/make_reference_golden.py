@@ -57,6 +57,22 @@ def warp_golden():
     print("ref_warp_image_120x160", int((out["warped_l0"] > 0).sum()), "pixels written")
 
 
+def biobjective_golden():
+    """CPhotoconsistencyOdometryBiObjective.h run from the reference source (photometric + depth rows)."""
+    tmp = tempfile.mkdtemp()
+    cases = [("ref_bi_120x160_all_levels", 120, 160, np.array([[131.25, 0, 79.5], [0, 131.25, 59.5], [0, 0, 1.]]), "test_3_level_all_active", 37),
+             ("ref_bi_240x320_cfg4", 240, 320, np.array([[262.5, 0, 159.5], [0, 262.5, 119.5], [0, 0, 1.]]), "config_4_level_optimization_analytic", 38)]
+    for name, rows, cols, K, cfg, seed in cases:
+        g0, d0, g1, d1 = phovo.synth.make_pair(rows, cols, K=K, seed=seed)
+        yml = phovo.configs.write_yaml(cfg, tmp)
+        s, iters = ref_py.ReferenceBiObjective(yml, K).align(g0, d0, g1, d1)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), gray0=g0, depth0=d0.astype(np.float32), gray1=g1, depth1=d1.astype(np.float32),
+                            K=K, config=np.array(cfg), state=s, n=np.array([it["n"] for it in iters]),
+                            H=np.array([it["H"] for it in iters]), g=np.array([it["g"] for it in iters]))
+        print(name, len(iters), "iterations", s)
+
+
 if __name__ == "__main__":
     warp_golden()
+    biobjective_golden()
     main()
