@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
     with open(os.path.join(CSRC, "ptxas_v.log"), "w") as f:
-        f.write("\n".join(log))
+        # compile times differ from run to run: keep the log stable under version control
+        f.write("\n".join(ln for chunk in log for ln in chunk.splitlines() if "Compile time" not in ln) + "\n")
     if verbose:
         print("\n".join(log))
     return LIB

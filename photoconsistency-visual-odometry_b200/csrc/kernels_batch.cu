@@ -4,13 +4,14 @@
 //        writes, for each ACTIVE pyramid level only, I0 and I1 as EXACT 10-bit tap sums (u16,
 //        value = sum/1020) and D0 as fp64 (the reference's own double average).  HBM-bound.
 //        (AN:115-163 with blur 0.)
-//   K3-batch k_batch_align : persistent CTAs; a CTA takes one pair at a time and runs the complete
-//        coarse-to-fine Gauss-Newton loop (AN:500-563) without leaving the SM: winner words,
-//        Scharr numerators and I1 resident in shared memory (10 B/px), D0 / I0 streamed from the
-//        pair's record in L2, warp-transposed fixed-order reduction, the 6x6 solve in one warp.
-//        No grid-wide synchronisation, no atomics on floating-point data; the thread->pixel
-//        mapping is fixed, so results are bitwise reproducible and independent of which SM, CTA
-//        or GPU processes the pair.
+//   K3-batch k_batch_level : one launch per active pyramid level; persistent CTAs take one pair at a
+//        time and run the complete Gauss-Newton loop of that level (AN:504-561) without leaving the
+//        SM: winner words, Scharr numerators and I1 resident in shared memory (10 B/px), D0 / I0
+//        streamed from the pair's record in L2, estimate-then-verify warp, warp-transposed
+//        fixed-order reduction, the 6x6 solve in registers.  No grid-wide synchronisation, no atomics
+//        on floating-point data; the thread->pixel mapping is a pure function of the level size,
+//        so results are bitwise reproducible and independent of which SM, CTA or GPU processes the
+//        pair.
 //
 // Why exact storage: the residual scatter (AN:358) makes the cost piecewise constant in the
 // warp; when a level does not converge (it often runs to max_num_iterations) any 1e-7

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/roofline_inputs.json: the per-unit figures bench.py's `roofline` object needs that only a
-profiler can give -- DRAM bytes per pair (ncu dram__bytes_read+write of ONE k_batch_align launch /
+profiler can give -- DRAM bytes per pair (ncu dram__bytes_read+write of the k_batch_level launches of ONE step /
 its pairs), fp64 arithmetic thread-instructions per executed pixel-iteration (ncu sass op counters /
 pixel-iterations of that launch), and the measured FP64 issue peak (tools/fp64_peak.cu).
 
