@@ -101,6 +101,32 @@ class ClockSampler:
                 "samples": len(self.samples), "reasons": sorted(k for k, b in self.BAD.items() if mask & b)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that its pinned host buffers are
+    allocated on (and copied from) the GPU's own NUMA node.  Matters for `e2e` when several ranks upload at once."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = index
+        if visible:
+            try:
+                idx = int(visible.split(",")[index])
+            except ValueError:
+                idx = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_bytes(cfg, iters, rows, cols):
     """SURVEY 8(d): 20 B/px per executed GN iteration at a level of N px + 216 B out per iteration;
     frame setup 1 843 200 B in + 5 images x active px x 4 B out per pair."""
@@ -192,6 +218,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    numa = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation (first touch decides the node)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -347,7 +374,7 @@ def main():
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "batched independent 640x480 RGB-D pairs, %s (BASELINE configs[3]), %d pairs per GPU per step" % (CONFIG, P),
-                       "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "u16 raw x 1/5000 m" if args.depth == "u16" else "f32 metres", "parallelism": "pairs sharded x%d, final pose all_gather" % world,
+                       "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "u16 raw x 1/5000 m" if args.depth == "u16" else "f32 metres", "parallelism": "pairs sharded x%d, final pose all_gather" % world, "host_cpus_bound_to_gpu_numa_node": numa,
                        "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (h2d_full / 1e9),
                        "e2e_upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe" % (h2d, h2d_full),
                        "mean_iterations_per_pair": {str(l): float(it_host[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0}},
