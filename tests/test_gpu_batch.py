@@ -191,3 +191,18 @@ def test_batch_at_scale_matches_general_path(phovo):
         assert [sum(1 for e in log if e["level"] == l) for l in (2, 3)] == [int(it[p, 2]), int(it[p, 3])], p
         worst = max(worst, float(np.max(np.abs(odo.GetOptimalStateVector() - st[p]))))
     assert worst < 1e-9, worst
+
+
+def test_randomised_parity_sweep(phovo, oracle):
+    """A small slice of tools/fuzz_parity.py as a regression test: random sizes / intrinsics / configs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--groups", "30", "--pairs", "8", "--seed", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    st = json.loads(out.stdout.strip().splitlines()[-1])
+    assert st["pairs"] >= 100 and st["iter_mismatch"] == 0 and st["pose_over_bar"] == 0 and st["nonfinite"] == 0, st
+    assert st["worst_trans"] < 1e-9 and st["worst_rot"] < 1e-9 and st["worst_general_vs_batch"] < 1e-9, st

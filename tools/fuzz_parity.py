@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Randomised parity sweep (GPU box): many small random pairs -- random sizes (odd and even, widths that do and
+do not divide the CTA widths), intrinsics, depth ranges, motions (small and large), configs (every level active
+or not, lambda != 1) -- through the batch kernels, the general path (cooperative and graph drivers) and the CPU
+oracle.  Counts pairs whose iteration counts differ or whose pose differs by more than the north-star bar, and
+reports the worst deviations.  Prints one JSON line."""
+import argparse, importlib, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--groups", type=int, default=40)
+    ap.add_argument("--pairs", type=int, default=24)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
+    phovo.build()
+    import oracle_py
+    oracle_py.build()
+    rng = np.random.default_rng(args.seed)
+    stats = dict(pairs=0, groups=0, iter_mismatch=0, pose_over_bar=0, worst_trans=0., worst_rot=0., general_checked=0,
+                 worst_general_vs_batch=0., nonfinite=0, sizes=[])
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    t0 = time.time()
+    for gi in range(args.groups):
+        rows = int(rng.integers(40, 150)); cols = int(rng.choice([80, 160, 96, 120, 64, int(rng.integers(50, 200))]))
+        f = float(rng.uniform(0.7, 1.4)) * cols
+        K = np.array([[f, 0, (cols - 1) / 2 + rng.uniform(-3, 3)], [0, f * rng.uniform(0.97, 1.03), (rows - 1) / 2 + rng.uniform(-3, 3)], [0, 0, 1.]])
+        levels = int(rng.integers(2, 4))
+        cfg = phovo.default_config()
+        cfg.num_levels = levels
+        for l in range(levels):
+            cfg.max_num_iterations[l] = int(rng.integers(0, 12)) if l > 0 or rng.random() < 0.5 else 0
+            cfg.min_gradient_norm[l] = float(rng.choice([1., 30., 300.]))
+            cfg.lambda_step[l] = float(rng.choice([1., 1., 0.8]))
+        if sum(cfg.max_num_iterations[l] for l in range(levels)) == 0:
+            cfg.max_num_iterations[levels - 1] = 5
+        cfg.min_depth, cfg.max_depth = float(rng.uniform(0.2, 1.0)), float(rng.uniform(2.1, 6.5))
+        cfg.mode = int(rng.integers(0, 2))
+        P = args.pairs
+        scale = float(rng.choice([1., 1., 3.]))            # some groups with large motions
+        g0 = np.empty((P, rows, cols), np.uint8); g1 = np.empty_like(g0); d0 = np.empty((P, rows, cols))
+        for p in range(P):
+            xi = phovo.synth.random_motion(int(rng.integers(0, 1 << 30))) * scale
+            g0[p], d0[p], g1[p], _ = phovo.synth.make_pair(rows, cols, K, xi, int(rng.integers(0, 1 << 30)))
+        odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
+        try:
+            st, it = odo.BatchAlign(g0, d0, g1)
+        except phovo.PhovoError as e:
+            if e.code == phovo.capi.E_UNSUPPORTED:
+                continue
+            raise
+        ocfg = oracle_py.Config.from_buffer_copy(bytes(cfg))
+        ost, oit, _, _ = oracle_py.align_batch(ocfg, K, g0, d0, g1, num_threads=os.cpu_count(), lean=True)
+        stats["groups"] += 1; stats["pairs"] += P; stats["sizes"].append([rows, cols, levels])
+        for p in range(P):
+            if not (np.isfinite(st[p]).all() and np.isfinite(ost[p]).all()):
+                stats["nonfinite"] += int(np.isfinite(st[p]).all() != np.isfinite(ost[p]).all())
+                continue
+            if not np.array_equal(it[p], oit[p]):
+                stats["iter_mismatch"] += 1
+            dt, dr = float(np.max(np.abs(st[p, :3] - ost[p, :3]))), float(np.max(np.abs(st[p, 3:] - ost[p, 3:])))
+            stats["worst_trans"] = max(stats["worst_trans"], dt); stats["worst_rot"] = max(stats["worst_rot"], dr)
+            if dt >= 1e-4 or dr >= 1e-5:
+                stats["pose_over_bar"] += 1
+        for path in (2, 1):                                  # the general path on two pairs of the group
+            odo.SetExecution(path)
+            for p in (0, P - 1):
+                odo.SetSourceFrame(g0[p], d0[p]); odo.SetTargetFrame(g1[p]); odo.SetInitialStateVector(np.zeros(6))
+                try:
+                    odo.Optimize()
+                except phovo.PhovoError as e:
+                    if e.code == phovo.capi.E_NUMERIC:
+                        continue
+                    raise
+                if np.isfinite(st[p]).all():
+                    stats["worst_general_vs_batch"] = max(stats["worst_general_vs_batch"], float(np.max(np.abs(odo.GetOptimalStateVector() - st[p]))))
+                    stats["general_checked"] += 1
+        odo.SetExecution(2)
+    stats["seconds"] = time.time() - t0
+    stats["sizes"] = stats["sizes"][:8]
+    print(json.dumps(stats))
+
+
+if __name__ == "__main__":
+    main()
