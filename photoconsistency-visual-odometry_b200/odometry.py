@@ -249,6 +249,35 @@ class CPhotoconsistencyOdometryCuda:
                                                      None if initial_states is None else initial_states.data_ptr(),
                                                      states_out.data_ptr(), iters_out.data_ptr()))
 
+    def AlignSequence(self, gray, depth, depth_scale=1.0):
+        """PhotoconsistencyVisualOdometry.cpp:212-259 for a whole recorded sequence in ONE batch call.
+
+        The app aligns frame k-1 (source) to frame k (target) from a ZERO initial state every frame
+        (VisualOdometry.cpp:175,224), so the N-1 alignments of a sequence are independent: the frames are
+        uploaded once and pair k reads frames k and k+1 of the same device arrays.  `gray` [N,R,C] u8 and
+        `depth` [N,R,C] (f64 / f32 metres or u16 raw * depth_scale), numpy or torch (host or device).
+        Returns (states [N-1,6], iterations [N-1,MAXL], poses [N,4,4]) with poses[0] = I and
+        poses[k] = poses[k-1] @ inv(Rt_k) as the app accumulates them (:234)."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = gray if isinstance(gray, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(gray))
+        d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
+        if d.dtype == torch.uint16:
+            d = d.view(torch.int16)
+        g, d = g.to(dev, non_blocking=True).contiguous(), d.to(dev, non_blocking=True).contiguous()
+        n = g.shape[0]
+        if n < 2:
+            raise ValueError("a sequence needs at least two frames")
+        states = torch.zeros((n - 1, 6), dtype=torch.float64, device=dev)
+        iters = torch.zeros((n - 1, capi.MAXL), dtype=torch.int32, device=dev)
+        self.SetStream(torch.cuda.current_stream(dev).cuda_stream)
+        self.BatchAlignDevice(g[:-1], d[:-1], g[1:], states, iters, depth_scale=depth_scale)   # overlapping views, no copies
+        st, it = states.cpu().numpy(), iters.cpu().numpy()
+        poses = np.tile(np.eye(4), (n, 1, 1))
+        for k in range(1, n):
+            poses[k] = poses[k - 1] @ np.linalg.inv(capi.state_to_rt(st[k - 1]))
+        return st, it, poses
+
     def BatchKernelTimes(self):
         """(pyramid_ms, align_ms) of the last BatchAlignDevice call, CUDA events on the context stream."""
         a, b = C.c_float(), C.c_float()

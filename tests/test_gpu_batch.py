@@ -206,3 +206,35 @@ def test_randomised_parity_sweep(phovo, oracle):
     st = json.loads(out.stdout.strip().splitlines()[-1])
     assert st["pairs"] >= 100 and st["iter_mismatch"] == 0 and st["pose_over_bar"] == 0 and st["nonfinite"] == 0, st
     assert st["worst_trans"] < 1e-9 and st["worst_rot"] < 1e-9 and st["worst_general_vs_batch"] < 1e-9, st
+
+
+def test_sequence_as_one_batch_matches_the_vo_loop(phovo, oracle):
+    """AlignSequence: the VO app's per-frame alignments (zero initial state every frame) computed as one
+    batch over overlapping views of the uploaded sequence == the sequential loop, frame by frame."""
+    K = phovo.synth.K_VISUAL_ODOMETRY
+    n = 12
+    frames = [phovo.synth.make_sequence_frame(k, 480, 640, K=K) for k in range(n)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames]).astype(np.float32)
+    cfg = phovo.configs.to_config("config_5_level_optimization_analytic", phovo.capi)
+    odo = make_odo(phovo, cfg, K)
+    st, it, poses = odo.AlignSequence(gray, depth)
+    assert st.shape == (n - 1, 6) and poses.shape == (n, 4, 4)
+    seq = make_odo(phovo, cfg, K)
+    pose = np.eye(4)
+    seq.SetSourceFrame(*frames[0])
+    for k in range(1, n):
+        if k > 1:
+            seq.PromoteTargetToSource(frames[k - 1][1])
+        seq.SetTargetFrame(frames[k][0])
+        seq.SetInitialStateVector(np.zeros(6))
+        seq.Optimize()
+        assert np.max(np.abs(seq.GetOptimalStateVector() - st[k - 1])) < 1e-9, k
+        assert len(seq.IterationStats()) == int(it[k - 1].sum())
+        pose = pose @ np.linalg.inv(seq.GetOptimalRigidTransformationMatrix())
+        assert np.max(np.abs(pose - poses[k])) < 1e-8
+    # against the oracle for the first frames
+    for k in (1, 2):
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+        o.set_source(*frames[k - 1]); o.set_target(frames[k][0]); o.set_initial_state(np.zeros(6)); o.optimize()
+        assert_pose_close(st[k - 1], o.state(), "frame %d" % k)
