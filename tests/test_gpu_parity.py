@@ -489,3 +489,41 @@ def test_error_paths(phovo):
     odo.SetConfig(cfg)
     with pytest.raises(phovo.PhovoError):
         odo.SetSourceFrame(g0, d0)
+
+
+def test_contexts_are_independent_and_do_not_leak(phovo):
+    """One context = one device + one stream, contexts independent (SURVEY 8b threading): two contexts driven
+    from two host threads at once give the results of a lone run; creating and destroying contexts returns
+    the device memory."""
+    import threading
+    import torch
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
+    pairs = [phovo.synth.make_pair(240, 320, K=K, seed=60 + k, xi=phovo.synth.random_motion(60 + k)) for k in range(2)]
+    lone = []
+    for g0, d0, g1, _ in pairs:
+        odo = make_odo(phovo, cfg, K)
+        lone.append(run_gpu(odo, g0, d0, g1)[0])
+        odo.close()
+    out = [None, None]
+
+    def work(k):
+        odo = make_odo(phovo, cfg, K)
+        for _ in range(20):
+            out[k] = run_gpu(odo, *pairs[k][:3])[0]
+        odo.close()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert np.array_equal(out[0], lone[0]) and np.array_equal(out[1], lone[1])
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(10):
+        odo = make_odo(phovo, cfg, K)
+        run_gpu(odo, *pairs[0][:3])
+        odo.BatchAlign(pairs[0][0][None], pairs[0][1][None].astype(np.float32), pairs[0][2][None])
+        odo.close()
+    torch.cuda.synchronize()
+    assert abs(torch.cuda.mem_get_info()[0] - free0) < 64 << 20     # nothing accumulates across create/destroy
