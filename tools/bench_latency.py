@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--mode", default="single", choices=["single", "vo", "ceres"])
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--path", type=int, default=2, help="iteration-loop driver: 2 cooperative kernel, 1 CUDA graph, 0 stream")
     args = ap.parse_args()
     phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
     phovo.build()
@@ -60,7 +61,7 @@ def main():
         cfg = phovo.configs.to_config(name, phovo.capi)
         g0, d0, g1, _ = phovo.synth.make_pair(480, 640, K=K, seed=0)
         odo = phovo.CPhotoconsistencyOdometryCuda()
-        odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
+        odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K); odo.SetExecution(args.path)
         hg0, hd0, hg1 = pinned(g0), pinned(d0), pinned(g1)
         opt_ms, setup_ms, wall_ms = [], [], []
         for rep in range(args.reps + 5):
@@ -84,7 +85,7 @@ def main():
             o.optimize()
             t2 = time.perf_counter()
             cpu_opt.append((t2 - t1) * 1e3); cpu_all.append((t2 - t0) * 1e3)
-        print(json.dumps({"mode": "single", "config": name, "iterations": len(log), "used_graph": odo.UsedGraph(),
+        print(json.dumps({"mode": "single", "config": name, "iterations": len(log), "driver": odo.LastPath(),
                           "gpu_optimize_ms_device_median": float(np.median(opt_ms)), "gpu_setup_ms_device_median": float(np.median(setup_ms)),
                           "gpu_host_in_pose_out_ms_wall_median": float(np.median(wall_ms)),
                           "kernel_launches_per_optimize": None,
