@@ -207,10 +207,6 @@ __device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double 
   return w;
 }
 
-__device__ __forceinline__ void smem_red_max(unsigned addr, unsigned v) {
-  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
 struct IterConst {          // per-iteration scalars besides the tables
   double x, y, z, cy, sy, rho;
   double fxs, fys, oxs, oys;   // fx 2^20, fy 2^20, (ox + 0.5) 2^20, (oy + 0.5) 2^20  (phase A fixed point)
