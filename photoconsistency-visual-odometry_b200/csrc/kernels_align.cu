@@ -524,6 +524,234 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ceres mode on the device: the restated trust-region Levenberg-Marquardt loop of one level
+// (CE:433-500 -> ceres::Solve) inside ONE persistent cooperative launch.  Every loop
+// trip is one evaluation of the CE:156-269 residual + Jacobian at `eval_x` (phase A winner map by
+// truncation, grid.sync, phase B bilinear samples + normal equations, grid.sync, fixed-order sum of
+// all partials in every CTA) followed by the LM decision, which thread 0 of every CTA takes
+// redundantly -- identical inputs, identical arithmetic, so all CTAs stay in lock step without a
+// broadcast.  CTA 0 writes the log.  The decision code mirrors the host loop in phovo_api.cu
+// (optimize_ceres), statement for statement.
+// ---------------------------------------------------------------------------------------------
+struct LmParams {
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_radius, max_radius, min_radius, min_relative_decrease;
+  int max_iterations;
+};
+
+struct LmState {
+  double x[6], xn[6], scale[6], step_norm, x_norm, model_cost_change;
+  double H[21], g[6], cost;       // `cur`
+  double radius, decrease_factor;
+  int num_valid, iteration, first, done;
+};
+
+__device__ bool chol_solve6_dev(const double M[36], const double b[6], double x[6]) {
+  double Lm[36];
+  for (int i = 0; i < 36; ++i) Lm[i] = 0.;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double sum = M[i * 6 + j];
+      for (int k = 0; k < j; ++k) sum -= Lm[i * 6 + k] * Lm[j * 6 + k];
+      if (i == j) { if (!(sum > 0)) return false; Lm[i * 6 + i] = sqrt(sum); }
+      else Lm[i * 6 + j] = sum / Lm[j * 6 + j];
+    }
+  double y[6];
+  for (int i = 0; i < 6; ++i) { double sum = b[i]; for (int k = 0; k < i; ++k) sum -= Lm[i * 6 + k] * y[k]; y[i] = sum / Lm[i * 6 + i]; }
+  for (int i = 5; i >= 0; --i) { double sum = y[i]; for (int k = i + 1; k < 6; ++k) sum -= Lm[k * 6 + i] * x[k]; x[i] = sum / Lm[i * 6 + i]; }
+  return true;
+}
+
+__device__ void expand_sym_dev(const double H[21], double M[36]) {
+  int k = 0;
+  for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { M[a * 6 + b] = H[k]; M[b * 6 + a] = H[k]; ++k; }
+}
+
+// log entry for the LM iteration being decided (host: `s`)
+__device__ void lm_log(const LevelParams& L, const LmState& S, phovo_iter_stats* log, int& log_count, int log_capacity, int accepted,
+                       const double* state_out) {
+  if (blockIdx.x == 0 && log && log_count < log_capacity) {
+    phovo_iter_stats* e = log + log_count;
+    e->level = L.level; e->iteration = S.iteration - 1; e->num_valid = S.num_valid; e->accepted = accepted;
+    double n2 = 0.;
+    for (int k = 0; k < 21; ++k) e->H[k] = S.H[k];
+    for (int k = 0; k < 6; ++k) { e->g[k] = S.g[k]; n2 += S.g[k] * S.g[k]; e->state_in[k] = S.x[k]; e->state_out[k] = state_out[k]; }
+    e->grad_norm = sqrt(n2); e->cost = S.cost; e->radius = S.radius;
+  }
+  log_count += 1;
+}
+
+// Prepare LM iteration `S.iteration + 1` from `cur`: returns false when the loop ends here.
+__device__ bool lm_next_step(const LevelParams& L, const LmParams& lm, LmState& S, phovo_iter_stats* log, int& log_count, int log_capacity) {
+  if (S.iteration >= lm.max_iterations) return false;
+  S.iteration += 1;
+  double M[36], Ms[36], gs[6], A[36], step[6];
+  expand_sym_dev(S.H, M);
+  for (int a = 0; a < 6; ++a) { gs[a] = S.g[a] * S.scale[a]; for (int b = 0; b < 6; ++b) Ms[a * 6 + b] = M[a * 6 + b] * S.scale[a] * S.scale[b]; }
+  for (int k = 0; k < 36; ++k) A[k] = Ms[k];
+  for (int a = 0; a < 6; ++a) { double d = Ms[a * 6 + a]; if (d < 1e-6) d = 1e-6; if (d > 1e32) d = 1e32; A[a * 6 + a] += d / S.radius; }
+  bool ok = chol_solve6_dev(A, gs, step);
+  for (int a = 0; a < 6; ++a) step[a] = -step[a];
+  double model_cost_change = 0;
+  if (ok) {
+    double dg = 0, dMd = 0;
+    for (int a = 0; a < 6; ++a) { dg += step[a] * gs[a]; double t = 0; for (int b = 0; b < 6; ++b) t += Ms[a * 6 + b] * step[b]; dMd += step[a] * t; }
+    model_cost_change = -(dg + 0.5 * dMd);
+    for (int a = 0; a < 6; ++a) if (!isfinite(step[a])) ok = false;
+  }
+  if (!ok || !(model_cost_change > 0)) { lm_log(L, S, log, log_count, log_capacity, 0, S.x); return false; }   // max_num_consecutive_invalid_steps = 0 (CE:477)
+  double step_norm = 0, x_norm = 0;
+  for (int a = 0; a < 6; ++a) { const double d = step[a] * S.scale[a]; S.xn[a] = S.x[a] + d; step_norm += d * d; x_norm += S.x[a] * S.x[a]; }
+  S.step_norm = sqrt(step_norm); S.x_norm = sqrt(x_norm); S.model_cost_change = model_cost_change;
+  return true;
+}
+
+__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
+                                                                     phovo_iter_stats* log, LmParams lm) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
+  __shared__ double s_tot[32];
+  __shared__ PoseDev s_pose;
+  __shared__ LmState S;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_pose = *pose;
+    for (int k = 0; k < 6; ++k) { S.x[k] = s_pose.state[k]; S.xn[k] = s_pose.state[k]; }
+    S.radius = lm.initial_radius; S.decrease_factor = 2.0; S.iteration = 0; S.first = 1; S.done = 0;
+  }
+  __syncthreads();
+  int log_count = s_pose.log_count;
+  const int log_capacity = s_pose.log_capacity;
+  const int n = L.rows * L.cols;
+  const int stride = gridDim.x * kCoopBlock;
+  for (;;) {
+    // ---- pose of the state to evaluate (every CTA, thread 0) ----
+    if (tid == 0) {
+      Pose Pn;
+      pose_from_state(S.xn, Pn);
+      for (int k = 0; k < 6; ++k) s_pose.state[k] = S.xn[k];
+      pose_store(Pn, &s_pose);
+    }
+    __syncthreads();
+    Pose T;
+    pose_load(&s_pose, T);
+    // ---- phase A: winner of each (truncated) target slot, CE:250-254, 261 ----
+    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+      const double d = __ldg(P.D0 + i);
+      const int r = i / L.cols, c = i - r * L.cols;
+      Warped w;
+      if (warp_pixel<true>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
+    }
+    grid.sync();
+    // ---- phase B: CE:156-269 residual + Jacobian rows of the surviving pixels ----
+    double acc[PHOVO_NACC];
+#pragma unroll
+    for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+      const int r = i / L.cols, c = i - r * L.cols;
+      const double d = __ldg(P.D0 + i);
+      Warped w;
+      if (!warp_pixel<true>(L, T, r, c, d, w)) continue;
+      acc[28] += 1.;
+      if (__ldcg(P.winner + w.t) != i) continue;   // overwritten by a later source pixel (CE:261)
+      P.winner[w.t] = -1;                            // the winner cleans its slot (a loser that reads -1 has lost all the same)
+      int x1, x2, y1, y2; double dx, dy;
+      linear_init_axis(w.tr - 0.5, L.rows, y1, y2, dy);   // sample.h:67-71
+      linear_init_axis(w.tc - 0.5, L.cols, x1, x2, dx);
+      const double s0 = bilinear(P.I1, L.cols, y1, y2, x1, x2, dy, dx);
+      const double s1 = bilinear(P.Gx, L.cols, y1, y2, x1, x2, dy, dx);
+      const double s2 = bilinear(P.Gy, L.cols, y1, y2, x1, x2, dy, dx);
+      const double res = s0 - __ldg(P.I0 + i);
+      double Ju[6], Jv[6], J[6];
+      projection_jacobian<false>(L, T, w, d, Ju, Jv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J[k] = s1 * Ju[k] + s2 * Jv[k];   // jet_extras.h:87-109
+      accumulate_row(acc, J, res);
+      acc[27] = fma(res, res, acc[27]);
+    }
+    {
+      const double total = block_reduce<kCoopBlock>(acc, smem);
+      if (tid < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + tid] = total;
+    }
+    grid.sync();   // partials complete, every winner slot back to -1
+    {
+      const int v = tid & 31, g = tid >> 5;
+      double sum = 0.;
+      for (int b = g; b < (int)gridDim.x; b += kCoopBlock / 32) sum += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
+      smem[g * PHOVO_ACC_STRIDE + v] = sum;
+      __syncthreads();
+      if (tid < 32) {
+        double t = 0.;
+#pragma unroll
+        for (int k = 0; k < kCoopBlock / 32; ++k) t += smem[k * PHOVO_ACC_STRIDE + tid];
+        s_tot[tid] = t;
+      }
+      __syncthreads();
+    }
+    // ---- LM decision (host twin: optimize_ceres in phovo_api.cu) ----
+    if (tid == 0) {
+      bool go;
+      if (S.first) {
+        S.first = 0;
+        for (int k = 0; k < 21; ++k) S.H[k] = s_tot[k];
+        for (int k = 0; k < 6; ++k) S.g[k] = s_tot[21 + k];
+        S.cost = 0.5 * s_tot[27]; S.num_valid = (int)s_tot[28];
+        double M[36]; expand_sym_dev(S.H, M);
+        for (int a = 0; a < 6; ++a) S.scale[a] = 1.0 / (1.0 + sqrt(M[a * 6 + a]));
+        double gmax = 0; for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(S.g[a]));
+        go = !(gmax <= lm.gradient_tolerance) && lm_next_step(L, lm, S, log, log_count, log_capacity);
+      } else {
+        const double cand_cost = 0.5 * s_tot[27];
+        go = true;
+        if (S.step_norm <= lm.parameter_tolerance * (S.x_norm + lm.parameter_tolerance)) { lm_log(L, S, log, log_count, log_capacity, 0, S.x); go = false; }
+        const double cost_change = S.cost - cand_cost;
+        if (go && fabs(cost_change) < lm.function_tolerance * S.cost) { lm_log(L, S, log, log_count, log_capacity, 0, S.x); go = false; }
+        if (go) {
+          const double rho = cost_change / S.model_cost_change;
+          if (rho > lm.min_relative_decrease) {
+            lm_log(L, S, log, log_count, log_capacity, 1, S.xn);
+            for (int k = 0; k < 6; ++k) S.x[k] = S.xn[k];
+            for (int k = 0; k < 21; ++k) S.H[k] = s_tot[k];
+            for (int k = 0; k < 6; ++k) S.g[k] = s_tot[21 + k];
+            S.cost = cand_cost; S.num_valid = (int)s_tot[28];
+            double gmax = 0; for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(S.g[a]));
+            if (gmax <= lm.gradient_tolerance) go = false;
+            else {
+              const double t = 2.0 * rho - 1.0;
+              double f = 1.0 - t * t * t; if (f < 1.0 / 3.0) f = 1.0 / 3.0;
+              S.radius = S.radius / f; if (S.radius > lm.max_radius) S.radius = lm.max_radius;
+              S.decrease_factor = 2.0;
+            }
+          } else {
+            lm_log(L, S, log, log_count, log_capacity, 0, S.x);
+            S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0;
+          }
+          if (go && S.radius < lm.min_radius) go = false;
+          if (go) go = lm_next_step(L, lm, S, log, log_count, log_capacity);
+        }
+      }
+      S.done = go ? 0 : 1;
+      s_pose.log_count = log_count;
+    }
+    __syncthreads();
+    log_count = s_pose.log_count;
+    if (S.done) break;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    Pose Pn;
+    pose_from_state(S.x, Pn);
+    for (int k = 0; k < 6; ++k) s_pose.state[k] = S.x[k];
+    pose_store(Pn, &s_pose);
+    s_pose.iteration = S.iteration;
+    s_pose.iters_per_level[L.level] = S.iteration;
+    s_pose.done = 1;
+    s_pose.log_count = log_count;
+    *pose = s_pose;
+  }
+}
+
 inline int grid_for(int n) {
   // one pixel per thread up to 8 CTAs per SM, then a fixed persistent grid (grid-stride loop);
   // the grid is a pure function of the level size, so the partial-sum order is reproducible.
@@ -613,6 +841,31 @@ int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs
   if (*err != cudaSuccess) return -1;
   *grid_out = grid;
   return 1;
+}
+
+int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, int sm_count, cudaError_t* err) {
+  static int blocks_per_sm = -1;
+  void* fn = (void*)k_level_coop_ceres;
+  if (blocks_per_sm < 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kCoopBlock, 0) != cudaSuccess) nb = 0;
+    blocks_per_sm = nb;
+  }
+  if (blocks_per_sm < 1) { *err = cudaErrorCooperativeLaunchTooLarge; return -1; }
+  const int n = L.rows * L.cols;
+  int grid = (n + kCoopBlock - 1) / kCoopBlock;
+  const int cap = sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  LevelParams Lc = L; LevelPtrs Pc = P;
+  LmParams lm;
+  lm.function_tolerance = lm_params[0]; lm.gradient_tolerance = lm_params[1]; lm.parameter_tolerance = lm_params[2];
+  lm.initial_radius = lm_params[3]; lm.max_radius = lm_params[4]; lm.min_radius = lm_params[5]; lm.min_relative_decrease = lm_params[6];
+  lm.max_iterations = max_iterations;
+  void* args[] = {&Lc, &Pc, &pose, &partials, &log, &lm};
+  *err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopBlock), args, 0, stream);
+  return *err == cudaSuccess ? 1 : -1;
 }
 
 int launch_reduce_solve(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* partials, int grid,

@@ -681,6 +681,33 @@ static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
 
 static int optimize_ceres(phovo_ctx* ctx);
 
+// Ceres mode with the LM loop on the device: one cooperative launch per active level.
+static int optimize_ceres_coop(phovo_ctx* ctx, bool* unavailable) {
+  *unavailable = false;
+  ctx->launches += launch_set_state(ctx->stream, ctx->d_pose, nullptr, ctx->state, ctx->log_cap);
+  for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
+    const int M = ctx->cfg.max_num_iterations[level];
+    if (!(M > 0)) continue;   // CE:437
+    const LevelParams L = ctx->level_params(level);
+    const LevelPtrs P = ctx->level_ptrs(level);
+    const double lm[7] = {ctx->cfg.function_tolerance[level], ctx->cfg.gradient_tolerance[level], ctx->cfg.parameter_tolerance[level],
+                          ctx->cfg.initial_trust_region_radius[level], ctx->cfg.max_trust_region_radius[level],
+                          ctx->cfg.min_trust_region_radius[level], ctx->cfg.min_relative_decrease[level]};
+    cudaError_t e = cudaSuccess;
+    const int rc = launch_level_coop_ceres(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, lm, M, ctx->sm_count, &e);
+    if (rc < 0) {
+      cudaGetLastError();
+      ctx->graph_error = std::string("cooperative launch unavailable: ") + cudaGetErrorString(e);
+      *unavailable = true;
+      CK(cudaStreamSynchronize(ctx->stream));
+      return PHOVO_OK;
+    }
+    ctx->launches += rc;
+  }
+  CK(cudaGetLastError());
+  return PHOVO_OK;
+}
+
 extern "C" int phovo_optimize(phovo_ctx* ctx) {
   if (!ctx) return PHOVO_E_INVALID;
   int rc = ready_to_solve(ctx);
@@ -691,7 +718,16 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev_time[2], ctx->stream));
   ctx->last_used_graph = 0;
   ctx->last_path = 0;
-  if (ctx->cfg.mode == PHOVO_MODE_CERES) return optimize_ceres(ctx);
+  if (ctx->cfg.mode == PHOVO_MODE_CERES) {
+    if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
+      bool unavailable = false;
+      rc = optimize_ceres_coop(ctx, &unavailable);
+      if (rc) return rc;
+      if (!unavailable) { ctx->last_path = 2; return read_back(ctx); }
+      ctx->coop_broken = true;
+    }
+    return optimize_ceres(ctx);   // host-driven LM over GPU evaluations
+  }
   if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1 && ctx->cfg.mode != PHOVO_MODE_BIOBJECTIVE) {
     bool unavailable = false;
     rc = optimize_coop(ctx, &unavailable);

@@ -68,6 +68,11 @@ int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err);
 
+// Ceres mode: the restated LM loop of one level in one cooperative launch.  lm_params: function, gradient, parameter
+// tolerance, initial / max / min trust-region radius, min relative decrease (CE:464-477).
+int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, int sm_count, cudaError_t* err);
+
 // Exchange area of the fused peer-store all-reduce (one per rank, IPC-shared with the peers).
 struct ShardExchange {
   double slots[2][8][32];              // [epoch parity][writer rank][value]

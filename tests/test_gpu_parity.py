@@ -450,6 +450,16 @@ def test_ceres_config_5_level_640x480(phovo, oracle):
         assert abs(a["cost"] - b["cost"]) < 1e-9 * b["cost"]
     assert_pose_close(s, o.state(), "ceres config 5")
     assert np.max(np.abs(s - o.state())) < 1e-9
+    # default driver = the LM loop ON the device (one cooperative launch per level); the host-driven LM over
+    # GPU evaluations takes the same decisions and ends at the same pose
+    assert odo.LastPath() == 2, odo.GraphError()
+    odo_h = make_odo(phovo, cfg, K, graph=True)
+    s_h, log_h = run_gpu(odo_h, g0, d0, g1)
+    assert odo_h.LastPath() != 2
+    assert [(e["level"], e["iteration"], e["accepted"]) for e in log_h] == [(e["level"], e["iteration"], e["accepted"]) for e in log]
+    assert np.max(np.abs(s_h - s)) < 1e-11
+    for a, b in zip(log, log_h):
+        assert abs(a["radius"] - b["radius"]) <= 1e-9 * b["radius"] and abs(a["cost"] - b["cost"]) <= 1e-11 * b["cost"]
 
 
 def test_error_paths(phovo):
