@@ -207,6 +207,44 @@ __global__ void __launch_bounds__(kBlock) k_winner_bi(LevelParams L, LevelPtrs P
   }
 }
 
+// Jacobian row k of the stacked 2N-row system of the photometric + depth solver (see the comment
+// above k_winner_bi); returns false for a zero row.  CG: read the validity flags with ld.global.cg
+// (they were written by other SMs inside the same cooperative launch).
+template <bool CG>
+__device__ __forceinline__ bool bi_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
+                                                double gain, int n, int k, double J[6]) {
+  int p = -1; bool depth_row = false;
+  const bool vk = k < n && (CG ? __ldcg(P.valid + k) : P.valid[k]);
+  if (k > 0 && vk) p = k;
+  else if ((k & 1) == 0 && (CG ? __ldcg(P.valid + (k >> 1)) : P.valid[k >> 1])) { p = k >> 1; depth_row = true; }
+  if (p < 0) return false;
+  const int r = p / L.cols, c = p - r * L.cols;
+  const double d = __ldg(P.D0 + p);
+  const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+  const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+  const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+  const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+  const double X = q0 + T.x, Y = q1 + T.y;
+  const double iz = 1.0 / (q2 + T.z);
+  // d(R p)/d(yaw, pitch, roll), BiObjective.h:364-377 in closed form
+  const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+  const double dp0 = T.cy * q2, dp1 = T.sy * q2;
+  const double dr0 = fma(T.R02, py, -(T.R01 * d)), dr1 = fma(T.R12, py, -(T.R11 * d)), dr2 = fma(T.R22, py, -(T.R21 * d));
+  // v = gradient * projection Jacobian (:380-400), then v * jacobianRt
+  const double gx = depth_row ? __ldg(P.GxD + p) : __ldg(P.Gx + p), gy = depth_row ? __ldg(P.GyD + p) : __ldg(P.Gy + p);
+  const double v0 = gx * L.fx * iz, v1 = gy * L.fy * iz;
+  const double v2 = -(fma(gx * L.fx, X, gy * L.fy * Y) * iz * iz);
+  J[0] = v0; J[1] = v1; J[2] = v2;
+  J[3] = fma(v1, q0, -(v0 * q1));
+  J[4] = fma(v0, dp0, fma(v1, dp1, v2 * Zp));
+  J[5] = fma(v0, dr0, fma(v1, dr1, v2 * dr2));
+  if (depth_row) {   // gain * (v * jacobianRt - jacobianRt_z), :404-414
+    J[0] = gain * J[0]; J[1] = gain * J[1]; J[2] = gain * (J[2] - 1.);
+    J[3] = gain * J[3]; J[4] = gain * (J[4] - Zp); J[5] = gain * (J[5] - dr2);
+  }
+  return true;
+}
+
 template <bool DUMP>
 __global__ void __launch_bounds__(kBlock) k_normal_eq_bi(LevelParams L, LevelPtrs P, const PoseDev* __restrict__ pose,
                                                          double* __restrict__ partials,
@@ -232,36 +270,9 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq_bi(LevelParams L, LevelPtr
       acc[27] = fma(res, res, acc[27]);
     }
     if (DUMP && dump_res) dump_res[k] = res;
-    int p = -1; bool depth_row = false;
-    if (k > 0 && k < n && P.valid[k]) p = k;
-    else if ((k & 1) == 0 && P.valid[k >> 1]) { p = k >> 1; depth_row = true; }
     if (k < n && P.valid[k]) acc[28] += 1.;
-    if (p < 0) continue;
-    const int r = p / L.cols, c = p - r * L.cols;
-    const double d = __ldg(P.D0 + p);
-    const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
-    const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
-    const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
-    const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
-    const double X = q0 + T.x, Y = q1 + T.y;
-    const double iz = 1.0 / (q2 + T.z);
-    // d(R p)/d(yaw, pitch, roll), BiObjective.h:364-377 in closed form
-    const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
-    const double dp0 = T.cy * q2, dp1 = T.sy * q2;
-    const double dr0 = fma(T.R02, py, -(T.R01 * d)), dr1 = fma(T.R12, py, -(T.R11 * d)), dr2 = fma(T.R22, py, -(T.R21 * d));
-    // v = gradient * projection Jacobian (:380-400), then v * jacobianRt
-    const double gx = depth_row ? __ldg(P.GxD + p) : __ldg(P.Gx + p), gy = depth_row ? __ldg(P.GyD + p) : __ldg(P.Gy + p);
-    const double v0 = gx * L.fx * iz, v1 = gy * L.fy * iz;
-    const double v2 = -(fma(gx * L.fx, X, gy * L.fy * Y) * iz * iz);
     double J[6];
-    J[0] = v0; J[1] = v1; J[2] = v2;
-    J[3] = fma(v1, q0, -(v0 * q1));
-    J[4] = fma(v0, dp0, fma(v1, dp1, v2 * Zp));
-    J[5] = fma(v0, dr0, fma(v1, dr1, v2 * dr2));
-    if (depth_row) {   // gain * (v * jacobianRt - jacobianRt_z), :404-414
-      J[0] = gain * J[0]; J[1] = gain * J[1]; J[2] = gain * (J[2] - 1.);
-      J[3] = gain * J[3]; J[4] = gain * (J[4] - Zp); J[5] = gain * (J[5] - dr2);
-    }
+    if (!bi_jacobian_row<false>(L, P, T, spsr, spcr, gain, n, k, J)) continue;
     accumulate_row(acc, J, res);
     if (DUMP && dump_jac) for (int a = 0; a < 6; ++a) dump_jac[(size_t)k * 6 + a] = J[a];
   }
@@ -430,7 +441,9 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       const int r = i / L.cols, c = i - r * L.cols;
       Warped w;
       const bool ok = warp_pixel<false>(L, T, r, c, d, w);
-      if (ok) atomicMax(P.winner + w.t, i);
+      if (MODE == 3) {   // photometric + depth solver: two residual slots per pixel, keys 2i+1 / 2i+2 (see k_winner_bi)
+        if (ok) { atomicMax(P.winner + w.t, 2 * i + 1); atomicMax(P.winner + 2 * w.t, 2 * i + 2); }
+      } else if (ok) atomicMax(P.winner + w.t, i);
       P.valid[i] = ok;
     }
     grid.sync();
@@ -439,36 +452,55 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
 #pragma unroll
     for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
     const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
-    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
-      const int win = __ldcg(P.winner + i);
-      P.winner[i] = -1;
-      double res = 0.;
-      if (win >= 0) {
-        res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
-        acc[27] = fma(res, res, acc[27]);
+    if (MODE == 3) {
+      const double gain = __ldg(P.gain);
+      for (int k = blockIdx.x * kCoopBlock + tid; k < 2 * n; k += stride) {
+        const int wkey = __ldcg(P.winner + k);
+        P.winner[k] = -1;
+        double res = 0.;
+        if (wkey > 0) {
+          const int src = (wkey - 1) >> 1;
+          if (((wkey - 1) & 1) == 0) res = __ldg(P.I1 + k) - __ldg(P.I0 + src);
+          else res = gain * (__ldg(P.D1 + (k >> 1)) - __ldg(P.D0 + src));
+          acc[27] = fma(res, res, acc[27]);
+        }
+        if (k < n && __ldcg(P.valid + k)) acc[28] += 1.;
+        double J[6];
+        if (!bi_jacobian_row<true>(L, P, T, spsr, spcr, gain, n, k, J)) continue;
+        accumulate_row(acc, J, res);
       }
-      if (!__ldcg(P.valid + i)) continue;
-      const int r = i / L.cols, c = i - r * L.cols;
-      const double d = __ldg(P.D0 + i);
-      const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
-      const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
-      const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
-      const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
-      const double iz = rcp_1ulp(q2 + T.z);
-      const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
-      const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
-      const double B = q1 + T.y;
-      double J[6];
-      J[0] = ga;
-      J[1] = gb;
-      J[2] = -(fma(ga, A, gb * B) * iz);
-      J[3] = fma(gb, q0, -(ga * q1));
-      const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
-      J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
-      const double Zr = fma(T.R22, py, -(T.R21 * d));
-      J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
-      accumulate_row(acc, J, res);
-      acc[28] += 1.;
+    } else {
+      for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+        const int win = __ldcg(P.winner + i);
+        P.winner[i] = -1;
+        double res = 0.;
+        if (win >= 0) {
+          res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
+          acc[27] = fma(res, res, acc[27]);
+        }
+        if (!__ldcg(P.valid + i)) continue;
+        const int r = i / L.cols, c = i - r * L.cols;
+        const double d = __ldg(P.D0 + i);
+        const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+        const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+        const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+        const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+        const double iz = rcp_1ulp(q2 + T.z);
+        const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
+        const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
+        const double B = q1 + T.y;
+        double J[6];
+        J[0] = ga;
+        J[1] = gb;
+        J[2] = -(fma(ga, A, gb * B) * iz);
+        J[3] = fma(gb, q0, -(ga * q1));
+        const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+        J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
+        const double Zr = fma(T.R22, py, -(T.R21 * d));
+        J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
+        accumulate_row(acc, J, res);
+        acc[28] += 1.;
+      }
     }
     {
       const double total = block_reduce<kCoopBlock>(acc, smem);
@@ -816,14 +848,14 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
   return launches + 2;
 }
 
-static int g_coop_blocks_per_sm[2] = {-1, -1};
+static int g_coop_blocks_per_sm[3] = {-1, -1, -1};
 
 // One cooperative launch for the whole iteration loop of a level.  Returns the number of launches
 // (1) or -1 if cooperative launch is not available (the caller falls back to the graph path).
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err) {
-  const int m = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
-  void* fn = m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
+  const int m = L.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
+  void* fn = m == 2 ? (void*)k_level_coop<3> : m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
   if (g_coop_blocks_per_sm[m] < 0) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kCoopBlock, 0) != cudaSuccess) nb = 0;

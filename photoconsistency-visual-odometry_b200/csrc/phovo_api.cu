@@ -728,7 +728,7 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
     }
     return optimize_ceres(ctx);   // host-driven LM over GPU evaluations
   }
-  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1 && ctx->cfg.mode != PHOVO_MODE_BIOBJECTIVE) {
+  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
     bool unavailable = false;
     rc = optimize_coop(ctx, &unavailable);
     if (rc) return rc;
