@@ -172,12 +172,19 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
 //   colA/B : {R00 cxi, R10 cxi}, {R20 cxi, -cp cxi}            per ITERATION: the column part of R*(ray) and of dZ'/dpitch
 //   row    : {R01 ryi + R02, R11 ryi + R12}, {R21 ryi + R22, -(sp sr ryi + sp cr)}, {R22 ryi - R21, R02 ryi - R01}, {R12 ryi - R11, 0}
 // so that  R p = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
+// The row table carries ceil(threads / cols) rows of zero padding: the second pixel of a thread's
+// last trip may lie up to `threads` pixels past the level and is read (and masked) without a guard.
 struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
-  double2* row;                   // [rows][4]
+  double2* row;                   // [rows + pad][4]
 };
-__host__ __device__ inline int table_doubles(int rows, int cols) { return 2 * (rows + cols) + 4 * cols + 8 * rows; }
+__host__ __device__ inline int table_pad_rows(int cols, int threads) { return (threads + cols - 1) / cols; }
+__host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
+  return 2 * (rows + cols) + 4 * cols + 8 * (rows + table_pad_rows(cols, threads));
+}
+// shared-memory slots of the three per-pixel arrays: the level plus `threads` slots of padding
+__host__ __device__ inline int padded_slots(int n, int threads) { return (n + threads + 7) & ~7; }
 
 struct WarpA { int tj, ti; bool ok; };
 
@@ -225,7 +232,7 @@ constexpr unsigned kFracOne = 1u << kFracBits;
 // `uncertain` is set and the caller runs warp_exact.  Saturated conversions (|t| >= 2^17, inf) land
 // out of bounds, NaN converts to 0 and is therefore uncertain.  Straight-line code.
 __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double d,
-                                               int rows, int cols, bool& uncertain) {
+                                               int rows, int cols, unsigned unc_thr, bool& uncertain) {
   const double M0 = col.a.x + r0.x, M1 = col.a.y + r0.y, M2 = col.b.x + r1.x;
   const double X = fma(d, M0, K.x), Y = fma(d, M1, K.y), Z = fma(d, M2, K.z);
   const double iz = rcp_1ulp(Z);
@@ -234,16 +241,17 @@ __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs
   const unsigned fx_ = (unsigned)lx & (kFracOne - 1u), fy_ = (unsigned)ly & (kFracOne - 1u);
   // exponent of Z must be ordinary, otherwise the estimate means nothing (0, denormal, huge, inf, NaN)
   const unsigned ez = ((unsigned)__double2hiint(Z) >> 20) & 0x7ffu;
-  uncertain = (fx_ - 1u >= kFracOne - 2u) | (fy_ - 1u >= kFracOne - 2u) | (ez - 64u > 1900u);
+  uncertain = (max(fx_ - 1u, fy_ - 1u) >= unc_thr) | (ez - 64u > 1900u);
   WarpA w;
   w.tj = lx >> kFracBits; w.ti = ly >> kFracBits;
   w.ok = ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);
   return w;
 }
 
-// predicated shared-memory max: no branch, so the surrounding block stays straight-line
-__device__ __forceinline__ void smem_red_max_if(bool p, unsigned addr, unsigned v) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.max.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((unsigned)p) : "memory");
+// shared-memory max without a result.  Pixels that do not bid are pointed at a per-lane dummy slot
+// instead of being branched around (ptxas turns a predicated red into a branch).
+__device__ __forceinline__ void smem_red_max(unsigned addr, unsigned v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // Phase B of one pixel: J' = J / (gk fx) and the integer residual numerator; the common factors
@@ -278,7 +286,7 @@ struct LevelCtx {
   int rows, cols, n, a, pair;
   const double* gD0; const unsigned short* gI0;
   unsigned* sWin; const unsigned* sG; const unsigned short* sI1; double* sRed;
-  unsigned sWinAddr;
+  unsigned sWinAddr, sDummyAddr;
   Tables tb;
 };
 
@@ -295,11 +303,15 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
   const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
   const double min_depth = bp.min_depth, max_depth = bp.max_depth;
   const int max_iters = bp.max_iters[a];
-  const bool force_exact = bp.exact_always != 0;   // test hook: every pixel takes the exact path
+  // a fraction f of the estimated coordinate is trusted when f - 1 < unc_thr; the test hook
+  // (every pixel takes the exact path) sets the threshold to 0
+  const unsigned unc_thr = bp.exact_always ? 0u : kFracOne - 2u;
+  const unsigned dummy = L.sDummyAddr + 4u * (unsigned)lane;
   // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT
   const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
   const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
   const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
+  const int rstep = 4 * dr2;
   // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
   const double gkfx = bp.grad_k[a] * fx;
   const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
@@ -335,41 +347,48 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
     mycol.cxi = my_cxi;
     __syncthreads();
     // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
+    // D0 / I0 are read through running pointers WITHOUT bounds guards: the prefetch runs up to
+    // 4 BT pixels past the level, into the rest of the record or the slack behind the store
+    // (kBatchStoreSlackBytes); whatever comes back there is masked by `in1` / the loop bound.
     unsigned long long valid = 0ull;
     {
       int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
-      int i = tid;
+      const double2* rp0 = tb.row + 4 * r0_first;     // COLFIX: the thread's column never changes, the row pointers
+      const double2* rp1 = tb.row + 4 * r1_first;     // advance by a constant (rows past the level are zero padding)
+      const double* pd = L.gD0 + tid;
+      const unsigned short* pu = L.gI0 + tid;
       // register prefetch: the loads of the next trip are issued at the top of the current one
-      double p0 = i < n ? __ldg(L.gD0 + i) : 0., p1 = i + BT < n ? __ldg(L.gD0 + i + BT) : 0.;
-      unsigned u0 = i < n ? (unsigned)__ldg(L.gI0 + i) : 0u, u1 = i + BT < n ? (unsigned)__ldg(L.gI0 + i + BT) : 0u;
+      double p0 = __ldg(pd), p1 = __ldg(pd + BT);
+      unsigned u0 = (unsigned)__ldg(pu), u1 = (unsigned)__ldg(pu + BT);
       unsigned vhi = 0u, vlo = 0u;     // validity bits enter at the top and shift down: bit k of `valid` = pixel k
-      for (; i < n; i += 2 * BT) {
-        double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
-        if (i + 2 * BT < n) { f0 = __ldg(L.gD0 + i + 2 * BT); w0 = (unsigned)__ldg(L.gI0 + i + 2 * BT); }
-        if (i + 3 * BT < n) { f1 = __ldg(L.gD0 + i + 3 * BT); w1 = (unsigned)__ldg(L.gI0 + i + 3 * BT); }
+      for (int i = tid; i < n; i += 2 * BT) {
+        const double f0 = __ldg(pd + 2 * BT), f1 = __ldg(pd + 3 * BT);
+        const unsigned w0 = (unsigned)__ldg(pu + 2 * BT), w1 = (unsigned)__ldg(pu + 3 * BT);
+        pd += 2 * BT; pu += 2 * BT;
         const bool in1 = i + BT < n;
-        const int rr1 = in1 ? r1 : 0, cc1 = in1 ? c1 : 0;
         ColRegs ca0 = mycol, ca1 = mycol;
         if (!COLFIX) {
           ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0];
-          ca1.a = tb.colA[cc1]; ca1.b = tb.colB[cc1];
+          ca1.a = tb.colA[c1]; ca1.b = tb.colB[c1];
+          rp0 = tb.row + 4 * r0; rp1 = tb.row + 4 * r1;
         }
         bool unc0, unc1;
-        WarpA a0 = warp_estimate(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], p0, rows, cols, unc0);
-        WarpA a1 = warp_estimate(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], p1, rows, cols, unc1);
+        WarpA a0 = warp_estimate(K, ca0, rp0[0], rp0[1], p0, rows, cols, unc_thr, unc0);
+        WarpA a1 = warp_estimate(K, ca1, rp1[0], rp1[1], p1, rows, cols, unc_thr, unc1);
         const bool dep0 = (min_depth < p0) & (p0 < max_depth);                 // strict bounds, AN:279-280
         const bool dep1 = (min_depth < p1) & (p1 < max_depth) & in1;
-        const bool ex0 = dep0 & (unc0 | force_exact), ex1 = dep1 & (unc1 | force_exact);
+        const bool ex0 = dep0 & unc0, ex1 = dep1 & unc1;
         if (ex0 | ex1) {                                                       // rare: ~2e-4 of the pixels
-          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[r0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
-          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[cc1], tb.ry[rr1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+          const int q0 = COLFIX ? (int)(rp0 - tb.row) >> 2 : r0, q1 = COLFIX ? (int)(rp1 - tb.row) >> 2 : r1;
+          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[q0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c1], tb.ry[q1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
         }
         const bool ok0 = a0.ok & dep0, ok1 = a1.ok & dep1;
-        smem_red_max_if(ok0, L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj), ((unsigned)(i + 1) << 16) | u0);
-        smem_red_max_if(ok1, L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj), ((unsigned)(i + BT + 1) << 16) | u1);
+        smem_red_max(ok0 ? L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj) : dummy, ((unsigned)(i + 1) << 16) | u0);
+        smem_red_max(ok1 ? L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj) : dummy, ((unsigned)(i + BT + 1) << 16) | u1);
         vlo = __funnelshift_r(vlo, vhi, 2);
         vhi = (vhi >> 2) | ((unsigned)ok0 << 30) | ((unsigned)ok1 << 31);
-        if (COLFIX) { r0 += dr2; r1 += dr2; }
+        if (COLFIX) { rp0 += rstep; rp1 += rstep; }
         else {
           c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
@@ -381,41 +400,45 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
     }
     __syncthreads();
     // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
+    // The second pixel of the last trip may lie past the level: its slots are padding (winner word
+    // 0, so residual 0) and its validity bit is 0 (so its Jacobian row is 0).
     double acc[28];
 #pragma unroll
     for (int v = 0; v < 28; ++v) acc[v] = 0.;
     {
       int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
+      const double2* rp0 = tb.row + 4 * r0_first;
+      const double2* rp1 = tb.row + 4 * r1_first;
+      const double* pd = L.gD0 + tid;
+      unsigned* pw = L.sWin + tid;
+      const unsigned* pg = L.sG + tid;
+      const unsigned short* pi1 = L.sI1 + tid;
       unsigned long long vm = valid;
-      int i = tid;
-      double p0 = i < n ? __ldg(L.gD0 + i) : 0., p1 = i + BT < n ? __ldg(L.gD0 + i + BT) : 0.;
-      for (; i < n; i += 2 * BT) {
-        double f0 = 0., f1 = 0.;
-        if (i + 2 * BT < n) f0 = __ldg(L.gD0 + i + 2 * BT);
-        if (i + 3 * BT < n) f1 = __ldg(L.gD0 + i + 3 * BT);
-        const bool in1 = i + BT < n;
-        const int j1 = in1 ? i + BT : i;
-        const int rr1 = in1 ? r1 : 0, cc1 = in1 ? c1 : 0;
-        const unsigned wa = L.sWin[i], wb = in1 ? L.sWin[j1] : 0u;
-        L.sWin[i] = 0u;
-        if (in1) L.sWin[j1] = 0u;
-        const int ra = wa ? (int)L.sI1[i] - (int)(wa & 0xffffu) : 0;
-        const int rb = wb ? (int)L.sI1[j1] - (int)(wb & 0xffffu) : 0;
-        const double resa = (double)ra, resb = (double)rb;
+      double p0 = __ldg(pd), p1 = __ldg(pd + BT);
+      for (int i = tid; i < n; i += 2 * BT) {
+        const double f0 = __ldg(pd + 2 * BT), f1 = __ldg(pd + 3 * BT);
+        pd += 2 * BT;
+        const unsigned wa = pw[0], wb = pw[BT];
+        pw[0] = 0u; pw[BT] = 0u;
+        const int da = (int)pi1[0] - (int)(wa & 0xffffu), db = (int)pi1[BT] - (int)(wb & 0xffffu);
+        const double resa = (double)(wa ? da : 0), resb = (double)(wb ? db : 0);
         ColRegs ca0 = mycol, ca1 = mycol;
         if (!COLFIX) {
           ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0]; ca0.cxi = MODE == 0 ? tb.cxi[c0] : 0.;
-          ca1.a = tb.colA[cc1]; ca1.b = tb.colB[cc1]; ca1.cxi = MODE == 0 ? tb.cxi[cc1] : 0.;
+          ca1.a = tb.colA[c1]; ca1.b = tb.colB[c1]; ca1.cxi = MODE == 0 ? tb.cxi[c1] : 0.;
+          rp0 = tb.row + 4 * r0; rp1 = tb.row + 4 * r1;
         }
+        const unsigned vbits = (unsigned)vm;
         double Ja[6], Jb[6];
-        jacobian_row<MODE>(K, ca0, tb.row[4 * r0], tb.row[4 * r0 + 1], tb.row[4 * r0 + 2], tb.row[4 * r0 + 3], p0, (vm & 1ull) != 0, L.sG[i], Ja);
-        jacobian_row<MODE>(K, ca1, tb.row[4 * rr1], tb.row[4 * rr1 + 1], tb.row[4 * rr1 + 2], tb.row[4 * rr1 + 3], p1, (vm & 2ull) != 0, L.sG[j1], Jb);
+        jacobian_row<MODE>(K, ca0, rp0[0], rp0[1], rp0[2], rp0[3], p0, (vbits & 1u) != 0, pg[0], Ja);
+        jacobian_row<MODE>(K, ca1, rp1[0], rp1[1], rp1[2], rp1[3], p1, (vbits & 2u) != 0, pg[BT], Jb);
         acc[27] = fma(resa, resa, acc[27]);
         accumulate_row(acc, Ja, resa);
         acc[27] = fma(resb, resb, acc[27]);
         accumulate_row(acc, Jb, resb);
         vm >>= 2;
-        if (COLFIX) { r0 += dr2; r1 += dr2; }
+        pw += 2 * BT; pg += 2 * BT; pi1 += 2 * BT;
+        if (COLFIX) { rp0 += rstep; rp1 += rstep; }
         else {
           c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
@@ -469,13 +492,14 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
   constexpr int NW = BT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
-  const int nal = (n + 7) & ~7;
+  const int nal = padded_slots(n, BT);
   unsigned* sWin = (unsigned*)smem_raw;
   unsigned* sG = sWin + nal;
   unsigned short* sI1 = (unsigned short*)(sG + nal);
   double* sTab = (double*)(sI1 + nal);
-  double* sRed = sTab + ((table_doubles(rows, cols) + 1) & ~1);
+  double* sRed = sTab + ((table_doubles(rows, cols, BT) + 1) & ~1);
   BatchShared* sh = (BatchShared*)(sRed + NW * 32);
+  unsigned* sDummy = (unsigned*)(sh + 1);            // 32 slots that absorb the bids of pixels without a target
   const int tid = threadIdx.x;
 
   for (;;) {
@@ -506,17 +530,21 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     L.gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
     L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
     L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
+    L.sDummyAddr = (unsigned)__cvta_generic_to_shared(sDummy);
+    const int pad_rows = table_pad_rows(cols, BT);
     Tables& tb = L.tb;
     tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
-    tb.cx = (double*)(tb.row + 4 * rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
+    tb.cx = (double*)(tb.row + 4 * (rows + pad_rows)); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
     {
       // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
       const double ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
       const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
       uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
-      const int ni = (n * 2 + 15) / 16, nw = (n * 4 + 15) / 16;
+      const int ni = (n * 2 + 15) / 16, nw = nal / 4;
       for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
-      for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);
+      for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);                 // level + padding: no winners
+      for (int k = n + tid; k < nal; k += BT) sG[k] = 0u;                               // padding slots (read, then masked)
+      for (int k = 4 * rows + tid; k < 4 * (rows + pad_rows); k += BT) tb.row[k] = make_double2(0., 0.);
       for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
       for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
     }
@@ -551,9 +579,9 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
 
 // dynamic shared memory of one CTA working on a level of rows x cols pixels with `threads` threads
 static size_t level_smem_bytes(int rows, int cols, int threads) {
-  const size_t nal = ((size_t)rows * cols + 7) & ~(size_t)7;
-  const size_t tab = ((size_t)table_doubles(rows, cols) + 1) & ~(size_t)1;
-  return nal * 10 + tab * sizeof(double) + (size_t)(threads / 32) * 32 * sizeof(double) + sizeof(BatchShared) + 64;
+  const size_t nal = (size_t)padded_slots(rows * cols, threads);
+  const size_t tab = ((size_t)table_doubles(rows, cols, threads) + 1) & ~(size_t)1;
+  return nal * 10 + tab * sizeof(double) + (size_t)(threads / 32) * 32 * sizeof(double) + sizeof(BatchShared) + 32 * sizeof(unsigned) + 64;
 }
 
 // A small level runs as 3 CTAs of kBatchThreadsSmall per SM (each gets a third of the 227 KB).

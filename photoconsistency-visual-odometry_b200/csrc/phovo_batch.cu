@@ -122,7 +122,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     level_size(rows, cols, level, &lr, &lc);
     if (lr < 1 || lc < 1) return ctx->fail(PHOVO_E_INVALID, "image too small for the number of pyramid levels");
     const int n = lr * lc;
-    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (22528 px); use the per-pair API");
+    if (n > kBatchMaxLevelPixels) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: an active level exceeds the shared-memory budget (about 20K px); use the per-pair API");
     nmax = std::max(nmax, n);
     bp->level[a] = level; bp->lrows[a] = lr; bp->lcols[a] = lc;
     bp->max_iters[a] = ctx->cfg.max_num_iterations[level];
@@ -268,7 +268,7 @@ extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows,
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
   BatchParams bp; size_t smem = 0;
   if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
-  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
+  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs + kBatchStoreSlackBytes));
   return run_device(ctx, b, bp, smem, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store,
                     initial_states, states, iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
 }
@@ -293,7 +293,7 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
   if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
   CK(ensure(&b->states, &b->states_cap, (size_t)num_pairs * 6));
   CK(ensure(&b->iters, &b->iters_cap, (size_t)num_pairs * PHOVO_MAX_LEVELS));
-  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs));
+  CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs + kBatchStoreSlackBytes));
   const double* d_init = nullptr;
   if (initial_states) {
     CK(ensure(&b->init, &b->init_cap, (size_t)num_pairs * 6));
