@@ -105,6 +105,31 @@ static_assert(kBatchMaxLevelPixels <= 64 * kBatchThreads, "per-thread validity m
 static_assert(kBatchSmallLevelPixels <= 64 * kBatchThreadsSmall, "per-thread validity mask is 64 bits");
 static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 in 16 bits");
 
+// Everything k_batch_level needs about ITS level, at fixed offsets of the kernel parameter block, so
+// that every field is a constant-bank operand (indexing BatchParams' per-level arrays with a
+// run-time level costs a load and a register per use, inside the pixel loops).
+struct LevelParams {
+  int num_pairs, rows, cols, n;
+  int level, max_iters, first, log_cap;          // first: coarsest active level (starts from the caller's state)
+  int exact_always, force_generic;
+  unsigned long long off_I0, off_I1, off_D0, record_bytes;
+  double fx, fy, ox, oy, inv_fx, inv_fy;
+  double lambda, min_grad, grad_k;
+  double min_depth, max_depth;
+};
+
+static LevelParams level_params(const BatchParams& bp, int a) {
+  LevelParams lv;
+  lv.num_pairs = bp.num_pairs; lv.rows = bp.lrows[a]; lv.cols = bp.lcols[a]; lv.n = lv.rows * lv.cols;
+  lv.level = bp.level[a]; lv.max_iters = bp.max_iters[a]; lv.first = a == 0; lv.log_cap = bp.log_cap;
+  lv.exact_always = bp.exact_always; lv.force_generic = bp.force_generic;
+  lv.off_I0 = bp.off_I0[a]; lv.off_I1 = bp.off_I1[a]; lv.off_D0 = bp.off_D0[a]; lv.record_bytes = bp.record_bytes;
+  lv.fx = bp.fx[a]; lv.fy = bp.fy[a]; lv.ox = bp.ox[a]; lv.oy = bp.oy[a]; lv.inv_fx = bp.inv_fx[a]; lv.inv_fy = bp.inv_fy[a];
+  lv.lambda = bp.lambda[a]; lv.min_grad = bp.min_grad[a]; lv.grad_k = bp.grad_k[a];
+  lv.min_depth = bp.min_depth; lv.max_depth = bp.max_depth;
+  return lv;
+}
+
 struct BatchShared {
   PoseDev pose;          // state + rotation / trig of the current iterate
   double totals[32];
@@ -122,7 +147,7 @@ struct BatchShared {
 // with one correctly rounded reciprocal per pivot.  No shuffles on the critical path: a serial
 // chain of ~50 dependent fp64 operations instead of ~100 shuffle round trips.  Then state update,
 // sincos on three lanes, rotation, termination flag.  Lane 0 publishes.
-__device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchParams& bp, int a, int it, int pair,
+__device__ __forceinline__ void warp_gn_step(double tot, int lane, const LevelParams& lv, int it, int pair,
                                              BatchShared* sh, phovo_iter_stats* log) {
   const unsigned FULL = 0xffffffffu;
   sh->totals[lane] = tot;
@@ -131,7 +156,7 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
   solve6_ldlt(sh->totals, sh->totals + 21, x);
 #pragma unroll
   for (int k = 0; k < 6; ++k) n2 = fma(sh->totals[21 + k], sh->totals[21 + k], n2);
-  const double lambda = bp.lambda[a];
+  const double lambda = lv.lambda;
   double s_in[6], s_out[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) { s_in[k] = sh->pose.state[k]; s_out[k] = s_in[k] - lambda * x[k]; }   // AN:539-540
@@ -146,13 +171,13 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchPa
   P.sr = __shfl_sync(FULL, sn, 2); P.cr = __shfl_sync(FULL, cs, 2);
   rotation_from_trig(P);
   const double gnorm = sqrt(n2);
-  const int done = (it + 1 >= bp.max_iters[a]) || (gnorm < bp.min_grad[a]);   // AN:383-392
+  const int done = (it + 1 >= lv.max_iters) || (gnorm < lv.min_grad);   // AN:383-392
   __syncwarp();
   if (lane == 0) {
-    if (log && sh->pose.log_count < bp.log_cap) {
+    if (log && sh->pose.log_count < lv.log_cap) {
       const double* t = sh->totals;
-      phovo_iter_stats* e = log + (size_t)pair * bp.log_cap + sh->pose.log_count;
-      e->level = bp.level[a]; e->iteration = it; e->num_valid = (int)t[28]; e->accepted = 1;
+      phovo_iter_stats* e = log + (size_t)pair * lv.log_cap + sh->pose.log_count;
+      e->level = lv.level; e->iteration = it; e->num_valid = (int)t[28]; e->accepted = 1;
       for (int k = 0; k < 21; ++k) e->H[k] = t[k];
       for (int k = 0; k < 6; ++k) { e->g[k] = t[21 + k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
       e->grad_norm = gnorm; e->cost = 0.5 * t[27]; e->radius = 0.;
@@ -186,13 +211,13 @@ __host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
 // shared-memory slots of the three per-pixel arrays: the level plus `threads` slots of padding
 __host__ __device__ inline int padded_slots(int n, int threads) { return (n + threads + 7) & ~7; }
 
-struct WarpA { int tj, ti; bool ok; };
+struct WarpA { int tj, ti; };   // rounded target column / row; out of the image <=> the pixel does not bid
 
 // The reference's warp of one pixel, AN:279-303: fp64, its operation order, no FMA contraction,
 // correctly rounded reciprocal, C round().  Used for the (rare) pixels whose cheap estimate falls
 // within 2^-17 px of a rounding boundary, and for everything when bp.exact_always is set.
 __device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double ry, double d, double fx, double fy, double ox, double oy,
-                                         double inv_fx, double inv_fy, int rows, int cols) {
+                                         double inv_fx, double inv_fy) {
   Pose T;
   pose_load(pose, T);
   const double px = __dmul_rn(__dmul_rn(cx, d), inv_fx);
@@ -203,14 +228,13 @@ __device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double 
   WarpA w;
   const double az = fabs(Z);
   // |Z| outside the normal range (incl. NaN / 0, where the reference's int cast is undefined) is out of bounds
-  if (!((az > 1e-300) & (az < 1e300))) { w.tj = -1; w.ti = -1; w.ok = false; return w; }
+  if (!((az > 1e-300) & (az < 1e300))) { w.tj = -1; w.ti = -1; return w; }
   const double iz = rcp_rn_normal(Z);                                       // AN:294 `1./Z`
   const double tc = __dadd_rn(__dmul_rn(__dmul_rn(X, fx), iz), ox);
   const double tr = __dadd_rn(__dmul_rn(__dmul_rn(Y, fy), iz), oy);
   // C round(): half away from zero == trunc(x + copysign(0.5, x)) with the add rounded toward zero
   w.tj = __double2int_rz(__dadd_rz(tc, copysign(0.5, tc)));
-  w.ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));
-  w.ok = ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);   // saturated casts fail the range test
+  w.ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));   // saturated casts fail the caller's range test
   return w;
 }
 
@@ -224,28 +248,38 @@ struct ColRegs { double2 a, b; double cxi; };   // column entries of the tables 
 constexpr int kFracBits = 14;                 // fixed-point fraction bits of the estimated target coordinate
 constexpr unsigned kFracOne = 1u << kFracBits;
 
-// Phase A of one pixel, fast path.  Estimates the warped coordinate from the per-iteration tables
-// (error < 1e-9 px: ~15 roundings of 2^-53 on coordinates below 2^16) as floor((t + 0.5) 2^14) in a
-// 32-bit integer.  If the 14-bit fraction is neither 0 nor 2^14 - 1 the estimate is at least
-// 2^-14 px away from a rounding boundary, so the rounded pixel is certain and equals the
-// reference's round() (also for t in (-0.5, 0), which round() maps to -0 -> column 0); otherwise
-// `uncertain` is set and the caller runs warp_exact.  Saturated conversions (|t| >= 2^17, inf) land
-// out of bounds, NaN converts to 0 and is therefore uncertain.  Straight-line code.
+// Phase A of one pixel, fast path.  Estimates the warped coordinate from the per-iteration tables as
+// floor((t + 0.5) 2^14) in a 32-bit integer.  If the 14-bit fraction is neither 0 nor 2^14 - 1 the
+// estimate is at least 2^-14 px away from a rounding boundary, so -- provided estimate and reference
+// agree to 2^-14 px -- the rounded pixel is certain and equals the reference's round() (also for t in
+// (-0.5, 0), which round() maps to -0 -> column 0); otherwise `uncertain` is set and the caller runs
+// warp_exact.  Agreement: both evaluations make ~25 roundings of 2^-53 relative to S, the largest
+// summand of X', Y', Z' (see gn_level), so t = f X'/Z' + o differs by at most
+// 2^-46 S (f + |t - o|) / |Z'|, which is below 2^-14 px for every t near the image once
+// |Z'| >= zmin = 2^-30 S (f + cols + rows + |o| + 2).  Pixels closer to the camera plane than zmin
+// (cancellation in Z') are uncertain as well: the caller passes the high word of zmin.  Saturated
+// conversions (|t| >= 2^17, inf) land out of bounds, NaN converts to 0 and is therefore
+// uncertain.  Straight-line code.
 __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double d,
-                                               int rows, int cols, unsigned unc_thr, bool& uncertain) {
+                                               unsigned unc_thr, unsigned zmin_hi, bool& uncertain) {
   const double M0 = col.a.x + r0.x, M1 = col.a.y + r0.y, M2 = col.b.x + r1.x;
   const double X = fma(d, M0, K.x), Y = fma(d, M1, K.y), Z = fma(d, M2, K.z);
   const double iz = rcp_1ulp(Z);
   const int lx = __double2int_rd(fma(X * K.fxs, iz, K.oxs));
   const int ly = __double2int_rd(fma(Y * K.fys, iz, K.oys));
   const unsigned fx_ = (unsigned)lx & (kFracOne - 1u), fy_ = (unsigned)ly & (kFracOne - 1u);
-  // exponent of Z must be ordinary, otherwise the estimate means nothing (0, denormal, huge, inf, NaN)
-  const unsigned ez = ((unsigned)__double2hiint(Z) >> 20) & 0x7ffu;
-  uncertain = (max(fx_ - 1u, fy_ - 1u) >= unc_thr) | (ez - 64u > 1900u);
+  uncertain = (max(fx_ - 1u, fy_ - 1u) >= unc_thr) | (((unsigned)__double2hiint(Z) & 0x7fffffffu) < zmin_hi);
   WarpA w;
   w.tj = lx >> kFracBits; w.ti = ly >> kFracBits;
-  w.ok = ((unsigned)w.tj < (unsigned)cols) & ((unsigned)w.ti < (unsigned)rows);
   return w;
+}
+
+// u16 from global memory straight into a 32-bit register (zero-extended by the load): as an
+// `unsigned short` the value travels in half registers and costs a PRMT and a mask per trip.
+__device__ __forceinline__ unsigned ldg_u16(const unsigned short* p) {
+  unsigned v;
+  asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 // shared-memory max without a result.  Pixels that do not bid are pointed at a per-lane dummy slot
@@ -283,7 +317,7 @@ __device__ __forceinline__ void jacobian_row(const IterConst& K, const ColRegs& 
 }
 
 struct LevelCtx {
-  int rows, cols, n, a, pair;
+  int pair;
   const double* gD0; const unsigned short* gI0;
   unsigned* sWin; const unsigned* sG; const unsigned short* sI1; double* sRed;
   unsigned sWinAddr, sDummyAddr;
@@ -295,25 +329,31 @@ struct LevelCtx {
 // of the tables live in registers and only the row advances.  The thread -> pixel mapping is the
 // same linear one in both variants, so results are bitwise identical.
 template <int MODE, bool COLFIX, int BT>
-__device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
+__device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
   constexpr int NW = BT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows = L.rows, cols = L.cols, n = L.n, a = L.a;
+  const int rows = lv.rows, cols = lv.cols, n = lv.n;
   const Tables& tb = L.tb;
-  const double fx = bp.fx[a], fy = bp.fy[a], ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
-  const double min_depth = bp.min_depth, max_depth = bp.max_depth;
-  const int max_iters = bp.max_iters[a];
+  const double fx = lv.fx, fy = lv.fy, ox = lv.ox, oy = lv.oy, inv_fx = lv.inv_fx, inv_fy = lv.inv_fy;
+  const double min_depth = lv.min_depth, max_depth = lv.max_depth;
+  const int max_iters = lv.max_iters;
   // a fraction f of the estimated coordinate is trusted when f - 1 < unc_thr; the test hook
   // (every pixel takes the exact path) sets the threshold to 0
-  const unsigned unc_thr = bp.exact_always ? 0u : kFracOne - 2u;
-  const unsigned dummy = L.sDummyAddr + 4u * (unsigned)lane;
+  const unsigned unc_thr = lv.exact_always ? 0u : kFracOne - 2u;
+  unsigned dummy;                                  // opaque, or ptxas rebuilds it from %tid in every trip
+  asm volatile("mov.u32 %0, %1;" : "=r"(dummy) : "r"(L.sDummyAddr + 4u * (unsigned)lane));
+  // geometry part of zmin (see warp_estimate) and the bound on |ray| of the level
+  const double zmin_geo = 0x1p-30 * (fmax(fabs(fx), fabs(fy)) + (double)(cols + rows + 2) + fabs(ox) + fabs(oy));
+  const double ray_bound = fmax(fabs(ox), fabs((double)(cols - 1) - ox)) * fabs(inv_fx) + fmax(fabs(oy), fabs((double)(rows - 1) - oy)) * fabs(inv_fy) + 1.0;
+  const double depth_bound = fmax(fabs(min_depth), fabs(max_depth));
   // pixel i = tid + k*BT; a trip of the loops handles pixels i and i + BT
   const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
   const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
   const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
-  const int rstep = 4 * dr2;
+  int rstep_bytes;                                 // row-table advance of one trip (opaque for the same reason)
+  asm volatile("mov.u32 %0, %1;" : "=r"(rstep_bytes) : "r"(4 * dr2 * (int)sizeof(double2)));
   // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
-  const double gkfx = bp.grad_k[a] * fx;
+  const double gkfx = lv.grad_k * fx;
   const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
   IterConst K;
   K.rho = fy / fx;
@@ -326,6 +366,13 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
     Pose T;
     pose_load(&sh->pose, T);
     K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy;
+    // S bounds every summand of X', Y', Z' of a pixel inside the depth range.  If it is not an ordinary
+    // number (diverged or NaN state, unbounded depth range) the estimate is not used at all.
+    const double S = fma(depth_bound, ray_bound, fmax(fmax(fabs(T.x), fabs(T.y)), fabs(T.z)));
+    const double zmin = fmax(S * zmin_geo, 0x1p-500);
+    const bool ordinary = (S < 0x1p500) & (zmin_geo < 0x1p100) & (T.x == T.x) & (T.y == T.y) & (T.z == T.z);
+    const unsigned thr = ordinary ? unc_thr : 0u;
+    const unsigned zmin_hi = (unsigned)__double2hiint(zmin) + 1u;
     // ---- per-iteration tables ----
     for (int k = tid; k < (COLFIX ? 0 : cols) + rows; k += BT) {
       if (!COLFIX && k < cols) {
@@ -359,11 +406,15 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
       const unsigned short* pu = L.gI0 + tid;
       // register prefetch: the loads of the next trip are issued at the top of the current one
       double p0 = __ldg(pd), p1 = __ldg(pd + BT);
-      unsigned u0 = (unsigned)__ldg(pu), u1 = (unsigned)__ldg(pu + BT);
+      unsigned u0 = ldg_u16(pu), u1 = ldg_u16(pu + BT);
       unsigned vhi = 0u, vlo = 0u;     // validity bits enter at the top and shift down: bit k of `valid` = pixel k
-      for (int i = tid; i < n; i += 2 * BT) {
-        const double f0 = __ldg(pd + 2 * BT), f1 = __ldg(pd + 3 * BT);
-        const unsigned w0 = (unsigned)__ldg(pu + 2 * BT), w1 = (unsigned)__ldg(pu + 3 * BT);
+      unsigned bid = (unsigned)(tid + 1) << 16;   // winner word of pixel i without its I0: (i + 1) << 16
+      // one trip: prefetch the next trip's pixels into (n0, n1, nu0, nu1), process (c0_, c1_, cu0, cu1).
+      // Two copies of the trip alternate the roles of the two register sets, so nothing is moved.
+      auto trip = [&](const double c0_, const double c1_, const unsigned cu0, const unsigned cu1,
+                      double& n0, double& n1, unsigned& nu0, unsigned& nu1, const int i) {
+        n0 = __ldg(pd + 2 * BT); n1 = __ldg(pd + 3 * BT);
+        nu0 = ldg_u16(pu + 2 * BT); nu1 = ldg_u16(pu + 3 * BT);
         pd += 2 * BT; pu += 2 * BT;
         const bool in1 = i + BT < n;
         ColRegs ca0 = mycol, ca1 = mycol;
@@ -373,27 +424,34 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
           rp0 = tb.row + 4 * r0; rp1 = tb.row + 4 * r1;
         }
         bool unc0, unc1;
-        WarpA a0 = warp_estimate(K, ca0, rp0[0], rp0[1], p0, rows, cols, unc_thr, unc0);
-        WarpA a1 = warp_estimate(K, ca1, rp1[0], rp1[1], p1, rows, cols, unc_thr, unc1);
-        const bool dep0 = (min_depth < p0) & (p0 < max_depth);                 // strict bounds, AN:279-280
-        const bool dep1 = (min_depth < p1) & (p1 < max_depth) & in1;
+        WarpA a0 = warp_estimate(K, ca0, rp0[0], rp0[1], c0_, thr, zmin_hi, unc0);
+        WarpA a1 = warp_estimate(K, ca1, rp1[0], rp1[1], c1_, thr, zmin_hi, unc1);
+        const bool dep0 = (min_depth < c0_) & (c0_ < max_depth);                 // strict bounds, AN:279-280
+        const bool dep1 = (min_depth < c1_) & (c1_ < max_depth) & in1;
         const bool ex0 = dep0 & unc0, ex1 = dep1 & unc1;
         if (ex0 | ex1) {                                                       // rare: ~2e-4 of the pixels
-          const int q0 = COLFIX ? (int)(rp0 - tb.row) >> 2 : r0, q1 = COLFIX ? (int)(rp1 - tb.row) >> 2 : r1;
-          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[q0], p0, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
-          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c1], tb.ry[q1], p1, fx, fy, ox, oy, inv_fx, inv_fy, rows, cols);
+          const int q0 = COLFIX ? i / cols : r0, q1 = COLFIX ? (i + BT) / cols : r1;
+          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[q0], c0_, fx, fy, ox, oy, inv_fx, inv_fy);
+          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c1], tb.ry[q1], c1_, fx, fy, ox, oy, inv_fx, inv_fy);
         }
-        const bool ok0 = a0.ok & dep0, ok1 = a1.ok & dep1;
-        smem_red_max(ok0 ? L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj) : dummy, ((unsigned)(i + 1) << 16) | u0);
-        smem_red_max(ok1 ? L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj) : dummy, ((unsigned)(i + BT + 1) << 16) | u1);
+        const bool ok0 = ((unsigned)a0.tj < (unsigned)cols) & ((unsigned)a0.ti < (unsigned)rows) & dep0;
+        const bool ok1 = ((unsigned)a1.tj < (unsigned)cols) & ((unsigned)a1.ti < (unsigned)rows) & dep1;
+        smem_red_max(ok0 ? L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj) : dummy, bid + cu0);
+        smem_red_max(ok1 ? L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj) : dummy, bid + ((unsigned)BT << 16) + cu1);
+        bid += (unsigned)(2 * BT) << 16;
         vlo = __funnelshift_r(vlo, vhi, 2);
         vhi = (vhi >> 2) | ((unsigned)ok0 << 30) | ((unsigned)ok1 << 31);
-        if (COLFIX) { rp0 += rstep; rp1 += rstep; }
+        if (COLFIX) { rp0 = (const double2*)((const char*)rp0 + rstep_bytes); rp1 = (const double2*)((const char*)rp1 + rstep_bytes); }
         else {
           c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
         }
-        p0 = f0; p1 = f1; u0 = w0; u1 = w1;
+      };
+      double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
+      for (int i = tid; i < n; i += 4 * BT) {
+        trip(p0, p1, u0, u1, f0, f1, w0, w1, i);
+        if (i + 2 * BT >= n) break;
+        trip(f0, f1, w0, w1, p0, p1, u0, u1, i + 2 * BT);
       }
       valid = ((unsigned long long)vhi << 32) | vlo;
       valid = trips > 0 ? valid >> (64 - 2 * trips) : 0ull;
@@ -415,8 +473,8 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
       const unsigned short* pi1 = L.sI1 + tid;
       unsigned long long vm = valid;
       double p0 = __ldg(pd), p1 = __ldg(pd + BT);
-      for (int i = tid; i < n; i += 2 * BT) {
-        const double f0 = __ldg(pd + 2 * BT), f1 = __ldg(pd + 3 * BT);
+      auto trip = [&](const double c0_, const double c1_, double& n0, double& n1) {
+        n0 = __ldg(pd + 2 * BT); n1 = __ldg(pd + 3 * BT);
         pd += 2 * BT;
         const unsigned wa = pw[0], wb = pw[BT];
         pw[0] = 0u; pw[BT] = 0u;
@@ -430,20 +488,25 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
         }
         const unsigned vbits = (unsigned)vm;
         double Ja[6], Jb[6];
-        jacobian_row<MODE>(K, ca0, rp0[0], rp0[1], rp0[2], rp0[3], p0, (vbits & 1u) != 0, pg[0], Ja);
-        jacobian_row<MODE>(K, ca1, rp1[0], rp1[1], rp1[2], rp1[3], p1, (vbits & 2u) != 0, pg[BT], Jb);
+        jacobian_row<MODE>(K, ca0, rp0[0], rp0[1], rp0[2], rp0[3], c0_, (vbits & 1u) != 0, pg[0], Ja);
+        jacobian_row<MODE>(K, ca1, rp1[0], rp1[1], rp1[2], rp1[3], c1_, (vbits & 2u) != 0, pg[BT], Jb);
         acc[27] = fma(resa, resa, acc[27]);
         accumulate_row(acc, Ja, resa);
         acc[27] = fma(resb, resb, acc[27]);
         accumulate_row(acc, Jb, resb);
         vm >>= 2;
         pw += 2 * BT; pg += 2 * BT; pi1 += 2 * BT;
-        if (COLFIX) { rp0 += rstep; rp1 += rstep; }
+        if (COLFIX) { rp0 = (const double2*)((const char*)rp0 + rstep_bytes); rp1 = (const double2*)((const char*)rp1 + rstep_bytes); }
         else {
           c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
         }
-        p0 = f0; p1 = f1;
+      };
+      double f0 = 0., f1 = 0.;
+      for (int i = tid; i < n; i += 4 * BT) {
+        trip(p0, p1, f0, f1);
+        if (i + 2 * BT >= n) break;
+        trip(f0, f1, p0, p1);
       }
     }
     // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
@@ -459,7 +522,7 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
       double t0 = 0., t1 = 0.;   // two interleaved chains, fixed order
 #pragma unroll
       for (int w = 0; w < NW; w += 2) { t0 += L.sRed[w * 32 + lane]; if (w + 1 < NW) t1 += L.sRed[(w + 1) * 32 + lane]; }
-      warp_gn_step((t0 + t1) * scale, lane, bp, a, it, L.pair, sh, log);
+      warp_gn_step((t0 + t1) * scale, lane, lv, it, L.pair, sh, log);
     }
     __syncthreads();
     if (sh->done) break;
@@ -484,14 +547,14 @@ __device__ __forceinline__ void gn_level(const BatchParams& bp, const LevelCtx& 
 // stays in a 64-bit register mask between the two phases of an iteration.  The thread -> pixel
 // mapping is a pure function of the level size, so results do not depend on grid, batch or GPU.
 template <int MODE, int BT, int MINB>
-__global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ BatchParams bp, const int a,
+__global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ LevelParams lv,
                                                           const uint8_t* __restrict__ store,
                                                           const double* __restrict__ init_states, double* __restrict__ states,
                                                           int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
                                                           int32_t* __restrict__ log_counts, unsigned int* __restrict__ next_pair) {
   constexpr int NW = BT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int rows = bp.lrows[a], cols = bp.lcols[a], n = rows * cols;
+  const int rows = lv.rows, cols = lv.cols, n = lv.n;
   const int nal = padded_slots(n, BT);
   unsigned* sWin = (unsigned*)smem_raw;
   unsigned* sG = sWin + nal;
@@ -507,27 +570,27 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     if (tid == 0) {
       const int pair = (int)atomicAdd(next_pair, 1u);
       sh->pair = pair;
-      if (pair < bp.num_pairs) {
+      if (pair < lv.num_pairs) {
         double s[6];
-        const double* src = a == 0 ? init_states : states;     // the first level starts from the caller's state
+        const double* src = lv.first ? init_states : states;     // the first level starts from the caller's state
         for (int k = 0; k < 6; ++k) s[k] = src ? src[(size_t)pair * 6 + k] : 0.;
         Pose P;
         pose_from_state(s, P);
         for (int k = 0; k < 6; ++k) sh->pose.state[k] = s[k];
         pose_store(P, &sh->pose);
-        sh->pose.log_count = (a == 0 || !log_counts) ? 0 : log_counts[pair];
+        sh->pose.log_count = (lv.first || !log_counts) ? 0 : log_counts[pair];
         sh->done = 0; sh->iteration = 0;
       }
     }
     __syncthreads();
     const int pair = sh->pair;
-    if (pair >= bp.num_pairs) break;
-    const uint8_t* rec = store + (size_t)pair * bp.record_bytes;
+    if (pair >= lv.num_pairs) break;
+    const uint8_t* rec = store + (size_t)pair * lv.record_bytes;
 
     LevelCtx L;
-    L.rows = rows; L.cols = cols; L.n = n; L.a = a; L.pair = pair;
-    L.gD0 = (const double*)(rec + bp.off_D0[a]);
-    L.gI0 = (const unsigned short*)(rec + bp.off_I0[a]);
+    L.pair = pair;
+    L.gD0 = (const double*)(rec + lv.off_D0);
+    L.gI0 = (const unsigned short*)(rec + lv.off_I0);
     L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
     L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
     L.sDummyAddr = (unsigned)__cvta_generic_to_shared(sDummy);
@@ -537,8 +600,8 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     tb.cx = (double*)(tb.row + 4 * (rows + pad_rows)); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
     {
       // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
-      const double ox = bp.ox[a], oy = bp.oy[a], inv_fx = bp.inv_fx[a], inv_fy = bp.inv_fy[a];
-      const uint4* gI1 = (const uint4*)(rec + bp.off_I1[a]);
+      const double ox = lv.ox, oy = lv.oy, inv_fx = lv.inv_fx, inv_fy = lv.inv_fy;
+      const uint4* gI1 = (const uint4*)(rec + lv.off_I1);
       uint4* i14 = (uint4*)sI1; uint4* w4 = (uint4*)sWin;
       const int ni = (n * 2 + 15) / 16, nw = nal / 4;
       for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
@@ -566,10 +629,10 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       }
     }
     // (the first barrier inside gn_level orders these writes before the pixel loops)
-    if (BT % cols == 0 && !bp.force_generic) gn_level<MODE, true, BT>(bp, L, sh, log);
-    else gn_level<MODE, false, BT>(bp, L, sh, log);
+    if (BT % cols == 0 && !lv.force_generic) gn_level<MODE, true, BT>(lv, L, sh, log);
+    else gn_level<MODE, false, BT>(lv, L, sh, log);
     __syncthreads();
-    if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + bp.level[a]] = sh->iteration;
+    if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + lv.level] = sh->iteration;
     if (tid < 6) states[(size_t)pair * 6 + tid] = sh->pose.state[tid];
     if (tid == 0 && log_counts) log_counts[pair] = sh->pose.log_count;
   }
@@ -620,16 +683,17 @@ int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count,
   int launches = 0;
   for (int a = 0; a < bp.num_active; ++a) {
     const int rows = bp.lrows[a], cols = bp.lcols[a];
+    const LevelParams lv = level_params(bp, a);
     const size_t smem = batch_level_smem_bytes(rows, cols);
     const bool fixed = bp.mode == PHOVO_MODE_ANALYTIC_FIXED;
     if (batch_level_is_small(rows, cols)) {
       const int grid = min(bp.num_pairs, 3 * sm_count);
-      if (fixed) k_batch_level<1, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
-      else k_batch_level<0, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+      if (fixed) k_batch_level<1, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
+      else k_batch_level<0, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
     } else {
       const int grid = min(bp.num_pairs, sm_count);
-      if (fixed) k_batch_level<1, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
-      else k_batch_level<0, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(bp, a, store, init_states, states, iters, log, log_counts, next_pair + a);
+      if (fixed) k_batch_level<1, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
+      else k_batch_level<0, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
     }
     ++launches;
   }
