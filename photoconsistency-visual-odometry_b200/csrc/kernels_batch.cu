@@ -195,18 +195,20 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const LevelPa
 //   exact  : cx[c] = fl(c - ox), ry[r] = fl(r - oy)            the reference's own roundings (AN:282-287)
 //   ray    : cxi[c] = cx[c] * inv_fx, ryi[r] = ry[r] * inv_fy  back-projected ray (px/d, py/d)
 //   colA/B : {R00 cxi, R10 cxi}, {R20 cxi, -cp cxi}            per ITERATION: the column part of R*(ray) and of dZ'/dpitch
-//   row    : {R01 ryi + R02, R11 ryi + R12}, {R21 ryi + R22, -(sp sr ryi + sp cr)}, {R22 ryi - R21, R02 ryi - R01}, {R12 ryi - R11, 0}
+//   row    : {R01 ryi + R02, R11 ryi + R12}, {R21 ryi + R22, -(sp sr ryi + sp cr)}, {R22 ryi - R21, R02 ryi - R01}, {R12 ryi - R11, 0},
+//            {fxs (R01 ryi + R02), fys (R11 ryi + R12)}          (entry 0 pre-scaled for the fixed-point estimate of phase A)
 // so that  R p = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
 // The row table carries ceil(threads / cols) rows of zero padding: the second pixel of a thread's
 // last trip may lie up to `threads` pixels past the level and is read (and masked) without a guard.
+constexpr int kRowEntries = 5;
 struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
-  double2* row;                   // [rows + pad][4]
+  double2* row;                   // [rows + pad][kRowEntries]
 };
 __host__ __device__ inline int table_pad_rows(int cols, int threads) { return (threads + cols - 1) / cols; }
 __host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
-  return 2 * (rows + cols) + 4 * cols + 8 * (rows + table_pad_rows(cols, threads));
+  return 2 * (rows + cols) + 4 * cols + 2 * kRowEntries * (rows + table_pad_rows(cols, threads));
 }
 // shared-memory slots of the three per-pixel arrays: the level plus `threads` slots of padding
 __host__ __device__ inline int padded_slots(int n, int threads) { return (n + threads + 7) & ~7; }
@@ -240,10 +242,12 @@ __device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double 
 
 struct IterConst {          // per-iteration scalars besides the tables
   double x, y, z, cy, sy, rho;
-  double fxs, fys, oxs, oys;   // fx 2^20, fy 2^20, (ox + 0.5) 2^20, (oy + 0.5) 2^20  (phase A fixed point)
+  double fxs, fys, oxs, oys;   // fx 2^14, fy 2^14, (ox + 0.5) 2^14, (oy + 0.5) 2^14  (phase A fixed point)
+  double xs, ys;               // fxs x, fys y
 };
 
-struct ColRegs { double2 a, b; double cxi; };   // column entries of the tables for one pixel
+struct ColRegs { double2 a, b; double cxix; };   // column entries of the tables for one pixel; cxix = cxi * x (MODE 0 only)
+struct ColRegsA { double2 as; double bx; };      // phase A: {fxs R00 cxi, fys R10 cxi}, R20 cxi
 
 constexpr int kFracBits = 14;                 // fixed-point fraction bits of the estimated target coordinate
 constexpr unsigned kFracOne = 1u << kFracBits;
@@ -260,13 +264,13 @@ constexpr unsigned kFracOne = 1u << kFracBits;
 // (cancellation in Z') are uncertain as well: the caller passes the high word of zmin.  Saturated
 // conversions (|t| >= 2^17, inf) land out of bounds, NaN converts to 0 and is therefore
 // uncertain.  Straight-line code.
-__device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double d,
+__device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegsA& col, double2 rs, double r1x, double d,
                                                unsigned unc_thr, unsigned zmin_hi, bool& uncertain) {
-  const double M0 = col.a.x + r0.x, M1 = col.a.y + r0.y, M2 = col.b.x + r1.x;
-  const double X = fma(d, M0, K.x), Y = fma(d, M1, K.y), Z = fma(d, M2, K.z);
+  const double M0 = col.as.x + rs.x, M1 = col.as.y + rs.y, M2 = col.bx + r1x;     // M0, M1 carry fxs, fys
+  const double X = fma(d, M0, K.xs), Y = fma(d, M1, K.ys), Z = fma(d, M2, K.z);
   const double iz = rcp_1ulp(Z);
-  const int lx = __double2int_rd(fma(X * K.fxs, iz, K.oxs));
-  const int ly = __double2int_rd(fma(Y * K.fys, iz, K.oys));
+  const int lx = __double2int_rd(fma(X, iz, K.oxs));
+  const int ly = __double2int_rd(fma(Y, iz, K.oys));
   const unsigned fx_ = (unsigned)lx & (kFracOne - 1u), fy_ = (unsigned)ly & (kFracOne - 1u);
   uncertain = (max(fx_ - 1u, fy_ - 1u) >= unc_thr) | (((unsigned)__double2hiint(Z) & 0x7fffffffu) < zmin_hi);
   WarpA w;
@@ -290,30 +294,32 @@ __device__ __forceinline__ void smem_red_max(unsigned addr, unsigned v) {
 
 // Phase B of one pixel: J' = J / (gk fx) and the integer residual numerator; the common factors
 // are applied once per iteration to the reduced sums.  Everything is computed unconditionally on
-// sanitised operands and masked, so that two pixels interleave without branches.
+// sanitised operands and masked, so that two pixels interleave without branches.  With
+// m = col + row (the rotated ray of the pixel, R p = d m) the closed form of AN:243-342 (SURVEY
+// appendix C) is written in the products ga d, gb d, J2 d, which needs 27 fp64 operations.
 template <int MODE>
 __device__ __forceinline__ void jacobian_row(const IterConst& K, const ColRegs& col, double2 r0, double2 r1, double2 r2, double2 r3,
                                              double d, bool valid, unsigned gw, double J[6]) {
   // an invalid pixel contributes a zero row: depth and 1/Z' are forced to 0 (the raw values may be
-  // 0, inf or NaN), everything downstream is then finite and multiplied by zero
+  // 0, inf or NaN), everything downstream is then a finite table entry times zero
   const double ds = valid ? d : 0.;
-  const double q0 = ds * (col.a.x + r0.x), q1 = ds * (col.a.y + r0.y), q2 = ds * (col.b.x + r1.x);
-  const double izr = rcp_1ulp(q2 + K.z);
+  const double m0 = col.a.x + r0.x, m1 = col.a.y + r0.y, m2 = col.b.x + r1.x, m3 = col.b.y + r1.y;
+  const double izr = rcp_1ulp(fma(ds, m2, K.z));
   const double iz = valid ? izr : 0.;
   // a' = Gx1[i] / Z', b' = Gy1[i] (fy/fx) / Z'   (gradients at the SOURCE index, AN:346-347)
   const double ga = (double)(short)(gw & 0xffffu) * iz;
   const double gb = (double)((int)gw >> 16) * (iz * K.rho);
-  // closed form of AN:243-342, gradient folded in
-  const double A = MODE == 0 ? fma(ds * col.cxi, K.x, q0) : q0 + K.x;   // AN:253 bug-compatible / Maxima-exact
-  const double B = q1 + K.y;
+  const double gau = ga * ds, gbu = gb * ds;
+  // ga X' + gb Y' with X' = d m0 + x (AN:253 reads d (m0 + cxi x): bug-compatible in MODE 0), Y' = d m1 + y
+  const double s = MODE == 0 ? fma(gau, m0 + col.cxix, fma(gbu, m1, gb * K.y))
+                             : fma(gau, m0, fma(gbu, m1, fma(ga, K.x, gb * K.y)));
   J[0] = ga;
   J[1] = gb;
-  J[2] = -(fma(ga, A, gb * B) * iz);
-  J[3] = fma(gb, q0, -(ga * q1));
-  const double Zp = ds * (col.b.y + r1.y);
-  J[4] = fma(q2, fma(ga, K.cy, gb * K.sy), Zp * J[2]);
-  const double Zr = ds * r2.x, t5a = ds * r2.y, t5b = ds * r3.x;
-  J[5] = fma(ga, t5a, fma(gb, t5b, Zr * J[2]));
+  J[2] = -(s * iz);
+  const double j2d = J[2] * ds;
+  J[3] = fma(gbu, m0, -(gau * m1));
+  J[4] = fma(m3, j2d, m2 * fma(gau, K.cy, gbu * K.sy));
+  J[5] = fma(gau, r2.y, fma(gbu, r3.x, r2.x * j2d));
 }
 
 struct LevelCtx {
@@ -351,7 +357,7 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
   const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
   const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
   int rstep_bytes;                                 // row-table advance of one trip (opaque for the same reason)
-  asm volatile("mov.u32 %0, %1;" : "=r"(rstep_bytes) : "r"(4 * dr2 * (int)sizeof(double2)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(rstep_bytes) : "r"(kRowEntries * dr2 * (int)sizeof(double2)));
   // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
   const double gkfx = lv.grad_k * fx;
   const double scale = lane < 21 ? gkfx * gkfx : lane < 27 ? gkfx * (1.0 / 1020.0) : lane == 27 ? (1.0 / 1020.0) * (1.0 / 1020.0) : 1.0;
@@ -366,6 +372,7 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
     Pose T;
     pose_load(&sh->pose, T);
     K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy;
+    K.xs = K.fxs * T.x; K.ys = K.fys * T.y;
     // S bounds every summand of X', Y', Z' of a pixel inside the depth range.  If it is not an ordinary
     // number (diverged or NaN state, unbounded depth range) the estimate is not used at all.
     const double S = fma(depth_bound, ray_bound, fmax(fmax(fabs(T.x), fabs(T.y)), fabs(T.z)));
@@ -382,16 +389,21 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
       } else {
         const int r = COLFIX ? k : k - cols;
         const double v = tb.ryi[r];
-        tb.row[4 * r + 0] = make_double2(fma(T.R01, v, T.R02), fma(T.R11, v, T.R12));
-        tb.row[4 * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
-        tb.row[4 * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
-        tb.row[4 * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
+        const double e0 = fma(T.R01, v, T.R02), e1 = fma(T.R11, v, T.R12);
+        tb.row[kRowEntries * r + 0] = make_double2(e0, e1);
+        tb.row[kRowEntries * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
+        tb.row[kRowEntries * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
+        tb.row[kRowEntries * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
+        tb.row[kRowEntries * r + 4] = make_double2(K.fxs * e0, K.fys * e1);
       }
     }
     ColRegs mycol;
     mycol.a = make_double2(T.R00 * my_cxi, T.R10 * my_cxi);
     mycol.b = make_double2(T.R20 * my_cxi, -(T.cp * my_cxi));
-    mycol.cxi = my_cxi;
+    mycol.cxix = __dmul_rn(my_cxi, T.x);
+    ColRegsA mycolA;
+    mycolA.as = make_double2(__dmul_rn(K.fxs, mycol.a.x), __dmul_rn(K.fys, mycol.a.y));
+    mycolA.bx = mycol.b.x;
     __syncthreads();
     // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
     // D0 / I0 are read through running pointers WITHOUT bounds guards: the prefetch runs up to
@@ -400,8 +412,8 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
     unsigned long long valid = 0ull;
     {
       int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
-      const double2* rp0 = tb.row + 4 * r0_first;     // COLFIX: the thread's column never changes, the row pointers
-      const double2* rp1 = tb.row + 4 * r1_first;     // advance by a constant (rows past the level are zero padding)
+      const double2* rp0 = tb.row + kRowEntries * r0_first;     // COLFIX: the thread's column never changes, the row pointers
+      const double2* rp1 = tb.row + kRowEntries * r1_first;     // advance by a constant (rows past the level are zero padding)
       const double* pd = L.gD0 + tid;
       const unsigned short* pu = L.gI0 + tid;
       // register prefetch: the loads of the next trip are issued at the top of the current one
@@ -417,15 +429,16 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
         nu0 = ldg_u16(pu + 2 * BT); nu1 = ldg_u16(pu + 3 * BT);
         pd += 2 * BT; pu += 2 * BT;
         const bool in1 = i + BT < n;
-        ColRegs ca0 = mycol, ca1 = mycol;
+        ColRegsA ca0 = mycolA, ca1 = mycolA;
         if (!COLFIX) {
-          ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0];
-          ca1.a = tb.colA[c1]; ca1.b = tb.colB[c1];
-          rp0 = tb.row + 4 * r0; rp1 = tb.row + 4 * r1;
+          const double2 t0 = tb.colA[c0], t1 = tb.colA[c1];
+          ca0.as = make_double2(__dmul_rn(K.fxs, t0.x), __dmul_rn(K.fys, t0.y)); ca0.bx = tb.colB[c0].x;
+          ca1.as = make_double2(__dmul_rn(K.fxs, t1.x), __dmul_rn(K.fys, t1.y)); ca1.bx = tb.colB[c1].x;
+          rp0 = tb.row + kRowEntries * r0; rp1 = tb.row + kRowEntries * r1;
         }
         bool unc0, unc1;
-        WarpA a0 = warp_estimate(K, ca0, rp0[0], rp0[1], c0_, thr, zmin_hi, unc0);
-        WarpA a1 = warp_estimate(K, ca1, rp1[0], rp1[1], c1_, thr, zmin_hi, unc1);
+        WarpA a0 = warp_estimate(K, ca0, rp0[4], rp0[1].x, c0_, thr, zmin_hi, unc0);
+        WarpA a1 = warp_estimate(K, ca1, rp1[4], rp1[1].x, c1_, thr, zmin_hi, unc1);
         const bool dep0 = (min_depth < c0_) & (c0_ < max_depth);                 // strict bounds, AN:279-280
         const bool dep1 = (min_depth < c1_) & (c1_ < max_depth) & in1;
         const bool ex0 = dep0 & unc0, ex1 = dep1 & unc1;
@@ -465,8 +478,8 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
     for (int v = 0; v < 28; ++v) acc[v] = 0.;
     {
       int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
-      const double2* rp0 = tb.row + 4 * r0_first;
-      const double2* rp1 = tb.row + 4 * r1_first;
+      const double2* rp0 = tb.row + kRowEntries * r0_first;
+      const double2* rp1 = tb.row + kRowEntries * r1_first;
       const double* pd = L.gD0 + tid;
       unsigned* pw = L.sWin + tid;
       const unsigned* pg = L.sG + tid;
@@ -482,9 +495,9 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
         const double resa = (double)(wa ? da : 0), resb = (double)(wb ? db : 0);
         ColRegs ca0 = mycol, ca1 = mycol;
         if (!COLFIX) {
-          ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0]; ca0.cxi = MODE == 0 ? tb.cxi[c0] : 0.;
-          ca1.a = tb.colA[c1]; ca1.b = tb.colB[c1]; ca1.cxi = MODE == 0 ? tb.cxi[c1] : 0.;
-          rp0 = tb.row + 4 * r0; rp1 = tb.row + 4 * r1;
+          ca0.a = tb.colA[c0]; ca0.b = tb.colB[c0]; ca0.cxix = MODE == 0 ? __dmul_rn(tb.cxi[c0], K.x) : 0.;   // not contracted: same bits as mycol.cxix
+          ca1.a = tb.colA[c1]; ca1.b = tb.colB[c1]; ca1.cxix = MODE == 0 ? __dmul_rn(tb.cxi[c1], K.x) : 0.;
+          rp0 = tb.row + kRowEntries * r0; rp1 = tb.row + kRowEntries * r1;
         }
         const unsigned vbits = (unsigned)vm;
         double Ja[6], Jb[6];
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     const int pad_rows = table_pad_rows(cols, BT);
     Tables& tb = L.tb;
     tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
-    tb.cx = (double*)(tb.row + 4 * (rows + pad_rows)); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
+    tb.cx = (double*)(tb.row + kRowEntries * (rows + pad_rows)); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
     {
       // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
       const double ox = lv.ox, oy = lv.oy, inv_fx = lv.inv_fx, inv_fy = lv.inv_fy;
@@ -607,7 +620,7 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       for (int k = tid; k < ni; k += BT) i14[k] = __ldg(gI1 + k);
       for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);                 // level + padding: no winners
       for (int k = n + tid; k < nal; k += BT) sG[k] = 0u;                               // padding slots (read, then masked)
-      for (int k = 4 * rows + tid; k < 4 * (rows + pad_rows); k += BT) tb.row[k] = make_double2(0., 0.);
+      for (int k = kRowEntries * rows + tid; k < kRowEntries * (rows + pad_rows); k += BT) tb.row[k] = make_double2(0., 0.);
       for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
       for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
     }
