@@ -278,11 +278,19 @@ __device__ __forceinline__ WarpA warp_estimate(const IterConst& K, const ColRegs
   return w;
 }
 
-// u16 from global memory straight into a 32-bit register (zero-extended by the load): as an
-// `unsigned short` the value travels in half registers and costs a PRMT and a mask per trip.
+// Prefetch loads of the pixel loops.  `asm volatile`: as plain ld.global.nc (__ldg) the compiler
+// treats them as invariant loads and sinks them to their first use one trip later, which turns the
+// register prefetch into a load-use stall of a full L2 round trip per trip.  The u16 goes straight
+// into a 32-bit register (zero-extended by the load): as an `unsigned short` it would travel in half
+// registers and cost a PRMT and a mask per trip.
 __device__ __forceinline__ unsigned ldg_u16(const unsigned short* p) {
   unsigned v;
-  asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
@@ -368,6 +376,12 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
   const int trips = (n - tid + 2 * BT - 1) / (2 * BT);   // loop trips of this thread (0 if tid >= n)
   const double my_cxi = COLFIX ? tb.cxi[c0_first] : 0., my_cx = COLFIX ? tb.cx[c0_first] : 0.;
 
+  // The first trip of both phases reads the same two pixels in every iteration.  Their loads are
+  // issued a whole reduction + solve ahead (before the loop / at the end of phase B) instead of behind
+  // the barrier that opens phase A, where every warp of the CTA would wait out the L2 latency at once.
+  double first_d0 = ldg_f64(L.gD0 + tid), first_d1 = ldg_f64(L.gD0 + tid + BT);
+  unsigned first_u0 = ldg_u16(L.gI0 + tid), first_u1 = ldg_u16(L.gI0 + tid + BT);
+
   for (int it = 0; it < max_iters; ++it) {
     Pose T;
     pose_load(&sh->pose, T);
@@ -417,15 +431,15 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
       const double* pd = L.gD0 + tid;
       const unsigned short* pu = L.gI0 + tid;
       // register prefetch: the loads of the next trip are issued at the top of the current one
-      double p0 = __ldg(pd), p1 = __ldg(pd + BT);
-      unsigned u0 = ldg_u16(pu), u1 = ldg_u16(pu + BT);
+      double p0 = first_d0, p1 = first_d1;
+      unsigned u0 = first_u0, u1 = first_u1;
       unsigned vhi = 0u, vlo = 0u;     // validity bits enter at the top and shift down: bit k of `valid` = pixel k
       unsigned bid = (unsigned)(tid + 1) << 16;   // winner word of pixel i without its I0: (i + 1) << 16
       // one trip: prefetch the next trip's pixels into (n0, n1, nu0, nu1), process (c0_, c1_, cu0, cu1).
       // Two copies of the trip alternate the roles of the two register sets, so nothing is moved.
       auto trip = [&](const double c0_, const double c1_, const unsigned cu0, const unsigned cu1,
                       double& n0, double& n1, unsigned& nu0, unsigned& nu1, const int i) {
-        n0 = __ldg(pd + 2 * BT); n1 = __ldg(pd + 3 * BT);
+        n0 = ldg_f64(pd + 2 * BT); n1 = ldg_f64(pd + 3 * BT);
         nu0 = ldg_u16(pu + 2 * BT); nu1 = ldg_u16(pu + 3 * BT);
         pd += 2 * BT; pu += 2 * BT;
         const bool in1 = i + BT < n;
@@ -460,10 +474,17 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
           c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
         }
       };
+      // An odd trip count is peeled off in front, so that the two copies inside the loop form ONE basic
+      // block: with an exit test between them ptxas sinks the first copy's prefetch below the test,
+      // right in front of its use.
       double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
-      for (int i = tid; i < n; i += 4 * BT) {
+      int i = tid;
+      if (trips & 1) {
         trip(p0, p1, u0, u1, f0, f1, w0, w1, i);
-        if (i + 2 * BT >= n) break;
+        p0 = f0; p1 = f1; u0 = w0; u1 = w1; i += 2 * BT;
+      }
+      for (; i < n; i += 4 * BT) {
+        trip(p0, p1, u0, u1, f0, f1, w0, w1, i);
         trip(f0, f1, w0, w1, p0, p1, u0, u1, i + 2 * BT);
       }
       valid = ((unsigned long long)vhi << 32) | vlo;
@@ -485,9 +506,12 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
       const unsigned* pg = L.sG + tid;
       const unsigned short* pi1 = L.sI1 + tid;
       unsigned long long vm = valid;
-      double p0 = __ldg(pd), p1 = __ldg(pd + BT);
+      double p0 = first_d0, p1 = first_d1;
       auto trip = [&](const double c0_, const double c1_, double& n0, double& n1) {
-        n0 = __ldg(pd + 2 * BT); n1 = __ldg(pd + 3 * BT);
+        n0 = ldg_f64(pd + 2 * BT); n1 = ldg_f64(pd + 3 * BT);
+        // scheduling fence: at the register limit ptxas otherwise sinks the two loads towards their use.
+        // Only the lanes that are here take part (trip counts differ between lanes when n % (2 BT) != 0).
+        __syncwarp(__activemask());
         pd += 2 * BT;
         const unsigned wa = pw[0], wb = pw[BT];
         pw[0] = 0u; pw[BT] = 0u;
@@ -516,12 +540,19 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
         }
       };
       double f0 = 0., f1 = 0.;
-      for (int i = tid; i < n; i += 4 * BT) {
+      int i = tid;
+      if (trips & 1) {
         trip(p0, p1, f0, f1);
-        if (i + 2 * BT >= n) break;
+        p0 = f0; p1 = f1; i += 2 * BT;
+      }
+      for (; i < n; i += 4 * BT) {
+        trip(p0, p1, f0, f1);
         trip(f0, f1, p0, p1);
       }
     }
+    // first trip of the next iteration: in flight during the reduction and the solve
+    first_d0 = ldg_f64(L.gD0 + tid); first_d1 = ldg_f64(L.gD0 + tid + BT);
+    first_u0 = ldg_u16(L.gI0 + tid); first_u1 = ldg_u16(L.gI0 + tid + BT);
     // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
     {
       double x[32];
