@@ -136,6 +136,43 @@ def test_batch_shortcuts_do_not_change_results(phovo, shape, cfg_name):
                 assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"])
 
 
+def test_batch_pixels_near_the_camera_plane(phovo, oracle):
+    """Initial states that put the scene ON the camera plane of the target frame (Z' = d + z crosses
+    zero inside the image): the estimated warp loses its accuracy to cancellation there, the kernel
+    has to notice (|Z'| < zmin) and take the exact path.  First-iteration winner counts and normal
+    equations must equal the oracle's for every pair, whatever happens to the trajectory later."""
+    K = np.array([[130., 0, 79.5], [0, 130., 59.5], [0, 0, 1]])
+    P = 4
+    g0, d0, g1, _ = phovo.synth.make_batch(P, 120, 160, K=K, seed0=700)
+    cfg = phovo.default_config()
+    cfg.num_levels = 2
+    cfg.max_num_iterations[0] = 3
+    cfg.max_num_iterations[1] = 3
+    cfg.min_gradient_norm[0] = cfg.min_gradient_norm[1] = 1e-3
+    cfg.min_depth, cfg.max_depth = 0.05, 20.
+    odo = make_odo(phovo, cfg, K)
+    odo.BatchSetRecordStats(True)
+    valid = d0[d0 > 0]
+    zs = [-float(np.median(valid)), -float(np.percentile(valid, 30)) + 1e-9, -float(valid.min()) - 1e-7, -float(np.percentile(valid, 70))]
+    init = np.zeros((P, 6))
+    for p in range(P):
+        init[p] = [1e-3, -2e-3, zs[p], 2e-3, -1e-3, 1e-3]
+    st, it = odo.BatchAlign(g0, d0, g1, initial_states=init)
+    for p in range(P):
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+        o.set_source(g0[p], d0[p])
+        o.set_target(g1[p])
+        o.set_initial_state(init[p])
+        o.optimize()
+        glog, olog = odo.BatchIterationStats(p), o.iter_stats()
+        assert len(glog) >= 1 and len(olog) >= 1
+        a, b = glog[0], olog[0]
+        assert a["num_valid"] == b["num_valid"], (p, a["num_valid"], b["num_valid"])
+        scale = max(np.max(np.abs(b["H"])), 1e-300)
+        assert np.max(np.abs(a["H"] - b["H"])) <= 1e-9 * scale, p
+        assert np.max(np.abs(a["g"] - b["g"])) <= 1e-9 * max(np.max(np.abs(b["g"])), 1e-300), p
+
+
 def test_batch_unsupported_configurations_fail_loudly(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)
