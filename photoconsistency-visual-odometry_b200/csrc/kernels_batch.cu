@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // K3-batch building blocks
 // ---------------------------------------------------------------------------------------------
-static_assert(kBatchMaxLevelPixels <= 64 * kBatchThreads, "per-thread validity mask is 64 bits");
-static_assert(kBatchSmallLevelPixels <= 64 * kBatchThreadsSmall, "per-thread validity mask is 64 bits");
+static_assert(kBatchMaxLevelPixels <= 60 * kBatchThreads, "per-thread validity mask is 64 bits (phase A fills it four pixels at a time)");
+static_assert(kBatchSmallLevelPixels <= 60 * kBatchThreadsSmall, "per-thread validity mask is 64 bits (phase A fills it four pixels at a time)");
 static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 in 16 bits");
 
 // Everything k_batch_level needs about ITS level, at fixed offsets of the kernel parameter block, so
@@ -198,15 +198,16 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const LevelPa
 //   row    : {R01 ryi + R02, R11 ryi + R12}, {R21 ryi + R22, -(sp sr ryi + sp cr)}, {R22 ryi - R21, R02 ryi - R01}, {R12 ryi - R11, 0},
 //            {fxs (R01 ryi + R02), fys (R11 ryi + R12)}          (entry 0 pre-scaled for the fixed-point estimate of phase A)
 // so that  R p = d * (col + row)  costs 3 adds + 3 multiplies instead of 4 + 9.
-// The row table carries ceil(threads / cols) rows of zero padding: the second pixel of a thread's
-// last trip may lie up to `threads` pixels past the level and is read (and masked) without a guard.
+// The row table carries ceil(3 threads / cols) rows of zero padding: the last pixels of a thread's
+// last (four-pixel) trip of phase A may lie up to 3 `threads` pixels past the level and are read
+// (and masked) without a guard.
 constexpr int kRowEntries = 5;
 struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
   double2* row;                   // [rows + pad][kRowEntries]
 };
-__host__ __device__ inline int table_pad_rows(int cols, int threads) { return (threads + cols - 1) / cols; }
+__host__ __device__ inline int table_pad_rows(int cols, int threads) { return (3 * threads + cols - 1) / cols; }
 __host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
   return 2 * (rows + cols) + 4 * cols + 2 * kRowEntries * (rows + table_pad_rows(cols, threads));
 }
@@ -364,6 +365,7 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
   const int r0_first = tid / cols, c0_first = tid - r0_first * cols;
   const int r1_first = (tid + BT) / cols, c1_first = (tid + BT) - r1_first * cols;
   const int dr2 = (2 * BT) / cols, dc2 = 2 * BT - dr2 * cols;
+  const int dr4 = (4 * BT) / cols, dc4 = 4 * BT - dr4 * cols;
   int rstep_bytes;                                 // row-table advance of one trip (opaque for the same reason)
   asm volatile("mov.u32 %0, %1;" : "=r"(rstep_bytes) : "r"(kRowEntries * dr2 * (int)sizeof(double2)));
   // common factors of the rows phase B accumulates: J = (gk fx) J', r = r_int / 1020
@@ -379,8 +381,9 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
   // The first trip of both phases reads the same two pixels in every iteration.  Their loads are
   // issued a whole reduction + solve ahead (before the loop / at the end of phase B) instead of behind
   // the barrier that opens phase A, where every warp of the CTA would wait out the L2 latency at once.
-  double first_d0 = ldg_f64(L.gD0 + tid), first_d1 = ldg_f64(L.gD0 + tid + BT);
-  unsigned first_u0 = ldg_u16(L.gI0 + tid), first_u1 = ldg_u16(L.gI0 + tid + BT);
+  double first_d[4]; unsigned first_u[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { first_d[j] = ldg_f64(L.gD0 + tid + j * BT); first_u[j] = ldg_u16(L.gI0 + tid + j * BT); }
 
   for (int it = 0; it < max_iters; ++it) {
     Pose T;
@@ -420,75 +423,91 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
     mycolA.bx = mycol.b.x;
     __syncthreads();
     // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
-    // D0 / I0 are read through running pointers WITHOUT bounds guards: the prefetch runs up to
-    // 4 BT pixels past the level, into the rest of the record or the slack behind the store
-    // (kBatchStoreSlackBytes); whatever comes back there is masked by `in1` / the loop bound.
+    // FOUR pixels per trip (i, i + BT, i + 2 BT, i + 3 BT): this phase has registers to spare, and four
+    // independent estimate chains hide more of their own latency than two.  D0 / I0 are read through
+    // running pointers WITHOUT bounds guards: the prefetch runs up to 8 BT pixels past the level, into
+    // the rest of the record or the slack behind the store (kBatchStoreSlackBytes); whatever comes
+    // back there is masked by the in-range tests.
     unsigned long long valid = 0ull;
+    const int quads = (trips + 1) >> 1;          // four-pixel trips of this thread
     {
-      int r0 = r0_first, c0 = c0_first, r1 = r1_first, c1 = c1_first;
-      const double2* rp0 = tb.row + kRowEntries * r0_first;     // COLFIX: the thread's column never changes, the row pointers
-      const double2* rp1 = tb.row + kRowEntries * r1_first;     // advance by a constant (rows past the level are zero padding)
+      int rr[4], cc[4];
+      const double2* rp[4];                       // COLFIX: the thread's column never changes, the row pointers
+#pragma unroll                                    // advance by a constant (rows past the level are zero padding)
+      for (int j = 0; j < 4; ++j) {
+        rr[j] = (tid + j * BT) / cols; cc[j] = (tid + j * BT) - rr[j] * cols;
+        rp[j] = tb.row + kRowEntries * rr[j];
+      }
       const double* pd = L.gD0 + tid;
       const unsigned short* pu = L.gI0 + tid;
       // register prefetch: the loads of the next trip are issued at the top of the current one
-      double p0 = first_d0, p1 = first_d1;
-      unsigned u0 = first_u0, u1 = first_u1;
+      double p[4], f[4]; unsigned u[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { p[j] = first_d[j]; u[j] = first_u[j]; f[j] = 0.; w[j] = 0u; }
       unsigned vhi = 0u, vlo = 0u;     // validity bits enter at the top and shift down: bit k of `valid` = pixel k
       unsigned bid = (unsigned)(tid + 1) << 16;   // winner word of pixel i without its I0: (i + 1) << 16
-      // one trip: prefetch the next trip's pixels into (n0, n1, nu0, nu1), process (c0_, c1_, cu0, cu1).
-      // Two copies of the trip alternate the roles of the two register sets, so nothing is moved.
-      auto trip = [&](const double c0_, const double c1_, const unsigned cu0, const unsigned cu1,
-                      double& n0, double& n1, unsigned& nu0, unsigned& nu1, const int i) {
-        n0 = ldg_f64(pd + 2 * BT); n1 = ldg_f64(pd + 3 * BT);
-        nu0 = ldg_u16(pu + 2 * BT); nu1 = ldg_u16(pu + 3 * BT);
-        pd += 2 * BT; pu += 2 * BT;
-        const bool in1 = i + BT < n;
-        ColRegsA ca0 = mycolA, ca1 = mycolA;
-        if (!COLFIX) {
-          const double2 t0 = tb.colA[c0], t1 = tb.colA[c1];
-          ca0.as = make_double2(__dmul_rn(K.fxs, t0.x), __dmul_rn(K.fys, t0.y)); ca0.bx = tb.colB[c0].x;
-          ca1.as = make_double2(__dmul_rn(K.fxs, t1.x), __dmul_rn(K.fys, t1.y)); ca1.bx = tb.colB[c1].x;
-          rp0 = tb.row + kRowEntries * r0; rp1 = tb.row + kRowEntries * r1;
+      // one trip: prefetch the next trip's pixels into (nd, nu), process (cd, cu).  Two copies of the
+      // trip alternate the roles of the two register sets, so nothing is moved.
+      auto trip = [&](const double (&cd)[4], const unsigned (&cu)[4], double (&nd)[4], unsigned (&nu)[4], const int i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { nd[j] = ldg_f64(pd + (4 + j) * BT); nu[j] = ldg_u16(pu + (4 + j) * BT); }
+        pd += 4 * BT; pu += 4 * BT;
+        WarpA a[4]; bool dep[4], ex[4];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ColRegsA ca = mycolA;
+          if (!COLFIX) {
+            const double2 t = tb.colA[cc[j]];
+            ca.as = make_double2(__dmul_rn(K.fxs, t.x), __dmul_rn(K.fys, t.y)); ca.bx = tb.colB[cc[j]].x;
+            rp[j] = tb.row + kRowEntries * rr[j];
+          }
+          bool unc;
+          a[j] = warp_estimate(K, ca, rp[j][4], rp[j][1].x, cd[j], thr, zmin_hi, unc);
+          dep[j] = (min_depth < cd[j]) & (cd[j] < max_depth) & (j == 0 || i + j * BT < n);   // strict bounds, AN:279-280
+          ex[j] = dep[j] & unc;
+          any |= ex[j];
         }
-        bool unc0, unc1;
-        WarpA a0 = warp_estimate(K, ca0, rp0[4], rp0[1].x, c0_, thr, zmin_hi, unc0);
-        WarpA a1 = warp_estimate(K, ca1, rp1[4], rp1[1].x, c1_, thr, zmin_hi, unc1);
-        const bool dep0 = (min_depth < c0_) & (c0_ < max_depth);                 // strict bounds, AN:279-280
-        const bool dep1 = (min_depth < c1_) & (c1_ < max_depth) & in1;
-        const bool ex0 = dep0 & unc0, ex1 = dep1 & unc1;
-        if (ex0 | ex1) {                                                       // rare: ~2e-4 of the pixels
-          const int q0 = COLFIX ? i / cols : r0, q1 = COLFIX ? (i + BT) / cols : r1;
-          if (ex0) a0 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c0], tb.ry[q0], c0_, fx, fy, ox, oy, inv_fx, inv_fy);
-          if (ex1) a1 = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[c1], tb.ry[q1], c1_, fx, fy, ox, oy, inv_fx, inv_fy);
+        if (any) {                                                             // rare: ~2e-4 of the pixels
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ex[j]) {
+              const int q = COLFIX ? (i + j * BT) / cols : rr[j];
+              a[j] = warp_exact(&sh->pose, COLFIX ? my_cx : tb.cx[cc[j]], tb.ry[q], cd[j], fx, fy, ox, oy, inv_fx, inv_fy);
+            }
         }
-        const bool ok0 = ((unsigned)a0.tj < (unsigned)cols) & ((unsigned)a0.ti < (unsigned)rows) & dep0;
-        const bool ok1 = ((unsigned)a1.tj < (unsigned)cols) & ((unsigned)a1.ti < (unsigned)rows) & dep1;
-        smem_red_max(ok0 ? L.sWinAddr + 4u * (unsigned)(a0.ti * cols + a0.tj) : dummy, bid + cu0);
-        smem_red_max(ok1 ? L.sWinAddr + 4u * (unsigned)(a1.ti * cols + a1.tj) : dummy, bid + ((unsigned)BT << 16) + cu1);
-        bid += (unsigned)(2 * BT) << 16;
-        vlo = __funnelshift_r(vlo, vhi, 2);
-        vhi = (vhi >> 2) | ((unsigned)ok0 << 30) | ((unsigned)ok1 << 31);
-        if (COLFIX) { rp0 = (const double2*)((const char*)rp0 + rstep_bytes); rp1 = (const double2*)((const char*)rp1 + rstep_bytes); }
-        else {
-          c0 += dc2; r0 += dr2; if (c0 >= cols) { c0 -= cols; ++r0; }
-          c1 += dc2; r1 += dr2; if (c1 >= cols) { c1 -= cols; ++r1; }
+        unsigned bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = ((unsigned)a[j].tj < (unsigned)cols) & ((unsigned)a[j].ti < (unsigned)rows) & dep[j];
+          smem_red_max(ok ? L.sWinAddr + 4u * (unsigned)(a[j].ti * cols + a[j].tj) : dummy, bid + ((unsigned)(j * BT) << 16) + cu[j]);
+          bits |= (unsigned)ok << (28 + j);
+        }
+        bid += (unsigned)(4 * BT) << 16;
+        vlo = __funnelshift_r(vlo, vhi, 4);
+        vhi = (vhi >> 4) | bits;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (COLFIX) rp[j] = (const double2*)((const char*)rp[j] + 2 * rstep_bytes);
+          else { cc[j] += dc4; rr[j] += dr4; if (cc[j] >= cols) { cc[j] -= cols; ++rr[j]; } }
         }
       };
       // An odd trip count is peeled off in front, so that the two copies inside the loop form ONE basic
       // block: with an exit test between them ptxas sinks the first copy's prefetch below the test,
       // right in front of its use.
-      double f0 = 0., f1 = 0.; unsigned w0 = 0u, w1 = 0u;
       int i = tid;
-      if (trips & 1) {
-        trip(p0, p1, u0, u1, f0, f1, w0, w1, i);
-        p0 = f0; p1 = f1; u0 = w0; u1 = w1; i += 2 * BT;
+      if (quads & 1) {
+        trip(p, u, f, w, i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { p[j] = f[j]; u[j] = w[j]; }
+        i += 4 * BT;
       }
-      for (; i < n; i += 4 * BT) {
-        trip(p0, p1, u0, u1, f0, f1, w0, w1, i);
-        trip(f0, f1, w0, w1, p0, p1, u0, u1, i + 2 * BT);
+      for (; i < n; i += 8 * BT) {
+        trip(p, u, f, w, i);
+        trip(f, w, p, u, i + 4 * BT);
       }
       valid = ((unsigned long long)vhi << 32) | vlo;
-      valid = trips > 0 ? valid >> (64 - 2 * trips) : 0ull;
+      valid = quads > 0 ? valid >> (64 - 4 * quads) : 0ull;
     }
     __syncthreads();
     // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
@@ -506,7 +525,7 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
       const unsigned* pg = L.sG + tid;
       const unsigned short* pi1 = L.sI1 + tid;
       unsigned long long vm = valid;
-      double p0 = first_d0, p1 = first_d1;
+      double p0 = first_d[0], p1 = first_d[1];
       auto trip = [&](const double c0_, const double c1_, double& n0, double& n1) {
         n0 = ldg_f64(pd + 2 * BT); n1 = ldg_f64(pd + 3 * BT);
         // scheduling fence: at the register limit ptxas otherwise sinks the two loads towards their use.
@@ -551,8 +570,8 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
       }
     }
     // first trip of the next iteration: in flight during the reduction and the solve
-    first_d0 = ldg_f64(L.gD0 + tid); first_d1 = ldg_f64(L.gD0 + tid + BT);
-    first_u0 = ldg_u16(L.gI0 + tid); first_u1 = ldg_u16(L.gI0 + tid + BT);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { first_d[j] = ldg_f64(L.gD0 + tid + j * BT); first_u[j] = ldg_u16(L.gI0 + tid + j * BT); }
     // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
     {
       double x[32];

@@ -15,9 +15,9 @@ constexpr int kBatchSmallLevelPixels = 6400; // largest level that runs 3 CTAs p
 constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + tables + scratch must fit 227 KB (checked exactly
                                             // by the host); also <= 64 * kBatchThreads (validity mask) and < 65535
 
-// The level kernel prefetches D0 / I0 up to 4 * kBatchThreads pixels past the end of a level without
+// The level kernel prefetches D0 / I0 up to 8 * kBatchThreads pixels past the end of a level without
 // bounds guards (the values are masked); the allocation behind the last record must cover that.
-constexpr size_t kBatchStoreSlackBytes = 4 * (size_t)kBatchThreads * sizeof(double) + 1024;
+constexpr size_t kBatchStoreSlackBytes = 8 * (size_t)kBatchThreads * sizeof(double) + 1024;
 
 // Everything the two batch kernels need, passed by value (__grid_constant__).
 struct BatchParams {
