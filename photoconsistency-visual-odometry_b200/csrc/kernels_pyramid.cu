@@ -49,17 +49,11 @@ __device__ __forceinline__ void linear_axis(int d, double scale, int ssize, bool
 // 2x2 of the pixel's 2^level cell with weights 1/2 (horizontal pair first, then vertical) --
 // cv::resize INTER_LINEAR from the ORIGINAL image, AN:132.  A warp reads one contiguous span of
 // each of two source rows, so every 32-byte sector fetched is used by the warp.
+// value of level pixel (y, x): the conversion of the source pixel at level 0, else cv::resize's four taps
 template <typename T>
-__global__ void __launch_bounds__(256) k_build_level(const void* __restrict__ src, size_t step, double src_scale,
-                                                     int rows, int cols, int level, double scale,
-                                                     double* __restrict__ dst, int orows, int ocols) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= ocols || y >= orows) return;
-  if (level == 0) {
-    dst[(size_t)y * ocols + x] = load_src<T>(src, step, y, x, src_scale);
-    return;
-  }
+__device__ __forceinline__ double level_value(const void* __restrict__ src, size_t step, double src_scale,
+                                              int rows, int cols, int level, double scale, int y, int x) {
+  if (level == 0) return load_src<T>(src, step, y, x, src_scale);
   int sx, sy; float fx, fy;
   linear_axis(x, scale, cols, true, sx, fx);
   linear_axis(y, scale, rows, false, sy, fy);
@@ -74,7 +68,59 @@ __global__ void __launch_bounds__(256) k_build_level(const void* __restrict__ sr
     r1 = load_src<T>(src, step, y1, sx, src_scale);
   }
   const double b0 = (double)(1.f - fy), b1 = (double)fy;
-  dst[(size_t)y * ocols + x] = __dadd_rn(__dmul_rn(r0, b0), __dmul_rn(r1, b1));
+  return __dadd_rn(__dmul_rn(r0, b0), __dmul_rn(r1, b1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_build_level(const void* __restrict__ src, size_t step, double src_scale,
+                                                     int rows, int cols, int level, double scale,
+                                                     double* __restrict__ dst, int orows, int ocols) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ocols || y >= orows) return;
+  dst[(size_t)y * ocols + x] = level_value<T>(src, step, src_scale, rows, cols, level, scale, y, x);
+}
+
+// K1+K2 fused over ALL active levels of one frame: one thread per level pixel (levels laid end to end
+// in the thread index).  Every level is resized from the ORIGINAL image (AN:132), so the levels do not
+// depend on each other; with GRAD the thread also evaluates its eight level neighbours (the same
+// four-tap function, so the same bits as the stored image; the taps come from L1/L2) and applies
+// cv::Scharr's arithmetic (AN:181-187) -- one launch instead of two per level, which is what a
+// VO frame's set-up time consists of.
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) k_build_levels(const void* __restrict__ src, size_t step, double src_scale,
+                                                      int rows, int cols, const __grid_constant__ PyramidLevels P) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= P.px_offset[P.num]) return;
+  int a = 0;
+  while (j >= P.px_offset[a + 1]) ++a;
+  const int q = j - P.px_offset[a];
+  const int oc = P.ocols[a], orr = P.orows[a], level = P.level[a];
+  const int y = q / oc, x = q - y * oc;
+  const double scale = (double)(1 << level);
+  if (!GRAD) {
+    P.dst[a][q] = level_value<T>(src, step, src_scale, rows, cols, level, scale, y, x);
+    return;
+  }
+  const int ym = reflect101(y - 1, orr), yp = reflect101(y + 1, orr), xm = reflect101(x - 1, oc), xp = reflect101(x + 1, oc);
+  double t[3][3];
+  const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) t[dy][dx] = level_value<T>(src, step, src_scale, rows, cols, level, scale, ys[dy], xs[dx]);
+  const double ks0 = P.ks0[a], ks1 = P.ks1[a];
+  // dx: row filter [-1 0 1] on three rows, then column filter centre-first
+  const double dm = __dsub_rn(t[0][2], t[0][0]);
+  const double d0 = __dsub_rn(t[1][2], t[1][0]);
+  const double dp = __dsub_rn(t[2][2], t[2][0]);
+  const double gx = __dadd_rn(__dmul_rn(ks1, d0), __dmul_rn(ks0, __dadd_rn(dp, dm)));
+  // dy: row filter [3 10 3]*scale left-to-right on rows y-1 and y+1, then column [-1 0 1]
+  const double sm = __dadd_rn(__dadd_rn(__dmul_rn(ks0, t[0][0]), __dmul_rn(ks1, t[0][1])), __dmul_rn(ks0, t[0][2]));
+  const double sp = __dadd_rn(__dadd_rn(__dmul_rn(ks0, t[2][0]), __dmul_rn(ks1, t[2][1])), __dmul_rn(ks0, t[2][2]));
+  P.dst[a][q] = t[1][1];
+  P.gx[a][q] = gx;
+  P.gy[a][q] = __dsub_rn(sp, sm);
 }
 
 struct GaussTaps { double k[32]; int n; };
@@ -149,6 +195,24 @@ int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_
     case SRC_F32: k_build_level<float><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
     default:      k_build_level<double><<<grid, block, 0, stream>>>(src, step, src_scale, rows, cols, level, scale, dst, orows, ocols); break;
   }
+  return 1;
+}
+
+int launch_build_levels(cudaStream_t stream, const void* src, int src_type, size_t step, double src_scale,
+                        int rows, int cols, const PyramidLevels& P, bool gradients) {
+  const int total = P.px_offset[P.num];
+  if (total <= 0) return 0;
+  const int grid = (total + 255) / 256;
+#define PHOVO_BUILD_LEVELS(T)                                                                                   \
+  if (gradients) k_build_levels<T, true><<<grid, 256, 0, stream>>>(src, step, src_scale, rows, cols, P);        \
+  else k_build_levels<T, false><<<grid, 256, 0, stream>>>(src, step, src_scale, rows, cols, P)
+  switch (src_type) {
+    case SRC_U8:  PHOVO_BUILD_LEVELS(uint8_t); break;
+    case SRC_U16: PHOVO_BUILD_LEVELS(uint16_t); break;
+    case SRC_F32: PHOVO_BUILD_LEVELS(float); break;
+    default:      PHOVO_BUILD_LEVELS(double); break;
+  }
+#undef PHOVO_BUILD_LEVELS
   return 1;
 }
 

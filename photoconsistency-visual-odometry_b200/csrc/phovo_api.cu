@@ -184,8 +184,35 @@ static int src_type_of_depth(int depth_type) {
 }
 static size_t depth_elt(int depth_type) { return depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2; }
 
+// the active levels of the current size as a PyramidLevels block; false if one of them is blurred
+// (the fused kernel has no blur stage: those configurations take the per-level launches)
+static bool fused_levels(const phovo_ctx* ctx, PyramidLevels* P) {
+  memset(P, 0, sizeof(*P));
+  for (int l = 0; l < ctx->cfg.num_levels; ++l) {
+    if (!ctx->level_active(l)) continue;
+    if (ctx->cfg.blur_filter_size[l] > 1) return false;
+    const int a = P->num++;
+    P->level[a] = l; P->orows[a] = ctx->lrows[l]; P->ocols[a] = ctx->lcols[l];
+    P->px_offset[a + 1] = P->px_offset[a] + ctx->lrows[l] * ctx->lcols[l];
+    const double s = ctx->cfg.grad_scale[l];
+    P->ks0[a] = s != 1. ? 3. * s : 3.; P->ks1[a] = s != 1. ? 10. * s : 10.;   // launch_scharr_store's kernel
+  }
+  return true;
+}
+
 // intensity pyramid (+ gradients for the target) of one frame; AN:471-474 / AN:484-490
 static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bool target) {
+  PyramidLevels P;
+  if (fused_levels(ctx, &P)) {
+    for (int a = 0; a < P.num; ++a) {
+      const int l = P.level[a];
+      P.dst[a] = target ? ctx->I1[l] : ctx->I0[l];
+      P.gx[a] = target ? ctx->Gx[l] : nullptr; P.gy[a] = target ? ctx->Gy[l] : nullptr;
+    }
+    ctx->launches += launch_build_levels(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, P, target);
+    CK(cudaGetLastError());
+    return PHOVO_OK;
+  }
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
     const int r = ctx->lrows[l], c = ctx->lcols[l];
@@ -203,11 +230,16 @@ static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bo
 }
 
 static int build_depth(phovo_ctx* ctx, const void* dev_depth, int depth_type, size_t step, double depth_scale) {
+  PyramidLevels P;   // the depth pyramid is never blurred (AN:471-476): every active level in one launch
+  memset(&P, 0, sizeof(P));
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
-    const int r = ctx->lrows[l], c = ctx->lcols[l];
-    ctx->launches += launch_build_level(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, l, ctx->D0[l], r, c);
+    const int a = P.num++;
+    P.level[a] = l; P.orows[a] = ctx->lrows[l]; P.ocols[a] = ctx->lcols[l];
+    P.px_offset[a + 1] = P.px_offset[a] + ctx->lrows[l] * ctx->lcols[l];
+    P.dst[a] = ctx->D0[l];
   }
+  ctx->launches += launch_build_levels(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, P, false);
   CK(cudaGetLastError());
   return PHOVO_OK;
 }
@@ -663,7 +695,8 @@ static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
     if (M <= 0) continue;
     const LevelParams L = ctx->level_params(level);
     const LevelPtrs P = ctx->level_ptrs(level);
-    ctx->launches += launch_begin_level(ctx->stream, ctx->d_pose, M);
+    // (no k_begin_level: the persistent kernel keeps iteration / done in registers and shared memory
+    // and writes the whole PoseDev back when the level ends)
     int grid = 0; cudaError_t e = cudaSuccess;
     const int rc = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, ctx->sm_count, &grid, &e);
     if (rc < 0) {

@@ -19,6 +19,20 @@ enum SrcType { SRC_U8 = 0, SRC_F64 = 1, SRC_F32 = 2, SRC_U16 = 3 };
 // (u8 * 1/255, AN:471; u16 * depth_scale).  Output fp64 scratch (orows x ocols, dense).
 int launch_build_level(cudaStream_t stream, const void* src, int src_type, size_t src_step_bytes,
                        double src_scale, int rows, int cols, int level, double* dst, int orows, int ocols);
+// K1 (+K2) for every active level of a frame in ONE launch: `dst` (and, with `gradients`, the Scharr
+// images `gx`, `gy` with the kernel scaled by grad_scale: ks0 = 3 s, ks1 = 10 s) of each listed level.
+// Same arithmetic as launch_build_level + launch_scharr_store, bit for bit; not for blurred levels.
+struct PyramidLevels {
+  int num;                                  // levels listed
+  int level[PHOVO_MAX_LEVELS];              // pyramid level index
+  int orows[PHOVO_MAX_LEVELS], ocols[PHOVO_MAX_LEVELS];
+  int px_offset[PHOVO_MAX_LEVELS + 1];      // prefix sum of orows * ocols
+  double* dst[PHOVO_MAX_LEVELS];
+  double* gx[PHOVO_MAX_LEVELS]; double* gy[PHOVO_MAX_LEVELS];
+  double ks0[PHOVO_MAX_LEVELS], ks1[PHOVO_MAX_LEVELS];
+};
+int launch_build_levels(cudaStream_t stream, const void* src, int src_type, size_t src_step_bytes, double src_scale,
+                        int rows, int cols, const PyramidLevels& P, bool gradients);
 // K2b: cv::GaussianBlur(k x k, sigma) applied once, BORDER_REFLECT_101, fp64 in place via `tmp`.
 int launch_gaussian_blur(cudaStream_t stream, double* img, double* tmp, int rows, int cols, int ksize, double sigma);
 // dst = src * alpha (Mat::convertTo with a scale), and gain[0] = mean(a) / mean(b) in a fixed summation order
