@@ -435,15 +435,26 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
   for (; it < L.max_iters; ++it) {
     Pose T;
     pose_load(&s_pose, T);
-    // ---- phase A: winner map + validity (exact reference arithmetic) ----
+    // ---- phase A: winner map + validity.  Estimate-then-verify (phovo_device.cuh): the exact
+    // reference arithmetic runs only for the pixels whose estimate lies next to a rounding boundary
+    // (~2e-4 of them); the graph / stream drivers (k_winner) run it for every pixel ----
+    const EstimateConst E = estimate_const(L, T);
     for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
       const double d = __ldg(P.D0 + i);
       const int r = i / L.cols, c = i - r * L.cols;
-      Warped w;
-      const bool ok = warp_pixel<false>(L, T, r, c, d, w);
+      const bool dep = (L.min_depth < d) & (d < L.max_depth);                  // strict bounds, AN:279-280
+      int tj, ti;
+      const bool unc = estimate_target(L, T, E, r, c, d, tj, ti);
+      bool ok = dep & ((unsigned)tj < (unsigned)L.cols) & ((unsigned)ti < (unsigned)L.rows);
+      int t = L.cols * ti + tj;
+      if (dep & unc) {
+        Warped w;
+        ok = warp_pixel<false>(L, T, r, c, d, w);
+        t = w.t;
+      }
       if (MODE == 3) {   // photometric + depth solver: two residual slots per pixel, keys 2i+1 / 2i+2 (see k_winner_bi)
-        if (ok) { atomicMax(P.winner + w.t, 2 * i + 1); atomicMax(P.winner + 2 * w.t, 2 * i + 2); }
-      } else if (ok) atomicMax(P.winner + w.t, i);
+        if (ok) { atomicMax(P.winner + t, 2 * i + 1); atomicMax(P.winner + 2 * t, 2 * i + 2); }
+      } else if (ok) atomicMax(P.winner + t, i);
       P.valid[i] = ok;
     }
     grid.sync();

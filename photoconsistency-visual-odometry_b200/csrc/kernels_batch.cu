@@ -108,7 +108,7 @@ static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 
 // Everything k_batch_level needs about ITS level, at fixed offsets of the kernel parameter block, so
 // that every field is a constant-bank operand (indexing BatchParams' per-level arrays with a
 // run-time level costs a load and a register per use, inside the pixel loops).
-struct LevelParams {
+struct BatchLevelParams {
   int num_pairs, rows, cols, n;
   int level, max_iters, first, log_cap;          // first: coarsest active level (starts from the caller's state)
   int exact_always, force_generic;
@@ -118,8 +118,8 @@ struct LevelParams {
   double min_depth, max_depth;
 };
 
-static LevelParams level_params(const BatchParams& bp, int a) {
-  LevelParams lv;
+static BatchLevelParams level_params(const BatchParams& bp, int a) {
+  BatchLevelParams lv;
   lv.num_pairs = bp.num_pairs; lv.rows = bp.lrows[a]; lv.cols = bp.lcols[a]; lv.n = lv.rows * lv.cols;
   lv.level = bp.level[a]; lv.max_iters = bp.max_iters[a]; lv.first = a == 0; lv.log_cap = bp.log_cap;
   lv.exact_always = bp.exact_always; lv.force_generic = bp.force_generic;
@@ -147,7 +147,7 @@ struct BatchShared {
 // with one correctly rounded reciprocal per pivot.  No shuffles on the critical path: a serial
 // chain of ~50 dependent fp64 operations instead of ~100 shuffle round trips.  Then state update,
 // sincos on three lanes, rotation, termination flag.  Lane 0 publishes.
-__device__ __forceinline__ void warp_gn_step(double tot, int lane, const LevelParams& lv, int it, int pair,
+__device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchLevelParams& lv, int it, int pair,
                                              BatchShared* sh, phovo_iter_stats* log) {
   const unsigned FULL = 0xffffffffu;
   sh->totals[lane] = tot;
@@ -250,8 +250,6 @@ struct IterConst {          // per-iteration scalars besides the tables
 struct ColRegs { double2 a, b; double cxix; };   // column entries of the tables for one pixel; cxix = cxi * x (MODE 0 only)
 struct ColRegsA { double2 as; double bx; };      // phase A: {fxs R00 cxi, fys R10 cxi}, R20 cxi
 
-constexpr int kFracBits = 14;                 // fixed-point fraction bits of the estimated target coordinate
-constexpr unsigned kFracOne = 1u << kFracBits;
 
 // Phase A of one pixel, fast path.  Estimates the warped coordinate from the per-iteration tables as
 // floor((t + 0.5) 2^14) in a 32-bit integer.  If the 14-bit fraction is neither 0 nor 2^14 - 1 the
@@ -344,7 +342,7 @@ struct LevelCtx {
 // of the tables live in registers and only the row advances.  The thread -> pixel mapping is the
 // same linear one in both variants, so results are bitwise identical.
 template <int MODE, bool COLFIX, int BT>
-__device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
+__device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
   constexpr int NW = BT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rows = lv.rows, cols = lv.cols, n = lv.n;
@@ -610,7 +608,7 @@ __device__ __forceinline__ void gn_level(const LevelParams& lv, const LevelCtx& 
 // stays in a 64-bit register mask between the two phases of an iteration.  The thread -> pixel
 // mapping is a pure function of the level size, so results do not depend on grid, batch or GPU.
 template <int MODE, int BT, int MINB>
-__global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ LevelParams lv,
+__global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ BatchLevelParams lv,
                                                           const uint8_t* __restrict__ store,
                                                           const double* __restrict__ init_states, double* __restrict__ states,
                                                           int32_t* __restrict__ iters, phovo_iter_stats* __restrict__ log,
@@ -746,7 +744,7 @@ int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count,
   int launches = 0;
   for (int a = 0; a < bp.num_active; ++a) {
     const int rows = bp.lrows[a], cols = bp.lcols[a];
-    const LevelParams lv = level_params(bp, a);
+    const BatchLevelParams lv = level_params(bp, a);
     const size_t smem = batch_level_smem_bytes(rows, cols);
     const bool fixed = bp.mode == PHOVO_MODE_ANALYTIC_FIXED;
     if (batch_level_is_small(rows, cols)) {

@@ -209,7 +209,14 @@ static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bo
       P.dst[a] = target ? ctx->I1[l] : ctx->I0[l];
       P.gx[a] = target ? ctx->Gx[l] : nullptr; P.gy[a] = target ? ctx->Gy[l] : nullptr;
     }
-    ctx->launches += launch_build_levels(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, P, target);
+    // The fused gradient evaluates nine level pixels per thread (36 taps through L1): a win while
+    // launch latency dominates (a 640x480 frame), a loss on big frames (8K: 0.92 vs 0.58 ms), where
+    // the tiled shared-memory Scharr of each level follows the single build launch instead.
+    const bool fuse_gradients = target && P.px_offset[P.num] <= (1 << 20);
+    ctx->launches += launch_build_levels(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, P, fuse_gradients);
+    if (target && !fuse_gradients)
+      for (int a = 0; a < P.num; ++a)
+        ctx->launches += launch_scharr_store(ctx->stream, P.dst[a], P.orows[a], P.ocols[a], ctx->cfg.grad_scale[P.level[a]], P.gx[a], P.gy[a]);
     CK(cudaGetLastError());
     return PHOVO_OK;
   }
