@@ -185,7 +185,9 @@ static int src_type_of_depth(int depth_type) {
 static size_t depth_elt(int depth_type) { return depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2; }
 
 // the active levels of the current size as a PyramidLevels block; false if one of them is blurred
-// (the fused kernel has no blur stage: those configurations take the per-level launches)
+// (the fused kernel has no blur stage) or if the frame is big: one launch for all levels wins while
+// launch latency dominates (640x480: set-up 0.18 -> 0.10 ms); on an 8K frame the per-level launches
+// with 2-D tiles and the shared-memory Scharr are faster (0.58 vs 0.77-0.92 ms)
 static bool fused_levels(const phovo_ctx* ctx, PyramidLevels* P) {
   memset(P, 0, sizeof(*P));
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
@@ -197,7 +199,7 @@ static bool fused_levels(const phovo_ctx* ctx, PyramidLevels* P) {
     const double s = ctx->cfg.grad_scale[l];
     P->ks0[a] = s != 1. ? 3. * s : 3.; P->ks1[a] = s != 1. ? 10. * s : 10.;   // launch_scharr_store's kernel
   }
-  return true;
+  return P->px_offset[P->num] <= (1 << 20);
 }
 
 // intensity pyramid (+ gradients for the target) of one frame; AN:471-474 / AN:484-490
@@ -209,14 +211,7 @@ static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bo
       P.dst[a] = target ? ctx->I1[l] : ctx->I0[l];
       P.gx[a] = target ? ctx->Gx[l] : nullptr; P.gy[a] = target ? ctx->Gy[l] : nullptr;
     }
-    // The fused gradient evaluates nine level pixels per thread (36 taps through L1): a win while
-    // launch latency dominates (a 640x480 frame), a loss on big frames (8K: 0.92 vs 0.58 ms), where
-    // the tiled shared-memory Scharr of each level follows the single build launch instead.
-    const bool fuse_gradients = target && P.px_offset[P.num] <= (1 << 20);
-    ctx->launches += launch_build_levels(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, P, fuse_gradients);
-    if (target && !fuse_gradients)
-      for (int a = 0; a < P.num; ++a)
-        ctx->launches += launch_scharr_store(ctx->stream, P.dst[a], P.orows[a], P.ocols[a], ctx->cfg.grad_scale[P.level[a]], P.gx[a], P.gy[a]);
+    ctx->launches += launch_build_levels(ctx->stream, dev_gray, SRC_U8, step, 1. / 255, ctx->rows, ctx->cols, P, target);
     CK(cudaGetLastError());
     return PHOVO_OK;
   }
@@ -237,7 +232,7 @@ static int build_intensity(phovo_ctx* ctx, const void* dev_gray, size_t step, bo
 }
 
 static int build_depth(phovo_ctx* ctx, const void* dev_depth, int depth_type, size_t step, double depth_scale) {
-  PyramidLevels P;   // the depth pyramid is never blurred (AN:471-476): every active level in one launch
+  PyramidLevels P;   // the depth pyramid is never blurred (AN:471-476)
   memset(&P, 0, sizeof(P));
   for (int l = 0; l < ctx->cfg.num_levels; ++l) {
     if (!ctx->level_active(l)) continue;
@@ -246,7 +241,13 @@ static int build_depth(phovo_ctx* ctx, const void* dev_depth, int depth_type, si
     P.px_offset[a + 1] = P.px_offset[a] + ctx->lrows[l] * ctx->lcols[l];
     P.dst[a] = ctx->D0[l];
   }
-  ctx->launches += launch_build_levels(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, P, false);
+  if (P.px_offset[P.num] <= (1 << 20)) {   // small frame: every active level in one launch (see fused_levels)
+    ctx->launches += launch_build_levels(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols, P, false);
+  } else {
+    for (int a = 0; a < P.num; ++a)
+      ctx->launches += launch_build_level(ctx->stream, dev_depth, src_type_of_depth(depth_type), step, depth_scale, ctx->rows, ctx->cols,
+                                          P.level[a], P.dst[a], P.orows[a], P.ocols[a]);
+  }
   CK(cudaGetLastError());
   return PHOVO_OK;
 }

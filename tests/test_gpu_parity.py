@@ -57,9 +57,10 @@ def test_library_loaded_is_the_in_tree_cuda_build(phovo):
     assert b"sm_100a" in phovo.capi.lib().phovo_version()
 
 
-@pytest.mark.parametrize("shape,levels", [((480, 640), 4), ((135, 241), 3)])
+@pytest.mark.parametrize("shape,levels", [((480, 640), 4), ((135, 241), 3), ((900, 1200), 3)])
 def test_pyramid_and_gradient_images(phovo, oracle, shape, levels):
-    """K1/K2 vs AN:115-189: every level of I0, D0, I1, Gx, Gy."""
+    """K1/K2 vs AN:115-189: every level of I0, D0, I1, Gx, Gy.  The two small frames take the fused
+    one-launch-per-frame kernel, the 900x1200 one (> 1 Mpx of levels) the per-level launches."""
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_pair(shape[0], shape[1], K=K, seed=3)
     cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
