@@ -386,6 +386,18 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
   for (int it = 0; it < max_iters; ++it) {
     Pose T;
     pose_load(&sh->pose, T);
+    // A state that is not finite (a singular solve upstream: tiny or textureless levels) makes every
+    // pixel invalid in the reference, whose Jacobian rows then stay zero: H = 0, g = 0, and the level
+    // stops as soon as 0 < min_gradient_norm.  Here invalid rows are "finite table entry times zero",
+    // so the tables are built from the identity pose instead (warp_exact still reads the real one and
+    // rejects every pixel).
+    const bool finite_pose = isfinite(T.x + T.y + T.z + T.R00 + T.R01 + T.R02 + T.R10 + T.R11 + T.R12 + T.R20 + T.R21 + T.R22 +
+                                      T.sy + T.cy + T.sp + T.cp + T.sr + T.cr);
+    if (!finite_pose) {
+      T.x = T.y = T.z = 0.;
+      T.R00 = T.R11 = T.R22 = 1.; T.R01 = T.R02 = T.R10 = T.R12 = T.R20 = T.R21 = 0.;
+      T.sy = T.sp = T.sr = 0.; T.cy = T.cp = T.cr = 1.;
+    }
     K.x = T.x; K.y = T.y; K.z = T.z; K.cy = T.cy; K.sy = T.sy;
     K.xs = K.fxs * T.x; K.ys = K.fys * T.y;
     // S bounds every summand of X', Y', Z' of a pixel inside the depth range.  If it is not an ordinary
@@ -393,7 +405,7 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     const double S = fma(depth_bound, ray_bound, fmax(fmax(fabs(T.x), fabs(T.y)), fabs(T.z)));
     const double zmin = fmax(S * zmin_geo, 0x1p-500);
     const bool ordinary = (S < 0x1p500) & (zmin_geo < 0x1p100) & (T.x == T.x) & (T.y == T.y) & (T.z == T.z);
-    const unsigned thr = ordinary ? unc_thr : 0u;
+    const unsigned thr = (ordinary & finite_pose) ? unc_thr : 0u;
     const unsigned zmin_hi = (unsigned)__double2hiint(zmin) + 1u;
     // ---- per-iteration tables ----
     for (int k = tid; k < (COLFIX ? 0 : cols) + rows; k += BT) {

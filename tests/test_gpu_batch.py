@@ -173,6 +173,31 @@ def test_batch_pixels_near_the_camera_plane(phovo, oracle):
         assert np.max(np.abs(a["g"] - b["g"])) <= 1e-9 * max(np.max(np.abs(b["g"])), 1e-300), p
 
 
+@pytest.mark.parametrize("rows,cols,levels", [(8, 8, 3), (5, 200, 2), (16, 24, 4), (9, 13, 2)])
+def test_batch_degenerate_levels_behave_like_the_reference(phovo, oracle, rows, cols, levels):
+    """Levels of a few pixels: the normal equations go singular, the state turns NaN, every pixel is
+    invalid from then on and the reference's zero Jacobian rows give a zero gradient, which ends each
+    later level after one iteration (AN:388).  Iteration counts and the NaN pattern must be the
+    reference's; where the alignment stays finite (9x13) the poses must agree as usual."""
+    f = 0.9 * cols
+    K = np.array([[f, 0, (cols - 1) / 2.], [0, f, (rows - 1) / 2.], [0, 0, 1.]])
+    P = 3
+    g0, d0, g1, _ = phovo.synth.make_batch(P, rows, cols, K=K, seed0=900 + rows)
+    cfg = phovo.default_config()
+    cfg.num_levels = levels
+    for l in range(levels):
+        cfg.max_num_iterations[l] = 6
+        cfg.min_gradient_norm[l] = 1.0
+    odo = make_odo(phovo, cfg, K)
+    st, it = odo.BatchAlign(g0, d0, g1)
+    ost, oit = oracle_batch(oracle, cfg, K, g0, d0, g1, threads=2)
+    assert np.array_equal(it, oit), (it.tolist(), oit.tolist())
+    assert np.array_equal(np.isnan(st), np.isnan(ost))
+    for p in range(P):
+        if np.isfinite(ost[p]).all():
+            assert_pose_close(st[p], ost[p])
+
+
 def test_batch_unsupported_configurations_fail_loudly(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)
