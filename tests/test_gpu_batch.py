@@ -198,6 +198,51 @@ def test_batch_degenerate_levels_behave_like_the_reference(phovo, oracle, rows, 
             assert_pose_close(st[p], ost[p])
 
 
+def test_batch_unusual_depth_values_and_ranges(phovo, oracle):
+    """NaN / inf / negative / zero / huge depths, depth ranges (0, 1e300), (-2, 5), (0.3, inf) and large
+    initial states: iteration counts, per-iteration valid-pixel counts and poses must be the reference's.
+    (An unbounded depth range switches the estimated warp off: every pixel takes the exact path.)"""
+    rows, cols, P = 96, 128, 4
+    K = np.array([[110., 0, 63.5], [0, 110., 47.5], [0, 0, 1.]])
+    g0, d0, g1, _ = phovo.synth.make_batch(P, rows, cols, K=K, seed0=1234)
+    rng = np.random.default_rng(5)
+    d = d0.copy()
+    m = rng.random(d.shape)
+    d[m < 0.02] = np.nan
+    d[(m > 0.02) & (m < 0.03)] = np.inf
+    d[(m > 0.03) & (m < 0.04)] = -1.5
+    d[(m > 0.04) & (m < 0.05)] = 0.
+    d[(m > 0.05) & (m < 0.06)] = 1e30
+    big = np.zeros((P, 6))
+    big[:, 0] = [0.5, -2., 10., 0.]
+    big[:, 3] = [0.3, 1.5, -3.0, 0.]
+    big[:, 5] = [0., 0.7, 0.1, 3.1]
+    for dd, (mn, mx), init in ((d, (0.3, 5.0), None), (d, (0.0, 1e300), None), (d, (-2.0, 5.0), None),
+                               (d0, (0.3, float("inf")), None), (d0, (0.3, 5.0), big)):
+        cfg = phovo.default_config()
+        cfg.num_levels = 3
+        for l in range(3):
+            cfg.max_num_iterations[l] = (0, 5, 8)[l]
+            cfg.min_gradient_norm[l] = 1e-2
+        cfg.min_depth, cfg.max_depth = mn, mx
+        odo = make_odo(phovo, cfg, K)
+        odo.BatchSetRecordStats(True)
+        st, _ = odo.BatchAlign(g0, dd, g1, initial_states=init)
+        for p in range(P):
+            o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+            o.set_source(g0[p], dd[p])
+            o.set_target(g1[p])
+            o.set_initial_state(np.zeros(6) if init is None else init[p])
+            o.optimize()
+            olog, glog = o.iter_stats(), odo.BatchIterationStats(p)
+            assert len(olog) == len(glog), (mn, mx, p)
+            assert [a["num_valid"] for a in glog] == [b["num_valid"] for b in olog], (mn, mx, p)
+            if np.isfinite(o.state()).all():
+                assert_pose_close(st[p], o.state(), "range (%g, %g) pair %d" % (mn, mx, p))
+            else:
+                assert np.array_equal(np.isnan(st[p]), np.isnan(o.state()))
+
+
 def test_batch_unsupported_configurations_fail_loudly(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)

@@ -43,3 +43,47 @@ for (rows, cols, levels, P) in [(8, 8, 3, 3), (9, 13, 2, 2), (16, 24, 4, 5), (33
         print("   device iterations", it.tolist(), "oracle", oit.tolist(), "device states", st.tolist()[:2], "oracle", ost.tolist()[:2])
     print(rows, cols, levels, P, "iters equal", same_it, "nan pattern equal", nan_same, "max diff batch", diff, "general", gdiff, "OK" if ok else "MISMATCH")
 print("bad", bad)
+
+# ---- unusual VALUES at an ordinary size: NaN / inf / negative / zero / huge depths, exotic depth ranges, large initial states ----
+print("--- unusual values")
+rows, cols, P = 96, 128, 4
+K = np.array([[110., 0, 63.5], [0, 110., 47.5], [0, 0, 1.]])
+g0, d0, g1, _ = phovo.synth.make_batch(P, rows, cols, K=K, seed0=1234)
+rng = np.random.default_rng(5)
+bad2 = 0
+cases = []
+d = d0.copy(); m = rng.random(d.shape); d[m < 0.02] = np.nan; d[(m > 0.02) & (m < 0.03)] = np.inf; d[(m > 0.03) & (m < 0.04)] = -1.5; d[(m > 0.04) & (m < 0.05)] = 0.; d[(m > 0.05) & (m < 0.06)] = 1e30
+cases.append(("nan/inf/negative/zero/huge depths", d, (0.3, 5.0), None))
+cases.append(("min_depth 0, max_depth 1e300", d, (0.0, 1e300), None))
+cases.append(("negative min_depth", d, (-2.0, 5.0), None))
+cases.append(("max_depth inf", d0, (0.3, float("inf")), None))
+big = np.zeros((P, 6)); big[:, 0] = [0.5, -2., 10., 0.]; big[:, 3] = [0.3, 1.5, -3.0, 0.]; big[:, 5] = [0., 0.7, 0.1, 3.1]
+cases.append(("large initial states", d0, (0.3, 5.0), big))
+tiny = np.zeros((P, 6)); tiny[:, 2] = -d0.reshape(P, -1).mean(axis=1)
+cases.append(("scene on the camera plane", d0, (0.05, 50.0), tiny))
+for name, dd, (mn, mx), init in cases:
+    cfg = phovo.default_config(); cfg.num_levels = 3
+    for l in range(3):
+        cfg.max_num_iterations[l] = (0, 5, 8)[l]; cfg.min_gradient_norm[l] = 1e-2
+    cfg.min_depth, cfg.max_depth = mn, mx
+    odo = phovo.CPhotoconsistencyOdometryCuda(); odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
+    odo.BatchSetRecordStats(True)
+    st, it = odo.BatchAlign(g0, dd, g1, initial_states=init)
+    ocfg = oracle_py.Config.from_buffer_copy(bytes(cfg))
+    worst, same_it, same_valid = 0.0, True, True
+    for p in range(P):
+        o = oracle_py.Oracle(ocfg, K)
+        o.set_source(g0[p], dd[p]); o.set_target(g1[p]); o.set_initial_state(np.zeros(6) if init is None else init[p]); o.optimize()
+        olog, glog = o.iter_stats(), odo.BatchIterationStats(p)
+        same_it &= len(olog) == len(glog)
+        for a, b in zip(glog, olog):
+            same_valid &= a["num_valid"] == b["num_valid"]
+        os_ = o.state()
+        if np.isfinite(os_).all() and np.isfinite(st[p]).all():
+            worst = max(worst, float(np.max(np.abs(st[p] - os_))))
+        else:
+            same_valid &= bool(np.array_equal(np.isnan(st[p]), np.isnan(os_)))
+    ok = same_it and same_valid and worst < 1e-6
+    bad2 += not ok
+    print(name, "| iterations equal", same_it, "| valid counts equal", same_valid, "| worst pose diff", worst, "OK" if ok else "MISMATCH")
+print("bad", bad2)
