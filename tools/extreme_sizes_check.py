@@ -1,6 +1,11 @@
 #!/usr/bin/env python
-"""Extreme image sizes (a few pixels per level, one-row / one-column strips, single level) through the batch
-kernels and the general path against the CPU oracle (GPU box).  Prints one line per case."""
+"""Corner cases against the CPU oracle (GPU box), one line per case:
+  * extreme image sizes (a few pixels per level, one-row / one-column strips, a single level), where the
+    normal equations go singular and the state turns NaN: iteration counts and NaN patterns must match;
+  * unusual VALUES at an ordinary size (NaN / inf / negative / zero / huge depths, depth ranges (0, 1e300),
+    (-2, 5), (0.3, inf), large initial states, a scene lying on the target camera plane) through the batch
+    kernels and through the general path under the cooperative (estimated warp) and graph (exact warp) drivers:
+    iteration counts, per-iteration valid-pixel counts and poses must match."""
 import importlib, sys, numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "oracle"); sys.path.insert(0, "tests")
 phovo = importlib.import_module("photoconsistency-visual-odometry_b200"); phovo.build()
@@ -87,3 +92,34 @@ for name, dd, (mn, mx), init in cases:
     bad2 += not ok
     print(name, "| iterations equal", same_it, "| valid counts equal", same_valid, "| worst pose diff", worst, "OK" if ok else "MISMATCH")
 print("bad", bad2)
+
+# ---- the same unusual values through the general path (cooperative driver: estimated warp; graph driver: exact warp) ----
+print("--- unusual values, general path")
+bad3 = 0
+for name, dd, (mn, mx), init in cases:
+    cfg = phovo.default_config(); cfg.num_levels = 3
+    for l in range(3):
+        cfg.max_num_iterations[l] = (0, 5, 8)[l]; cfg.min_gradient_norm[l] = 1e-2
+    cfg.min_depth, cfg.max_depth = mn, mx
+    ocfg = oracle_py.Config.from_buffer_copy(bytes(cfg))
+    for path in (2, 1):
+        odo = phovo.CPhotoconsistencyOdometryCuda(); odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K); odo.SetExecution(path)
+        worst, same = 0.0, True
+        for p in range(P):
+            o = oracle_py.Oracle(ocfg, K)
+            s0 = np.zeros(6) if init is None else init[p]
+            o.set_source(g0[p], dd[p]); o.set_target(g1[p]); o.set_initial_state(s0); o.optimize()
+            odo.SetSourceFrame(g0[p], dd[p]); odo.SetTargetFrame(g1[p]); odo.SetInitialStateVector(s0)
+            try:
+                odo.Optimize()
+            except phovo.PhovoError:
+                same &= not np.isfinite(o.state()).all()
+                continue
+            glog, olog = odo.IterationStats(), o.iter_stats()
+            same &= len(glog) == len(olog) and all(a["num_valid"] == b["num_valid"] for a, b in zip(glog, olog))
+            if np.isfinite(o.state()).all():
+                worst = max(worst, float(np.max(np.abs(odo.GetOptimalStateVector() - o.state()))))
+        ok = same and worst < 1e-6
+        bad3 += not ok
+        print(name, "| driver", path, "| iterations and valid counts equal", same, "| worst pose diff", worst, "OK" if ok else "MISMATCH")
+print("bad", bad3)
