@@ -341,7 +341,7 @@ struct LevelCtx {
 // of the level width, so a thread's pixels t, t+BT, ... all lie in ONE column: the column entries
 // of the tables live in registers and only the row advances.  The thread -> pixel mapping is the
 // same linear one in both variants, so results are bitwise identical.
-template <int MODE, bool COLFIX, int BT>
+template <int MODE, bool COLFIX, int BT, bool STATS>
 __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const LevelCtx& L, BatchShared* sh, phovo_iter_stats* log) {
   constexpr int NW = BT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -556,9 +556,9 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
         double Ja[6], Jb[6];
         jacobian_row<MODE>(K, ca0, rp0[0], rp0[1], rp0[2], rp0[3], c0_, (vbits & 1u) != 0, pg[0], Ja);
         jacobian_row<MODE>(K, ca1, rp1[0], rp1[1], rp1[2], rp1[3], c1_, (vbits & 2u) != 0, pg[BT], Jb);
-        acc[27] = fma(resa, resa, acc[27]);
+        if (STATS) acc[27] = fma(resa, resa, acc[27]);   // sum r^2: only the iteration log reports it (the reference has no cost)
         accumulate_row(acc, Ja, resa);
-        acc[27] = fma(resb, resb, acc[27]);
+        if (STATS) acc[27] = fma(resb, resb, acc[27]);
         accumulate_row(acc, Jb, resb);
         vm >>= 2;
         pw += 2 * BT; pg += 2 * BT; pi1 += 2 * BT;
@@ -619,7 +619,7 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
 // Thread t owns pixels t, t+BT, ...; whether pixel k of a thread is valid under the current pose
 // stays in a 64-bit register mask between the two phases of an iteration.  The thread -> pixel
 // mapping is a pure function of the level size, so results do not depend on grid, batch or GPU.
-template <int MODE, int BT, int MINB>
+template <int MODE, int BT, int MINB, bool STATS>
 __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant__ BatchLevelParams lv,
                                                           const uint8_t* __restrict__ store,
                                                           const double* __restrict__ init_states, double* __restrict__ states,
@@ -702,8 +702,8 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       }
     }
     // (the first barrier inside gn_level orders these writes before the pixel loops)
-    if (BT % cols == 0 && !lv.force_generic) gn_level<MODE, true, BT>(lv, L, sh, log);
-    else gn_level<MODE, false, BT>(lv, L, sh, log);
+    if (BT % cols == 0 && !lv.force_generic) gn_level<MODE, true, BT, STATS>(lv, L, sh, STATS ? log : nullptr);
+    else gn_level<MODE, false, BT, STATS>(lv, L, sh, STATS ? log : nullptr);
     __syncthreads();
     if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + lv.level] = sh->iteration;
     if (tid < 6) states[(size_t)pair * 6 + tid] = sh->pose.state[tid];
@@ -729,13 +729,20 @@ size_t batch_level_smem_bytes(int rows, int cols) {
   return level_smem_bytes(rows, cols, batch_level_is_small(rows, cols) ? kBatchThreadsSmall : kBatchThreads);
 }
 
+template <int MODE, int BT, int MINB>
+static cudaError_t set_level_smem(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k_batch_level<MODE, BT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_batch_level<MODE, BT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 cudaError_t batch_align_prepare() {
   cudaError_t e;
   const int big = 227 * 1024, small = (227 * 1024) / 3 - 1024;
-  if ((e = cudaFuncSetAttribute(k_batch_level<0, kBatchThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_batch_level<1, kBatchThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_batch_level<0, kBatchThreadsSmall, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_batch_level<1, kBatchThreadsSmall, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  if ((e = set_level_smem<0, kBatchThreads, 1>(big)) != cudaSuccess) return e;
+  if ((e = set_level_smem<1, kBatchThreads, 1>(big)) != cudaSuccess) return e;
+  if ((e = set_level_smem<0, kBatchThreadsSmall, 3>(small)) != cudaSuccess) return e;
+  return set_level_smem<1, kBatchThreadsSmall, 3>(small);
 }
 
 int launch_batch_pyramid(cudaStream_t stream, const BatchParams& bp, const uint8_t* gray0, const void* depth0,
@@ -759,15 +766,22 @@ int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count,
     const BatchLevelParams lv = level_params(bp, a);
     const size_t smem = batch_level_smem_bytes(rows, cols);
     const bool fixed = bp.mode == PHOVO_MODE_ANALYTIC_FIXED;
+    // STATS: the kernel that also accumulates sum r^2 and writes the iteration log
+#define PHOVO_LAUNCH_LEVEL(MODE, BT, MINB, grid)                                                                                        \
+  do {                                                                                                                                  \
+    if (log) k_batch_level<MODE, BT, MINB, true><<<grid, BT, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);   \
+    else k_batch_level<MODE, BT, MINB, false><<<grid, BT, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);      \
+  } while (0)
     if (batch_level_is_small(rows, cols)) {
       const int grid = min(bp.num_pairs, 3 * sm_count);
-      if (fixed) k_batch_level<1, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
-      else k_batch_level<0, kBatchThreadsSmall, 3><<<grid, kBatchThreadsSmall, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
+      if (fixed) PHOVO_LAUNCH_LEVEL(1, kBatchThreadsSmall, 3, grid);
+      else PHOVO_LAUNCH_LEVEL(0, kBatchThreadsSmall, 3, grid);
     } else {
       const int grid = min(bp.num_pairs, sm_count);
-      if (fixed) k_batch_level<1, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
-      else k_batch_level<0, kBatchThreads, 1><<<grid, kBatchThreads, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);
+      if (fixed) PHOVO_LAUNCH_LEVEL(1, kBatchThreads, 1, grid);
+      else PHOVO_LAUNCH_LEVEL(0, kBatchThreads, 1, grid);
     }
+#undef PHOVO_LAUNCH_LEVEL
     ++launches;
   }
   return launches;

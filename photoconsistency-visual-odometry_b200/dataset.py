@@ -142,8 +142,9 @@ def open_rgbd_dataset(directory):
 class PrefetchingSource(object):
     """Runs a CMultiSensorDataSource `ahead` frames ahead on a background thread.  Every decoded image
     is copied into a slot of a ring of page-locked host buffers (when CUDA is available), so that the
-    solver's uploads are direct DMA.  A slot is recycled `ahead + 2` frames later: the consumer may hold
-    the current and the previous frame.  Iterating yields {sensor id: SensorData}; errors of the worker
+    solver's uploads are direct DMA.  A slot is recycled `ahead + 3` frames later: `ahead` items wait in
+    the queue, the worker fills one more while the queue is full, and the consumer may hold the current and
+    the previous frame.  Iterating yields {sensor id: SensorData}; errors of the worker
     are re-raised in the consumer."""
 
     def __init__(self, source, ahead=4, pin=None):
@@ -161,7 +162,7 @@ class PrefetchingSource(object):
         self._thread = threading.Thread(target=self._work, daemon=True)
 
     def _buffer(self, key, like):
-        slots = self._ahead + 2
+        slots = self._ahead + 3
         k = (key, like.shape, like.dtype.str)
         if k not in self._ring:
             if self._pin:

@@ -98,9 +98,11 @@ def test_multi_sensor_source_pairs_by_order_and_stops_with_the_shorter_record(ph
 def test_prefetching_source_yields_the_same_frames(phovo, tmp_path):
     ds = phovo.dataset
     _, frames = write_sequence(phovo, str(tmp_path), n=7)
+    import time
     held = []
     for k, item in enumerate(ds.PrefetchingSource(ds.open_rgbd_dataset(str(tmp_path)), ahead=2, pin=False)):
         held.append(item)
+        time.sleep(0.05)          # let the worker run as far ahead as it can: it must not recycle a slot still in use
         # the consumer keeps the previous frame while it works on the current one: both must still be intact
         for j in (k - 1, k):
             if j >= 0:

@@ -45,6 +45,10 @@ def test_batch_matches_oracle_640x480(phovo, oracle, cfg_name, K_name, mode):
     # f64 depth input and device-resident inputs give bitwise the same result
     st64, it64 = odo.BatchAlign(g0, d0, g1)
     assert np.array_equal(st64, st) and np.array_equal(it64, it)
+    # so does the kernel variant without the iteration log (it does not accumulate sum r^2)
+    odo.BatchSetRecordStats(False)
+    stq, itq = odo.BatchAlign(g0, d0.astype(np.float32), g1)
+    assert np.array_equal(stq, st) and np.array_equal(itq, it)
     import torch
     tg0, td0, tg1 = (torch.from_numpy(a).cuda() for a in (g0, d0.astype(np.float32), g1))
     stdev, itdev = odo.BatchAlign(tg0, td0, tg1)
