@@ -67,6 +67,10 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.nvml = pynvml
             self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            # the first call of each query can take tens of milliseconds: pay for it before the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            pynvml.nvmlDeviceGetPowerUsage(self.handle)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
             return
@@ -80,7 +84,7 @@ class ClockSampler:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
                 reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
                 # power is a slow query: every 8th sample is enough for the maximum
-                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if len(self.samples) % 8 == 0 else 0.0
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if len(self.samples) % 8 == 7 else 0.0
                 self.samples.append((sm, reasons, power))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
