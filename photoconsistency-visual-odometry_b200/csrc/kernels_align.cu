@@ -415,6 +415,31 @@ __global__ void k_solve_from_buffer(LevelParams L, PoseDev* pose, const double* 
 // ---------------------------------------------------------------------------------------------
 constexpr int kCoopBlock = 256;
 
+// Jacobian row of a valid source pixel i (analytic modes): compact closed form of AN:243-342 with
+// the image gradient folded in.  Shared by the cooperative and the cluster kernel.
+template <int MODE>
+__device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
+                                                      int i, double J[6]) {
+  const int r = i / L.cols, c = i - r * L.cols;
+  const double d = __ldg(P.D0 + i);
+  const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
+  const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
+  const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
+  const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
+  const double iz = rcp_1ulp(q2 + T.z);
+  const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
+  const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
+  const double B = q1 + T.y;
+  J[0] = ga;
+  J[1] = gb;
+  J[2] = -(fma(ga, A, gb * B) * iz);
+  J[3] = fma(gb, q0, -(ga * q1));
+  const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
+  J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
+  const double Zr = fma(T.R22, py, -(T.R21 * d));
+  J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
                                                                phovo_iter_stats* log) {
@@ -490,25 +515,8 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
           acc[27] = fma(res, res, acc[27]);
         }
         if (!__ldcg(P.valid + i)) continue;
-        const int r = i / L.cols, c = i - r * L.cols;
-        const double d = __ldg(P.D0 + i);
-        const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
-        const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
-        const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
-        const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
-        const double iz = rcp_1ulp(q2 + T.z);
-        const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
-        const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
-        const double B = q1 + T.y;
         double J[6];
-        J[0] = ga;
-        J[1] = gb;
-        J[2] = -(fma(ga, A, gb * B) * iz);
-        J[3] = fma(gb, q0, -(ga * q1));
-        const double Zp = -fma(spsr, py, fma(spcr, d, T.cp * px));
-        J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
-        const double Zr = fma(T.R22, py, -(T.R21 * d));
-        J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
+        analytic_jacobian_row<MODE>(L, P, T, spsr, spcr, i, J);
         accumulate_row(acc, J, res);
         acc[28] += 1.;
       }
@@ -565,6 +573,136 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
     s_pose.log_count = log_count;
     *pose = s_pose;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Thread-block-cluster variant for SMALL levels (analytic modes): ONE cluster of kClusterSize CTAs runs
+// the whole Gauss-Newton loop of a level.  The winner map lives in DISTRIBUTED shared memory: CTA k
+// owns the target slots (and the source pixels) [k chunk, (k+1) chunk); phase A bids with a remote
+// shared-memory atomicMax into the owner's slice, phase B reads only the CTA's own slice.  The two
+// grid-wide barriers of the cooperative kernel (~2.5 us each, which is what a 4 800-px level costs)
+// become two cluster barriers (~0.2 us).  Every CTA deposits its 29 partial sums in every CTA's
+// shared memory, sums the kClusterSize partials in rank order and takes the same step redundantly.
+// Bitwise reproducible; equal to the cooperative kernel up to the grouping of the partial sums.
+// ---------------------------------------------------------------------------------------------
+constexpr int kClusterBlock = 512;
+constexpr int kClusterSize = 16;          // non-portable cluster size (8 is the portable maximum)
+constexpr int kClusterMaxPixels = 24576;  // levels up to this size take the cluster kernel
+
+template <int MODE>
+__global__ void __launch_bounds__(kClusterBlock, 1) k_level_cluster(LevelParams L, LevelPtrs P, PoseDev* pose, phovo_iter_stats* log) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), nblk = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) unsigned char cl_smem[];
+  const int n = L.rows * L.cols;
+  const int chunk = (n + nblk - 1) / nblk;
+  double* sPart = (double*)cl_smem;                                   // [nblk][PHOVO_ACC_STRIDE]: partials of every CTA
+  double* sRed = sPart + kClusterSize * PHOVO_ACC_STRIDE;             // block_reduce scratch
+  int* sWin = (int*)(sRed + (kClusterBlock / 32) * PHOVO_ACC_STRIDE); // [chunk] winner source index per owned target slot
+  unsigned char* sValid = (unsigned char*)(sWin + chunk);             // [chunk] validity of the owned source pixels
+  __shared__ double s_tot[32];
+  __shared__ PoseDev s_pose;
+  __shared__ int s_done;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_pose = *pose; s_done = 0; }
+  for (int k = tid; k < chunk; k += kClusterBlock) sWin[k] = -1;
+  __syncthreads();
+  cluster.sync();                       // every slice is initialised before anybody bids into it
+  int log_count = s_pose.log_count;
+  const int log_capacity = s_pose.log_capacity;
+  const int begin = rank * chunk, end = min(n, begin + chunk);
+  int it = 0;
+  for (; it < L.max_iters; ++it) {
+    Pose T;
+    pose_load(&s_pose, T);
+    // ---- phase A: bids of the owned source pixels into the owners of their target slots ----
+    const EstimateConst E = estimate_const(L, T);
+    for (int i = begin + tid; i < end; i += kClusterBlock) {
+      const double d = __ldg(P.D0 + i);
+      const int r = i / L.cols, c = i - r * L.cols;
+      const bool dep = (L.min_depth < d) & (d < L.max_depth);                  // strict bounds, AN:279-280
+      int tj, ti;
+      const bool unc = estimate_target(L, T, E, r, c, d, tj, ti);
+      bool ok = dep & ((unsigned)tj < (unsigned)L.cols) & ((unsigned)ti < (unsigned)L.rows);
+      int t = L.cols * ti + tj;
+      if (dep & unc) {
+        Warped w;
+        ok = warp_pixel<false>(L, T, r, c, d, w);
+        t = w.t;
+      }
+      if (ok) {
+        const int owner = t / chunk;
+        atomicMax(cluster.map_shared_rank(sWin, owner) + (t - owner * chunk), i);   // raster-order last writer wins (AN:358)
+      }
+      sValid[i - begin] = ok;
+    }
+    cluster.sync();
+    // ---- phase B: residual + Jacobian + normal equations of the owned pixels ----
+    double acc[PHOVO_NACC];
+#pragma unroll
+    for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
+    const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
+    for (int i = begin + tid; i < end; i += kClusterBlock) {
+      const int win = sWin[i - begin];
+      sWin[i - begin] = -1;
+      double res = 0.;
+      if (win >= 0) {
+        res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
+        acc[27] = fma(res, res, acc[27]);
+      }
+      if (!sValid[i - begin]) continue;
+      double J[6];
+      analytic_jacobian_row<MODE>(L, P, T, spsr, spcr, i, J);
+      accumulate_row(acc, J, res);
+      acc[28] += 1.;
+    }
+    {
+      const double total = block_reduce<kClusterBlock>(acc, sRed);
+      if (tid < PHOVO_NACC)
+        for (int b = 0; b < nblk; ++b) cluster.map_shared_rank(sPart, b)[rank * PHOVO_ACC_STRIDE + tid] = total;
+    }
+    cluster.sync();
+    // ---- every CTA: partials summed in rank order, same step taken redundantly ----
+    if (tid < 32) {
+      double t = 0.;
+      if (tid < PHOVO_NACC)
+        for (int b = 0; b < nblk; ++b) t += sPart[b * PHOVO_ACC_STRIDE + tid];
+      s_tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double g[6], step[6], s_in[6], s_out[6], n2 = 0.;
+      for (int k = 0; k < 6; ++k) { g[k] = s_tot[21 + k]; n2 = fma(g[k], g[k], n2); s_in[k] = s_pose.state[k]; }
+      solve6_ldlt(s_tot, g, step);
+      for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];
+      const double gnorm = sqrt(n2);
+      const int done = (it + 1 >= L.max_iters) || (gnorm < L.min_grad_norm);
+      if (rank == 0 && log && log_count < log_capacity) {
+        phovo_iter_stats* e = log + log_count;
+        e->level = L.level; e->iteration = it; e->num_valid = (int)s_tot[28]; e->accepted = 1;
+        for (int k = 0; k < 21; ++k) e->H[k] = s_tot[k];
+        for (int k = 0; k < 6; ++k) { e->g[k] = g[k]; e->state_in[k] = s_in[k]; e->state_out[k] = s_out[k]; }
+        e->grad_norm = gnorm; e->cost = 0.5 * s_tot[27]; e->radius = 0.;
+      }
+      Pose Pn;
+      pose_from_state(s_out, Pn);
+      for (int k = 0; k < 6; ++k) s_pose.state[k] = s_out[k];
+      pose_store(Pn, &s_pose);
+      s_done = done;
+    }
+    log_count += 1;
+    __syncthreads();
+    if (s_done) { ++it; break; }
+  }
+  if (rank == 0 && tid == 0) {
+    s_pose.iteration = it;
+    s_pose.iters_per_level[L.level] = it;
+    s_pose.done = 1;
+    s_pose.log_count = log_count;
+    *pose = s_pose;
+  }
+  cluster.sync();                       // nobody leaves while its shared memory may still be written remotely
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -884,6 +1022,32 @@ int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs
   if (*err != cudaSuccess) return -1;
   *grid_out = grid;
   return 1;
+}
+
+// One cluster per level launch.  Returns 1, 0 if the level does not qualify (mode, size), -1 on a launch error.
+int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, cudaError_t* err) {
+  *err = cudaSuccess;
+  const int n = L.rows * L.cols;
+  if (n > kClusterMaxPixels || (L.mode != PHOVO_MODE_ANALYTIC_REF && L.mode != PHOVO_MODE_ANALYTIC_FIXED)) return 0;
+  if (L.row_begin != 0 || L.row_end != L.rows) return 0;
+  void (*fn)(LevelParams, LevelPtrs, PoseDev*, phovo_iter_stats*) = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? k_level_cluster<1> : k_level_cluster<0>;
+  const int chunk = (n + kClusterSize - 1) / kClusterSize;
+  const size_t smem = sizeof(double) * PHOVO_ACC_STRIDE * (kClusterSize + kClusterBlock / 32) + (size_t)chunk * 5 + 16;
+  static bool prepared[2] = {false, false};
+  const int m = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
+  if (!prepared[m]) {
+    if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return -1;
+    if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * PHOVO_ACC_STRIDE * (kClusterSize + kClusterBlock / 32) + (size_t)((kClusterMaxPixels + kClusterSize - 1) / kClusterSize) * 5 + 16))) != cudaSuccess) return -1;
+    prepared[m] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kClusterSize); cfg.blockDim = dim3(kClusterBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  *err = cudaLaunchKernelEx(&cfg, fn, L, P, pose, log);
+  return *err == cudaSuccess ? 1 : -1;
 }
 
 int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,

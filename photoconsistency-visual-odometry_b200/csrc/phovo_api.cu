@@ -441,7 +441,7 @@ extern "C" int phovo_set_use_graph(phovo_ctx* ctx, int enable) {
 }
 
 extern "C" int phovo_set_execution(phovo_ctx* ctx, int path) {
-  if (!ctx || path < 0 || path > 2) return PHOVO_E_INVALID;
+  if (!ctx || path < 0 || path > 3) return PHOVO_E_INVALID;
   ctx->execution = path;
   ctx->use_graph = path >= 1;
   return PHOVO_OK;
@@ -706,6 +706,15 @@ static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
     // (no k_begin_level: the persistent kernel keeps iteration / done in registers and shared memory
     // and writes the whole PoseDev back when the level ends)
     int grid = 0; cudaError_t e = cudaSuccess;
+    if (ctx->execution == 3 && !ctx->cluster_broken) {      // small level: one thread-block cluster, cluster barriers
+      const int rcl = launch_level_cluster(ctx->stream, L, P, ctx->d_pose, ctx->d_log, &e);
+      if (rcl > 0) { ctx->launches += rcl; continue; }
+      if (rcl < 0) {
+        cudaGetLastError();
+        ctx->cluster_broken = true;
+        ctx->graph_error = std::string("cluster launch unavailable: ") + cudaGetErrorString(e);
+      }
+    }
     const int rc = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, ctx->sm_count, &grid, &e);
     if (rc < 0) {
       cudaGetLastError();
@@ -760,7 +769,7 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
   ctx->last_used_graph = 0;
   ctx->last_path = 0;
   if (ctx->cfg.mode == PHOVO_MODE_CERES) {
-    if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
+    if (ctx->execution >= 2 && !ctx->coop_broken && ctx->shard_world == 1) {
       bool unavailable = false;
       rc = optimize_ceres_coop(ctx, &unavailable);
       if (rc) return rc;
@@ -769,11 +778,11 @@ extern "C" int phovo_optimize(phovo_ctx* ctx) {
     }
     return optimize_ceres(ctx);   // host-driven LM over GPU evaluations
   }
-  if (ctx->execution == 2 && !ctx->coop_broken && ctx->shard_world == 1) {
+  if (ctx->execution >= 2 && !ctx->coop_broken && ctx->shard_world == 1) {
     bool unavailable = false;
     rc = optimize_coop(ctx, &unavailable);
     if (rc) return rc;
-    if (!unavailable) { ctx->last_path = 2; return read_back(ctx); }
+    if (!unavailable) { ctx->last_path = (ctx->execution == 3 && !ctx->cluster_broken) ? 3 : 2; return read_back(ctx); }
     ctx->coop_broken = true;   // remember and use the graph path from now on
   }
   bool done = false;

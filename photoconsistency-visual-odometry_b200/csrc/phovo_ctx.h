@@ -66,7 +66,7 @@ struct phovo_ctx {
   // CUDA graph of the whole Optimize()
   bool use_graph = true, graph_broken = false;
   // 2 (default): persistent cooperative kernel per level; 1: CUDA graph with WHILE nodes; 0: stream launches + host polling
-  int execution = 2; bool coop_broken = false; int sm_count = 0; int last_path = 0;
+  int execution = 2; bool coop_broken = false; bool cluster_broken = false; int sm_count = 0; int last_path = 0;
   cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
   int graph_launches_fixed = 0, graph_launches_per_iter = 0;
   int last_used_graph = 0;

@@ -82,6 +82,11 @@ int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err);
 
+// thread-block-cluster kernel for small levels (analytic modes, <= 24 576 px): the loop of one level inside ONE
+// cluster of 16 CTAs, winner map in distributed shared memory.  Returns 1 (launched), 0 (level does not
+// qualify: use launch_level_coop), -1 (launch error in *err).
+int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, cudaError_t* err);
+
 // Ceres mode: the restated LM loop of one level in one cooperative launch.  lm_params: function, gradient, parameter
 // tolerance, initial / max / min trust-region radius, min relative decrease (CE:464-477).
 int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,

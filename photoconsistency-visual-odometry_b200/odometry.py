@@ -164,7 +164,8 @@ class CPhotoconsistencyOdometryCuda:
         self._check(self._L.phovo_set_stream(self._h, cuda_stream))
 
     def SetExecution(self, path):
-        """2 persistent cooperative kernel per level (default), 1 CUDA graph, 0 stream launches."""
+        """2 persistent cooperative kernel per level (default), 3 the same with small levels inside one
+        thread-block cluster, 1 CUDA graph, 0 stream launches."""
         self._check(self._L.phovo_set_execution(self._h, int(path)))
 
     def LastPath(self):

@@ -175,6 +175,42 @@ def test_graph_and_stream_paths_are_bitwise_identical_and_reproducible(phovo):
         assert all(np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"]) for a, b in zip(lp, lp2))
 
 
+@pytest.mark.parametrize("shape,mode,levels", [((480, 640), 0, (0, 0, 20, 50)), ((480, 640), 1, (0, 0, 20, 50)),
+                                               ((135, 241), 0, (6, 8, 10)), ((240, 320), 0, (4, 6, 8, 10))])
+def test_cluster_driver_matches_the_cooperative_driver(phovo, oracle, shape, mode, levels):
+    """Execution path 3: small levels inside one thread-block cluster (winner map in distributed shared
+    memory, cluster barriers); levels above 24 576 px (240x320 level 0) stay on the cooperative kernel.
+    Same winners, same sums up to the grouping of the partials, bitwise reproducible, oracle parity."""
+    K = phovo.synth.K_FRAME_ALIGNMENT.copy()
+    K[:2] *= shape[1] / 640.
+    g0, d0, g1, _ = phovo.synth.make_pair(shape[0], shape[1], K=K, seed=11)
+    cfg = phovo.default_config()
+    cfg.mode = mode
+    cfg.num_levels = len(levels)
+    for l, m in enumerate(levels):
+        cfg.max_num_iterations[l] = m
+        cfg.min_gradient_norm[l] = 300. if shape == (480, 640) else 30.
+    odo_c = make_odo(phovo, cfg, K)
+    odo_c.SetExecution(3)
+    sc, lc = run_gpu(odo_c, g0, d0, g1)
+    assert odo_c.LastPath() == 3, odo_c.GraphError()
+    odo_p = make_odo(phovo, cfg, K)
+    sp, lp = run_gpu(odo_p, g0, d0, g1)
+    assert odo_p.LastPath() == 2
+    assert len(lc) == len(lp) and np.max(np.abs(sc - sp)) < 1e-12
+    for a, b in zip(lc, lp):
+        assert a["level"] == b["level"] and a["num_valid"] == b["num_valid"]
+        assert np.max(np.abs(a["H"] - b["H"])) <= 1e-12 * np.max(np.abs(b["H"]))
+        assert np.max(np.abs(a["g"] - b["g"])) <= 1e-11 * np.max(np.abs(b["g"]))
+    for _ in range(3):
+        s2, l2 = run_gpu(odo_c, g0, d0, g1)
+        assert np.array_equal(sc, s2)
+        assert all(np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"]) for a, b in zip(lc, l2))
+    o = run_oracle(oracle, cfg, K, g0, d0, g1)
+    assert_logs_match(lc, o.iter_stats(), rel=REL_NORMAL_EQ, what="cluster driver")
+    assert_pose_close(sc, o.state(), "cluster driver")
+
+
 @pytest.mark.parametrize("name", ["pair_96x128_ref", "pair_96x128_fixed", "pair_90x135_ref"])
 def test_alignment_matches_golden(phovo, name):
     gd = load_golden(name)
