@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // K3-batch building blocks
 // ---------------------------------------------------------------------------------------------
+static_assert(kBatchThreads % 32 == 0 && kBatchThreadsSmall % 32 == 0, "whole warps: the reduction scratch has one row per warp");
 static_assert(kBatchMaxLevelPixels <= 60 * kBatchThreads, "per-thread validity mask is 64 bits (phase A fills it four pixels at a time)");
 static_assert(kBatchSmallLevelPixels <= 60 * kBatchThreadsSmall, "per-thread validity mask is 64 bits (phase A fills it four pixels at a time)");
 static_assert(kBatchMaxLevelPixels < 65535, "winner word keeps source index + 1 in 16 bits");
