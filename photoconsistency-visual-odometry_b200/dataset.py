@@ -19,8 +19,9 @@ Reference interfaces restated (names, argument meaning and behaviour kept; code 
 
 What is B200-specific: depth stays raw u16 on the host and is scaled by `depthScalingFactor` on the
 device (`(double)raw * scale`, the same product the app forms in `Mat_<double> * scalar`, :208/:220);
-`PrefetchingSource` decodes the PNGs on a background thread into a ring of PINNED buffers, so decode
-overlaps the alignment of the previous frame and every upload runs at full PCIe speed; frame k's target
+`PrefetchingSource` decodes the PNGs on a pool of background threads into a ring of PINNED buffers (in
+record order), so decode -- the slowest stage of a recorded sequence by two orders of magnitude -- runs
+on several cores beside the alignment and every upload runs at full PCIe speed; frame k's target
 pyramid is promoted to frame k+1's source pyramid on the device instead of being rebuilt.
 """
 import os
@@ -140,17 +141,20 @@ def open_rgbd_dataset(directory):
 
 
 class PrefetchingSource(object):
-    """Runs a CMultiSensorDataSource `ahead` frames ahead on a background thread.  Every decoded image
-    is copied into a slot of a ring of page-locked host buffers (when CUDA is available), so that the
-    solver's uploads are direct DMA.  A slot is recycled `ahead + 3` frames later: `ahead` items wait in
-    the queue, the worker fills one more while the queue is full, and the consumer may hold the current and
-    the previous frame.  Iterating yields {sensor id: SensorData}; errors of the worker
-    are re-raised in the consumer."""
+    """Runs a CMultiSensorDataSource ahead of its consumer on background threads.  PNG decoding is what
+    bounds a recorded sequence (a 640x480 colour + 16-bit depth pair takes ~5-20 ms per core, the solver
+    0.2 ms), so the frames are decoded by a pool of `workers` threads (cv2 releases the GIL) and handed
+    over in record order.  Every decoded image is copied into a slot of a ring of page-locked host
+    buffers (when CUDA is available), so that the solver's uploads are direct DMA.  A slot is recycled
+    `ahead + workers + 3` frames later: up to `workers` frames are being decoded, `ahead` wait in the
+    queue, one is in hand-over, and the consumer may hold the current and the previous frame.
+    Iterating yields {sensor id: SensorData}; errors of the workers are re-raised in the consumer.
+    Sources that are not CCameraRecord-like (no next_entry / read_image) are read sequentially."""
 
-    def __init__(self, source, ahead=4, pin=None):
-        self._src, self._ahead = source, max(1, int(ahead))
+    def __init__(self, source, ahead=4, pin=None, workers=4):
+        self._src, self._ahead, self._workers = source, max(1, int(ahead)), max(1, int(workers))
         self._q = queue.Queue(maxsize=self._ahead)
-        self._ring, self._slot = {}, 0
+        self._ring, self._lock = {}, threading.Lock()
         if pin is None:
             try:
                 import torch
@@ -161,37 +165,81 @@ class PrefetchingSource(object):
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._work, daemon=True)
 
-    def _buffer(self, key, like):
-        slots = self._ahead + 3
+    def _buffer(self, key, like, slot):
+        slots = self._ahead + self._workers + 3
         k = (key, like.shape, like.dtype.str)
-        if k not in self._ring:
-            if self._pin:
-                import torch
-                tdt = {"|u1": torch.uint8, "<u2": torch.int16, "<f4": torch.float32, "<f8": torch.float64}[like.dtype.str]
-                self._ring[k] = [torch.empty(like.shape, dtype=tdt).pin_memory().numpy().view(like.dtype) for _ in range(slots)]
-            else:
-                self._ring[k] = [np.empty(like.shape, like.dtype) for _ in range(slots)]
-        return self._ring[k][self._slot % slots]
+        with self._lock:
+            if k not in self._ring:
+                if self._pin:
+                    import torch
+                    tdt = {"|u1": torch.uint8, "<u2": torch.int16, "<f4": torch.float32, "<f8": torch.float64}[like.dtype.str]
+                    self._ring[k] = [torch.empty(like.shape, dtype=tdt).pin_memory().numpy().view(like.dtype) for _ in range(slots)]
+                else:
+                    self._ring[k] = [np.empty(like.shape, like.dtype) for _ in range(slots)]
+            return self._ring[k][slot % slots]
+
+    def _stage(self, item, slot):
+        staged = {}
+        for key, sd in item.items():
+            buf = self._buffer(key, sd.GetData(), slot)
+            np.copyto(buf, sd.GetData())
+            staged[key] = SensorData(sd.GetTimeStamp(), buf)
+        return staged
+
+    def _records(self):
+        """{id: record} if every source can be split into (next line, decode), else None."""
+        srcs = getattr(self._src, "_sources", None)
+        if not srcs or not all(hasattr(r, "next_entry") and hasattr(r, "read_image") for r in srcs.values()):
+            return None
+        return srcs
+
+    def _put(self, item):
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return
+            except queue.Full:
+                pass
 
     def _work(self):
         try:
             self._src.Start()
-            while not self._stop.is_set():
-                item = self._src.GetMultiSensorData()
-                if item is None:
-                    break
-                staged = {}
-                for key, sd in item.items():
-                    buf = self._buffer(key, sd.GetData())
-                    np.copyto(buf, sd.GetData())
-                    staged[key] = SensorData(sd.GetTimeStamp(), buf)
-                self._slot += 1
+            records = self._records()
+            slot = 0
+            if records is None or self._workers == 1:
                 while not self._stop.is_set():
-                    try:
-                        self._q.put(staged, timeout=0.1)
+                    item = self._src.GetMultiSensorData()
+                    if item is None:
                         break
-                    except queue.Full:
-                        pass
+                    self._put(self._stage(item, slot))
+                    slot += 1
+            else:
+                import collections
+                from concurrent.futures import ThreadPoolExecutor
+
+                def decode(entries, slot_):
+                    return self._stage({k: SensorData(ts, records[k].read_image(path)) for k, (ts, path) in entries.items()}, slot_)
+
+                pending, exhausted = collections.deque(), False
+                with ThreadPoolExecutor(self._workers) as pool:
+                    while not self._stop.is_set():
+                        while not exhausted and len(pending) < self._workers:
+                            entries = {}
+                            for k in sorted(records):              # one line of every record, like GetMultiSensorData
+                                e = records[k].next_entry()
+                                if e is None:
+                                    exhausted = True
+                                    break
+                                entries[k] = e
+                            if exhausted:
+                                break
+                            pending.append(pool.submit(decode, entries, slot))
+                            slot += 1
+                        if not pending:
+                            break
+                        self._put(pending.popleft().result())
+                    for f in pending:
+                        f.cancel()
             self._src.Stop()
             self._q.put(None)
         except Exception as e:      # noqa: BLE001 -- handed to the consumer

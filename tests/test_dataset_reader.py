@@ -95,12 +95,13 @@ def test_multi_sensor_source_pairs_by_order_and_stops_with_the_shorter_record(ph
         assert item[ds.DepthCameraIdentifier].GetTimeStamp() == pytest.approx(ts + 0.011, abs=1e-6)   # own timestamps, no association
 
 
-def test_prefetching_source_yields_the_same_frames(phovo, tmp_path):
+@pytest.mark.parametrize("workers", [1, 3])
+def test_prefetching_source_yields_the_same_frames(phovo, tmp_path, workers):
     ds = phovo.dataset
-    _, frames = write_sequence(phovo, str(tmp_path), n=7)
+    _, frames = write_sequence(phovo, str(tmp_path), n=7 if workers == 1 else 17)
     import time
     held = []
-    for k, item in enumerate(ds.PrefetchingSource(ds.open_rgbd_dataset(str(tmp_path)), ahead=2, pin=False)):
+    for k, item in enumerate(ds.PrefetchingSource(ds.open_rgbd_dataset(str(tmp_path)), ahead=2, pin=False, workers=workers)):
         held.append(item)
         time.sleep(0.05)          # let the worker run as far ahead as it can: it must not recycle a slot still in use
         # the consumer keeps the previous frame while it works on the current one: both must still be intact
@@ -108,11 +109,11 @@ def test_prefetching_source_yields_the_same_frames(phovo, tmp_path):
             if j >= 0:
                 assert np.array_equal(held[j][ds.IntensityCameraIdentifier].GetData(), frames[j][1])
                 assert np.array_equal(held[j][ds.DepthCameraIdentifier].GetData(), frames[j][2])
-    assert len(held) == 7
+    assert len(held) == len(frames)
     # errors of the worker thread surface in the consumer
     (tmp_path / "rgb.txt").write_text("1.0 rgb/missing.png\n")
     with pytest.raises(RuntimeError, match="Unable to read image"):
-        list(ds.PrefetchingSource(ds.open_rgbd_dataset(str(tmp_path)), pin=False))
+        list(ds.PrefetchingSource(ds.open_rgbd_dataset(str(tmp_path)), pin=False, workers=workers))
 
 
 def test_quaternion_and_trajectory_line(phovo):
