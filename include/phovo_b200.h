@@ -196,7 +196,7 @@ int phovo_set_stream(phovo_ctx* ctx, void* cuda_stream);
 int phovo_set_use_graph(phovo_ctx* ctx, int enable);
 /* How phovo_optimize drives the iteration loop of a level (results agree to rounding; each path is
  * bitwise reproducible run to run):
- *   3           as 2, but a small level (analytic solvers, <= 24 576 px) runs inside ONE thread-block cluster
+ *   3           as 2, but a small level (analytic solvers, <= 8 192 px) runs inside ONE thread-block cluster
  *               of 16 CTAs: winner map in distributed shared memory, cluster barriers instead of grid barriers
  *   2 (default) one persistent cooperative kernel per level, grid-wide barriers between the phases
  *   1           one CUDA graph for the whole Optimize with a conditional WHILE node per level

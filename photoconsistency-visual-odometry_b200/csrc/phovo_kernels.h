@@ -82,7 +82,7 @@ int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err);
 
-// thread-block-cluster kernel for small levels (analytic modes, <= 24 576 px): the loop of one level inside ONE
+// thread-block-cluster kernel for small levels (analytic modes, <= 8 192 px): the loop of one level inside ONE
 // cluster of 16 CTAs, winner map in distributed shared memory.  Returns 1 (launched), 0 (level does not
 // qualify: use launch_level_coop), -1 (launch error in *err).
 int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, cudaError_t* err);

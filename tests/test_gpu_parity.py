@@ -179,7 +179,8 @@ def test_graph_and_stream_paths_are_bitwise_identical_and_reproducible(phovo):
                                                ((135, 241), 0, (6, 8, 10)), ((240, 320), 0, (4, 6, 8, 10))])
 def test_cluster_driver_matches_the_cooperative_driver(phovo, oracle, shape, mode, levels):
     """Execution path 3: small levels inside one thread-block cluster (winner map in distributed shared
-    memory, cluster barriers); levels above 24 576 px (240x320 level 0) stay on the cooperative kernel.
+    memory, cluster barriers); levels above 8 192 px (e.g. the 160x120 level of a 640x480 frame) stay on the
+    cooperative kernel, so every case here mixes the two kernels.
     Same winners, same sums up to the grouping of the partials, bitwise reproducible, oracle parity."""
     K = phovo.synth.K_FRAME_ALIGNMENT.copy()
     K[:2] *= shape[1] / 640.
