@@ -1,0 +1,41 @@
+#!/usr/bin/env bash
+# Regenerates the measured evidence under profiles/ on a B200 box (run from the repo root, library built:
+# `python __graft_entry__.py`).  Every ncu pass runs only after the same command has exited 0 without ncu;
+# numbers printed under ncu are never bench values.  Output goes to $OUT (default gpurun_out/); copy what
+# should be kept into profiles/ under the tag of the round (see profiles/README.md).
+set -euo pipefail
+OUT=${OUT:-gpurun_out}; TAG=${TAG:-rXX}
+mkdir -p "$OUT"
+
+# 1. headline bench, reference arm, multi-GPU (N = 2, 4, 8 when the box has them)
+python bench.py > "$OUT/${TAG}_bench.json"
+python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_reference_arm.json"
+# python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 3 > "$OUT/${TAG}_bench_8gpu.json"
+
+# 2. ncu: launch list of the default bench command, then the full capture of the two level kernels
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_batch --csv --log-file "$OUT/${TAG}_launches_default_bench.csv" \
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null
+python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/prof_${TAG}_bench.log"
+ncu --set full --clock-control none --import-source on -k regex:k_batch_level --launch-skip 6 -c 2 -f -o "$OUT/prof_${TAG}" \
+    python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null
+python tools/ncu_summary.py "$OUT/prof_${TAG}.ncu-rep" > "$OUT/${TAG}_k_batch_level_ncu_full.txt"
+python tools/make_roofline_inputs.py "$OUT/prof_${TAG}.ncu-rep" "$OUT/prof_${TAG}_bench.log" profiles/r01_fp64_peak.jsonl "$TAG" > "$OUT/roofline_inputs.json"
+
+# 3. parity sweeps (GPU vs the CPU oracle)
+python tools/fuzz_parity.py --groups 1466 --pairs 24 --seed 1 > "$OUT/${TAG}_fuzz_parity.json"
+python tools/fullsize_parity.py --pairs 4096 > "$OUT/${TAG}_fullsize_parity_4096_pairs.json"
+python tools/extreme_sizes_check.py > "$OUT/${TAG}_extreme_cases.txt"
+
+# 4. latency of the per-pair API (BASELINE configs 0, 1, 2, 4) and the recorded-sequence reader
+python tools/bench_latency.py --mode single > "$OUT/${TAG}_latency_single_pair.json"
+python tools/bench_latency.py --mode single --path 3 > "$OUT/${TAG}_latency_single_pair_cluster_driver.json"
+python tools/bench_latency.py --mode vo --frames 1000 > "$OUT/${TAG}_latency_vo_sequence_1000frames.json"
+python tools/bench_latency.py --mode ceres > "$OUT/${TAG}_latency_ceres_config.json"
+python tools/run_row_sharded.py > "$OUT/${TAG}_row_sharded_8k_1gpu.json"
+python tools/bench_dataset.py > "$OUT/${TAG}_dataset_vo_on_disk.json"
+
+# 5. hardware probes the rooflines lean on
+for p in fp64_peak fp64_latency dmma_probe; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o "tools/$p" "tools/$p.cu" && "./tools/$p" > "$OUT/${TAG}_$p.jsonl"
+done
