@@ -451,6 +451,13 @@ static int analytic_residuals_jacobians(const pho_oracle* o, int level, const do
 /* (SA:104-123) chains the bilinearly sampled Gx/Gy into it (JE:87-109).                     */
 /* residuals N, jac N x 6 ROW-major (Ceres layout), both target-indexed, zero-initialised    */
 /* here (CE:206-212).                                                                         */
+/* jet_arith: Ceres' AutoDiffCostFunction runs the functor on T = double when only the cost   */
+/* is wanted and on T = Jet<double,6> when the Jacobian is; the scalar part of a Jet quotient */
+/* is f.a * (1 / g.a) (ceres/jet.h operator/), not f.a / g.a, so CE:241-242 round differently */
+/* in the two instantiations.  It only matters where a projected coordinate sits on an        */
+/* integer (CE:250-251 truncates) -- which is EVERY pixel at the identity state the apps      */
+/* start from.  Pinned against the reference functor compiled on the Jet stand-in             */
+/* (oracle/shim/ceres/jet.h) in tests/test_reference_ceres_functor.py.                        */
 /* ---------------------------------------------------------------------------------------- */
 static void linear_init_axis(double x, int size, int* x1, int* x2, double* dx) { /* SA:36-50 */
   const int ix = (int)x;
@@ -460,7 +467,7 @@ static void linear_init_axis(double x, int size, int* x1, int* x2, double* dx) {
 }
 
 static int ceres_residuals_jacobians(const pho_oracle* o, int level, const double st[6],
-                                     double* residuals, double* jac, int32_t* winners) {
+                                     double* residuals, double* jac, int32_t* winners, int jet_arith) {
   const int nRows = o->rows[level], nCols = o->cols[level];
   const size_t N = (size_t)nRows * nCols;
   const double* I0 = o->I0[level]; const double* D0 = o->D0[level];
@@ -491,8 +498,15 @@ static int ceres_residuals_jacobians(const pho_oracle* o, int level, const doubl
       double X = R00 * px + R01 * py + R02 * pz + x * 1.0; /* CE:235-238 */
       double Y = R10 * px + R11 * py + R12 * pz + y * 1.0;
       double Z = R20 * px + R21 * py + R22 * pz + z * 1.0;
-      double tc = ((X * fx) / Z) + ox;                 /* CE:241 */
-      double tr = ((Y * fy) / Z) + oy;                 /* CE:242 */
+      double tc, tr;
+      if (jet_arith) {                                 /* CE:241-242 on Jets: quotient = f.a * (1 / g.a) */
+        const double z_inverse = 1.0 / Z;
+        tc = ((X * fx) * z_inverse) + ox;
+        tr = ((Y * fy) * z_inverse) + oy;
+      } else {
+        tc = ((X * fx) / Z) + ox;                      /* CE:241 */
+        tr = ((Y * fy) / Z) + oy;                      /* CE:242 */
+      }
       if (!(tr >= 0. && tr < (double)nRows && tc >= 0. && tc < (double)nCols)) continue; /* CE:246-247 */
       int tri = (int)tr, tci = (int)tc;                /* CE:250-251 truncation */
       /* SA:53-99 SampleLinear at (x = tc, y = tr) with the -0.5 shift */
@@ -622,7 +636,7 @@ void pho_eval(pho_oracle* o, int level, const double state[6], phovo_iter_stats*
   memcpy(out->state_in, state, sizeof(double) * 6);
   memcpy(out->state_out, state, sizeof(double) * 6);
   if (o->cfg.mode == PHOVO_MODE_CERES) {
-    out->num_valid = ceres_residuals_jacobians(o, level, state, res, jac, NULL);
+    out->num_valid = ceres_residuals_jacobians(o, level, state, res, jac, NULL, 1);
     normal_equations_rowmajor(jac, res, N, out->H, out->g, &out->cost);
     if (jacobian) memcpy(jacobian, jac, sizeof(double) * N * 6);
   } else {
@@ -641,7 +655,7 @@ void pho_winner_map(pho_oracle* o, int level, const double state[6], int32_t* ou
   const size_t N = (size_t)o->rows[level] * o->cols[level];
   double* res = (double*)calloc(N, sizeof(double));
   double* jac = (double*)calloc(N * 6, sizeof(double));
-  if (o->cfg.mode == PHOVO_MODE_CERES) ceres_residuals_jacobians(o, level, state, res, NULL, out);
+  if (o->cfg.mode == PHOVO_MODE_CERES) ceres_residuals_jacobians(o, level, state, res, NULL, out, 1);
   else analytic_residuals_jacobians(o, level, state, res, jac, out);
   free(res); free(jac);
 }
@@ -712,98 +726,122 @@ static int chol_solve6(const double M[36], const double b[6], double xout[6]) {
   return 1;
 }
 
-static void ceres_eval(pho_oracle* o, int level, const double st[6], int want_jac,
-                       double H[21], double g[6], double* cost, int* count, double* res, double* jac) {
-  const size_t N = (size_t)o->rows[level] * o->cols[level];
-  *count = ceres_residuals_jacobians(o, level, st, res, want_jac ? jac : NULL, NULL);
-  if (want_jac) normal_equations_rowmajor(jac, res, N, H, g, cost);
-  else { double s = 0; for (size_t i = 0; i < N; ++i) s += res[i] * res[i]; *cost = 0.5 * s; }
+/* The restated trust-region loop, written against an evaluation callback so that oracle/_ref can
+ * run the SAME loop on the reference's own functor (oracle/shim/ref_driver_ceres.cpp).
+ * eval(user, x, want_jac, H, g, cost, count): H/g are only written when want_jac != 0.
+ * new_entry(user) returns a zeroed log record for the iteration that starts.  Returns iterations. */
+int pho_lm_minimize(const pho_lm_options* opt, pho_lm_eval_fn eval, void* eval_user,
+                    pho_lm_entry_fn new_entry, void* entry_user, int level, double x[6]) {
+  const int max_it = opt->max_num_iterations;
+  double radius = opt->initial_trust_region_radius;
+  const double max_radius = opt->max_trust_region_radius;
+  const double min_radius = opt->min_trust_region_radius;
+  const double eta = opt->min_relative_decrease;
+  double decrease_factor = 2.0;
+  double H[21], g[6], cost; int count;
+  eval(eval_user, x, 1, H, g, &cost, &count);
+  /* jacobi scaling: 1 / (1 + column norm), fixed from the first Jacobian */
+  double scale[6]; { double Mfull[36]; expand_sym(H, Mfull);
+    for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(Mfull[a * 6 + a])); }
+  double gmax = 0; for (int a = 0; a < 6; ++a) if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
+  int iteration = 0;
+  if (!(gmax <= opt->gradient_tolerance)) {
+    while (1) {
+      if (iteration >= max_it) break;
+      ++iteration;
+      phovo_iter_stats* s = new_entry(entry_user);
+      s->level = level; s->iteration = iteration - 1; s->num_valid = count; s->cost = cost; s->radius = radius;
+      memcpy(s->H, H, sizeof(H)); memcpy(s->g, g, sizeof(g)); memcpy(s->state_in, x, sizeof(double) * 6);
+      memcpy(s->state_out, x, sizeof(double) * 6);
+      { double n2 = 0; for (int a = 0; a < 6; ++a) n2 += g[a] * g[a]; s->grad_norm = sqrt(n2); }
+      /* scaled system */
+      double M[36], Ms[36], gs[6];
+      expand_sym(H, M);
+      for (int a = 0; a < 6; ++a) { gs[a] = g[a] * scale[a]; for (int b = 0; b < 6; ++b) Ms[a * 6 + b] = M[a * 6 + b] * scale[a] * scale[b]; }
+      double A[36]; memcpy(A, Ms, sizeof(A));
+      for (int a = 0; a < 6; ++a) {
+        double d = Ms[a * 6 + a]; if (d < 1e-6) d = 1e-6; if (d > 1e32) d = 1e32;
+        A[a * 6 + a] += d / radius;
+      }
+      double step[6]; int ok = chol_solve6(A, gs, step);
+      for (int a = 0; a < 6; ++a) step[a] = -step[a];
+      double model_cost_change = 0;
+      if (ok) {
+        /* -(J d)^T (r + J d / 2) = -(d^T g + 0.5 d^T M d) */
+        double dg = 0, dMd = 0;
+        for (int a = 0; a < 6; ++a) { dg += step[a] * gs[a]; double t = 0; for (int b = 0; b < 6; ++b) t += Ms[a * 6 + b] * step[b]; dMd += step[a] * t; }
+        model_cost_change = -(dg + 0.5 * dMd);
+        for (int a = 0; a < 6; ++a) if (!isfinite(step[a])) ok = 0;
+      }
+      if (!ok || !(model_cost_change > 0)) {
+        /* max_num_consecutive_invalid_steps = 0 (CE:477): the first invalid step terminates */
+        s->accepted = 0;
+        break;
+      }
+      double delta[6], xn[6], step_norm = 0, x_norm = 0;
+      for (int a = 0; a < 6; ++a) { delta[a] = step[a] * scale[a]; xn[a] = x[a] + delta[a]; step_norm += delta[a] * delta[a]; x_norm += x[a] * x[a]; }
+      step_norm = sqrt(step_norm); x_norm = sqrt(x_norm);
+      double new_cost; int ncount; double Hd[21], gd[6];
+      eval(eval_user, xn, 0, Hd, gd, &new_cost, &ncount);
+      const double ptol = opt->parameter_tolerance;
+      if (step_norm <= ptol * (x_norm + ptol)) { s->accepted = 0; break; }
+      double cost_change = cost - new_cost;
+      if (fabs(cost_change) < opt->function_tolerance * cost) { s->accepted = 0; break; }
+      double rho = cost_change / model_cost_change;
+      if (rho > eta) {
+        memcpy(x, xn, sizeof(double) * 6);
+        s->accepted = 1; memcpy(s->state_out, x, sizeof(double) * 6);
+        eval(eval_user, x, 1, H, g, &cost, &count);
+        gmax = 0; for (int a = 0; a < 6; ++a) if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
+        if (gmax <= opt->gradient_tolerance) break;
+        double t = 2.0 * rho - 1.0;
+        double f = 1.0 - t * t * t; if (f < 1.0 / 3.0) f = 1.0 / 3.0;
+        radius = radius / f; if (radius > max_radius) radius = max_radius;
+        decrease_factor = 2.0;
+      } else {
+        s->accepted = 0;
+        radius = radius / decrease_factor; decrease_factor *= 2.0;
+      }
+      if (radius < min_radius) break;
+    }
+  }
+  return iteration;
 }
+
+/* J^T J (upper 21), J^T r and the cost from a row-major N x 6 Jacobian: the sums the loop above needs */
+void pho_normal_equations_rowmajor(const double* jac, const double* res, size_t n, double H[21], double g[6], double* cost) {
+  normal_equations_rowmajor(jac, res, n, H, g, cost);
+}
+
+typedef struct { pho_oracle* o; int level; double* res; double* jac; } ceres_level_ctx;
+
+static void ceres_level_eval(void* user, const double st[6], int want_jac, double H[21], double g[6], double* cost, int* count) {
+  ceres_level_ctx* c = (ceres_level_ctx*)user;
+  const size_t N = (size_t)c->o->rows[c->level] * c->o->cols[c->level];
+  *count = ceres_residuals_jacobians(c->o, c->level, st, c->res, want_jac ? c->jac : NULL, NULL, want_jac);
+  if (want_jac) normal_equations_rowmajor(c->jac, c->res, N, H, g, cost);
+  else { double s = 0; for (size_t i = 0; i < N; ++i) s += c->res[i] * c->res[i]; *cost = 0.5 * s; }
+}
+
+static phovo_iter_stats* ceres_level_entry(void* user) { return push_log((pho_oracle*)user); }
 
 static void optimize_ceres(pho_oracle* o) {
   for (int level = o->cfg.num_levels - 1; level >= 0; --level) {
     o->iters_per_level[level] = 0;
     if (!(o->cfg.max_num_iterations[level] > 0)) continue; /* CE:437 */
     const size_t N = (size_t)o->rows[level] * o->cols[level];
-    double* res = (double*)malloc(sizeof(double) * N);
-    double* jac = (double*)malloc(sizeof(double) * N * 6);
-    const int max_it = o->cfg.max_num_iterations[level];
-    double radius = o->cfg.initial_trust_region_radius[level];
-    const double max_radius = o->cfg.max_trust_region_radius[level];
-    const double min_radius = o->cfg.min_trust_region_radius[level];
-    const double eta = o->cfg.min_relative_decrease[level];
-    double decrease_factor = 2.0;
-    double x[6]; memcpy(x, o->state, sizeof(x));
-    double H[21], g[6], cost; int count;
-    ceres_eval(o, level, x, 1, H, g, &cost, &count, res, jac);
-    /* jacobi scaling: 1 / (1 + column norm), fixed from the first Jacobian */
-    double scale[6]; { int k = 0; double Mfull[36]; expand_sym(H, Mfull); (void)k;
-      for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(Mfull[a * 6 + a])); }
-    double gmax = 0; for (int a = 0; a < 6; ++a) if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
-    int iteration = 0;
-    if (!(gmax <= o->cfg.gradient_tolerance[level])) {
-      while (1) {
-        if (iteration >= max_it) break;
-        ++iteration;
-        phovo_iter_stats* s = push_log(o);
-        s->level = level; s->iteration = iteration - 1; s->num_valid = count; s->cost = cost; s->radius = radius;
-        memcpy(s->H, H, sizeof(H)); memcpy(s->g, g, sizeof(g)); memcpy(s->state_in, x, sizeof(x));
-        memcpy(s->state_out, x, sizeof(x));
-        { double n2 = 0; for (int a = 0; a < 6; ++a) n2 += g[a] * g[a]; s->grad_norm = sqrt(n2); }
-        /* scaled system */
-        double M[36], Ms[36], gs[6];
-        expand_sym(H, M);
-        for (int a = 0; a < 6; ++a) { gs[a] = g[a] * scale[a]; for (int b = 0; b < 6; ++b) Ms[a * 6 + b] = M[a * 6 + b] * scale[a] * scale[b]; }
-        double A[36]; memcpy(A, Ms, sizeof(A));
-        for (int a = 0; a < 6; ++a) {
-          double d = Ms[a * 6 + a]; if (d < 1e-6) d = 1e-6; if (d > 1e32) d = 1e32;
-          A[a * 6 + a] += d / radius;
-        }
-        double step[6]; int ok = chol_solve6(A, gs, step);
-        for (int a = 0; a < 6; ++a) step[a] = -step[a];
-        double model_cost_change = 0;
-        if (ok) {
-          /* -(J d)^T (r + J d / 2) = -(d^T g + 0.5 d^T M d) */
-          double dg = 0, dMd = 0;
-          for (int a = 0; a < 6; ++a) { dg += step[a] * gs[a]; double t = 0; for (int b = 0; b < 6; ++b) t += Ms[a * 6 + b] * step[b]; dMd += step[a] * t; }
-          model_cost_change = -(dg + 0.5 * dMd);
-          for (int a = 0; a < 6; ++a) if (!isfinite(step[a])) ok = 0;
-        }
-        if (!ok || !(model_cost_change > 0)) {
-          /* max_num_consecutive_invalid_steps = 0 (CE:477): the first invalid step terminates */
-          s->accepted = 0;
-          break;
-        }
-        double delta[6], xn[6], step_norm = 0, x_norm = 0;
-        for (int a = 0; a < 6; ++a) { delta[a] = step[a] * scale[a]; xn[a] = x[a] + delta[a]; step_norm += delta[a] * delta[a]; x_norm += x[a] * x[a]; }
-        step_norm = sqrt(step_norm); x_norm = sqrt(x_norm);
-        double new_cost; int ncount; double Hd[21], gd[6];
-        ceres_eval(o, level, xn, 0, Hd, gd, &new_cost, &ncount, res, jac);
-        const double ptol = o->cfg.parameter_tolerance[level];
-        if (step_norm <= ptol * (x_norm + ptol)) { s->accepted = 0; break; }
-        double cost_change = cost - new_cost;
-        if (fabs(cost_change) < o->cfg.function_tolerance[level] * cost) { s->accepted = 0; break; }
-        double rho = cost_change / model_cost_change;
-        if (rho > eta) {
-          memcpy(x, xn, sizeof(x));
-          s->accepted = 1; memcpy(s->state_out, x, sizeof(x));
-          ceres_eval(o, level, x, 1, H, g, &cost, &count, res, jac);
-          gmax = 0; for (int a = 0; a < 6; ++a) if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
-          if (gmax <= o->cfg.gradient_tolerance[level]) break;
-          double t = 2.0 * rho - 1.0;
-          double f = 1.0 - t * t * t; if (f < 1.0 / 3.0) f = 1.0 / 3.0;
-          radius = radius / f; if (radius > max_radius) radius = max_radius;
-          decrease_factor = 2.0;
-        } else {
-          s->accepted = 0;
-          radius = radius / decrease_factor; decrease_factor *= 2.0;
-        }
-        if (radius < min_radius) break;
-      }
-    }
-    memcpy(o->state, x, sizeof(x));
-    o->iters_per_level[level] = iteration;
-    free(res); free(jac);
+    ceres_level_ctx ctx = { o, level, (double*)malloc(sizeof(double) * N), (double*)malloc(sizeof(double) * N * 6) };
+    pho_lm_options opt;                                    /* CE:464-477 */
+    opt.max_num_iterations = o->cfg.max_num_iterations[level];
+    opt.function_tolerance = o->cfg.function_tolerance[level];
+    opt.gradient_tolerance = o->cfg.gradient_tolerance[level];
+    opt.parameter_tolerance = o->cfg.parameter_tolerance[level];
+    opt.initial_trust_region_radius = o->cfg.initial_trust_region_radius[level];
+    opt.max_trust_region_radius = o->cfg.max_trust_region_radius[level];
+    opt.min_trust_region_radius = o->cfg.min_trust_region_radius[level];
+    opt.min_relative_decrease = o->cfg.min_relative_decrease[level];
+    o->iters_per_level[level] = pho_lm_minimize(&opt, ceres_level_eval, &ctx, ceres_level_entry, o, level, o->state);
+    free(ctx.res); free(ctx.jac);
   }
 }
 

@@ -104,6 +104,21 @@ double pho_align_batch(const phovo_config* cfg, const double K[9], int num_pairs
 
 void pho_state_to_rt(const double s[6], double rt[16]);
 
+/* ---- the restated Levenberg-Marquardt loop of Ceres mode (CE:433-500 hands each level to
+ * ceres::Solve; Ceres is third-party and absent, see the header comment), exposed so that
+ * oracle/_ref can run the same loop on the reference's OWN residual functor. ---- */
+typedef struct {
+  int max_num_iterations;                                    /* CE:465 */
+  double function_tolerance, gradient_tolerance, parameter_tolerance;          /* CE:468-470 */
+  double initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius; /* CE:471-473 */
+  double min_relative_decrease;                              /* CE:474 */
+} pho_lm_options;
+typedef void (*pho_lm_eval_fn)(void* user, const double x[6], int want_jac, double H[21], double g[6], double* cost, int* count);
+typedef phovo_iter_stats* (*pho_lm_entry_fn)(void* user);
+int pho_lm_minimize(const pho_lm_options* opt, pho_lm_eval_fn eval, void* eval_user,
+                    pho_lm_entry_fn new_entry, void* entry_user, int level, double x[6]);
+void pho_normal_equations_rowmajor(const double* jac, const double* res, size_t n, double H[21], double g[6], double* cost);
+
 #ifdef __cplusplus
 }
 #endif

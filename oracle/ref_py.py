@@ -57,6 +57,19 @@ def lib():
         L.refbi_get_state.argtypes = [vp, dp]
         L.refbi_num_iterations.argtypes = [vp]
         L.refbi_get_iteration.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, dp]
+        L.refce_create.restype = vp
+        L.refce_destroy.argtypes = [vp]
+        L.refce_read_config.argtypes = [vp, C.c_char_p]
+        L.refce_set_intrinsics.argtypes = [vp, dp]
+        L.refce_set_source.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.refce_set_target.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.refce_set_initial_state.argtypes = [vp, dp]
+        L.refce_get_state.argtypes = [vp, dp]
+        L.refce_evaluate.argtypes = [vp, C.c_int, dp, dp, dp]
+        L.refce_evaluate.restype = C.c_int
+        L.refce_optimize.argtypes = [vp]
+        L.refce_num_iter_stats.argtypes = [vp]
+        L.refce_get_iter_stats.argtypes = [vp, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -140,6 +153,59 @@ class ReferenceBiObjective:
             self.L.refbi_get_iteration(self.h, i, C.byref(n), _dp(H), _dp(g))
             iters.append(dict(n=n.value, H=H.reshape(6, 6), g=g))
         return s, iters
+
+
+class ReferenceCeres:
+    """The reference's Ceres-based solver class (CPhotoconsistencyOdometryCeres.h) with ITS residual
+    functor and sampler (third_party/sample.h, jet_extras.h), compiled unmodified against the
+    ceres::Jet / ceres::Problem stand-ins of oracle/shim/ceres.  Ceres' minimiser is absent:
+    evaluate() pins residuals + Jacobians; optimize() runs the oracle's restated LM on that functor."""
+
+    def __init__(self, config_yaml, K):
+        self.L = lib()
+        self.h = self.L.refce_create()
+        self.L.refce_read_config(self.h, os.fsencode(config_yaml))
+        self.K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        self.L.refce_set_intrinsics(self.h, _dp(self.K))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refce_destroy(self.h)
+            self.h = None
+
+    def set_frames(self, gray0, depth0, gray1):
+        g0 = np.ascontiguousarray(gray0, dtype=np.uint8)
+        d0 = np.ascontiguousarray(depth0, dtype=np.float64)
+        g1 = np.ascontiguousarray(gray1, dtype=np.uint8)
+        r, c = g0.shape
+        self.L.refce_set_source(self.h, g0.ctypes.data, d0.ctypes.data, r, c)
+        self.L.refce_set_target(self.h, g1.ctypes.data, r, c)
+
+    def evaluate(self, level_shape, state, want_jacobian=True):
+        """Residuals (rows x cols) and Jacobian (rows*cols x 6) of the level with that shape at `state`:
+        the reference functor on T = Jet<double,6> (or on T = double when want_jacobian is False)."""
+        n = int(level_shape[0]) * int(level_shape[1])
+        st = np.ascontiguousarray(state, dtype=np.float64)
+        res = np.zeros(n)
+        jac = np.zeros((n, 6)) if want_jacobian else None
+        ok = self.L.refce_evaluate(self.h, n, _dp(st), _dp(res), _dp(jac) if want_jacobian else None)
+        if not ok:
+            raise RuntimeError("no optimised level with %d pixels in this configuration" % n)
+        return res.reshape(level_shape), jac
+
+    def optimize(self, state0=None):
+        import oracle_py
+        s0 = np.zeros(6) if state0 is None else np.ascontiguousarray(state0, dtype=np.float64)
+        self.L.refce_set_initial_state(self.h, _dp(s0))
+        self.L.refce_optimize(self.h)
+        s = np.zeros(6)
+        self.L.refce_get_state(self.h, _dp(s))
+        log = []
+        for i in range(self.L.refce_num_iter_stats(self.h)):
+            e = oracle_py.IterStats()
+            self.L.refce_get_iter_stats(self.h, i, C.addressof(e))
+            log.append(e.as_dict())
+        return s, log
 
 
 def warp_image(gray, depth, rt, K):

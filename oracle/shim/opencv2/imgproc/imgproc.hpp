@@ -50,12 +50,15 @@ template< class T >
 class Mat_
 {
 public:
-  Mat_() : rows( 0 ), cols( 0 ) {}
+  typedef T value_type;
+  Mat_() : rows( 0 ), cols( 0 ), data( 0 ), step( 0 ) {}
   Mat_( int r, int c ) { create( r, c ); }
   void create( int r, int c )
   {
     rows = r; cols = c;
     m_Buf.reset( new std::vector< T >( size_t( r ) * size_t( c ), T( 0 ) ) );
+    data = reinterpret_cast< unsigned char * >( m_Buf->data() );
+    step = size_t( c ) * sizeof( T );
   }
   static Mat_ zeros( int r, int c ) { return Mat_( r, c ); }
   bool empty() const { return !m_Buf || m_Buf->empty(); }
@@ -75,6 +78,8 @@ public:
     dst = out;
   }
   int rows, cols;
+  unsigned char * data;   // cv::Mat's raw view: first byte and row stride in bytes (always continuous here)
+  size_t step;
 private:
   std::shared_ptr< std::vector< T > > m_Buf;
 };
