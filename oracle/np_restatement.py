@@ -16,8 +16,19 @@ except Exception:  # pragma: no cover - cv2 exists in the build container; the G
 
 
 def build_pyramids(gray0, depth0, gray1, num_levels, blur, grad_scale):
-    """AN:466-491 replayed through cv2 (same calls as the reference makes in C++)."""
+    """AN:466-491 replayed through cv2 (same calls as the reference makes in C++), on OpenCV's portable
+    C++ code path: the IPP / SIMD dispatch of this particular cv2 build rounds differently in the last bit
+    (and does not go through single precision on border cells of the half-size resize)."""
     assert cv2 is not None
+    was_optimized = cv2.useOptimized()
+    cv2.setUseOptimized(False)
+    try:
+        return _build_pyramids(gray0, depth0, gray1, num_levels, blur, grad_scale)
+    finally:
+        cv2.setUseOptimized(was_optimized)
+
+
+def _build_pyramids(gray0, depth0, gray1, num_levels, blur, grad_scale):
     a0 = gray0.astype(np.float64) * (1. / 255)        # convertTo(CV_64F, 1./255)
     a1 = gray1.astype(np.float64) * (1. / 255)
     I0, D0, I1, Gx, Gy = [], [], [], [], []

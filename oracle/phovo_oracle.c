@@ -62,8 +62,47 @@ static void linear_axis(int d, double scale, int ssize, int* s0, float* w1, int 
   *w1 = f;
 }
 
+/* cv::resize by EXACTLY one half: imgproc/resize.cpp switches INTER_LINEAR to INTER_AREA when both
+ * integer scale factors are 2 ("if( interpolation == INTER_LINEAR && is_area_fast && iscale_x == 2 &&
+ * iscale_y == 2 ) interpolation = INTER_AREA") and runs resizeAreaFast_Invoker<double, double>:
+ *   whole 2x2 cells : sum = ((S[0,0] + S[0,1]) + S[1,0]) + S[1,1], D = sum * 0.25f
+ *   cells cut by the right / bottom edge (output size is cvRound(size / 2), so sizes = 3 mod 4 have
+ *   them): the taps inside the image are summed in raster order and D = (float)sum / count -- in
+ *   SINGLE precision.
+ * Pinned bit for bit against cv2 with cv2.setUseOptimized(False) (plain C++ path; the IPP / SIMD
+ * dispatch of a particular build rounds differently), tests/test_oracle_pins.py. */
+static void resize_half_area(const double* src, int rows, int cols, int orows, int ocols, double* dst) {
+  const int dwidth1 = cols / 2;
+  for (int dy = 0; dy < orows; ++dy) {
+    double* D = dst + (size_t)dy * ocols;
+    const int sy0 = dy * 2;
+    const int w = sy0 + 2 <= rows ? dwidth1 : 0;
+    if (sy0 >= rows) { for (int dx = 0; dx < ocols; ++dx) D[dx] = 0; continue; }
+    int dx = 0;
+    for (; dx < w; ++dx) {
+      const double* S = src + (size_t)sy0 * cols + 2 * dx;
+      double sum = 0;
+      sum += S[0] + S[1] + S[cols] + S[cols + 1];
+      D[dx] = sum * 0.25f;
+    }
+    for (; dx < ocols; ++dx) {
+      double sum = 0; int count = 0; const int sx0 = 2 * dx;
+      for (int sy = 0; sy < 2; ++sy) {
+        if (sy0 + sy >= rows) break;
+        const double* S = src + (size_t)(sy0 + sy) * cols + sx0;
+        for (int sx = 0; sx < 2; ++sx) {
+          if (sx0 + sx >= cols) break;
+          sum += S[sx]; count++;
+        }
+      }
+      D[dx] = (double)((float)sum / count);
+    }
+  }
+}
+
 /* AN:132, default interpolation INTER_LINEAR, always from the ORIGINAL image (not iterative).
- * For the exact factor 2^-level the taps are the central 2x2 of each 2^level cell, weights .5. */
+ * For the exact factor 2^-level, level >= 2, the taps are the central 2x2 of each 2^level cell,
+ * weights .5; level 1 takes OpenCV's area path (above). */
 void pho_resize_level(const double* src, int rows, int cols, int level, double* dst) {
   int orows, ocols;
   pho_level_size(rows, cols, level, &orows, &ocols);
@@ -71,6 +110,7 @@ void pho_resize_level(const double* src, int rows, int cols, int level, double* 
     memcpy(dst, src, sizeof(double) * (size_t)rows * cols);
     return;
   }
+  if (level == 1) { resize_half_area(src, rows, cols, orows, ocols, dst); return; }
   double scale = 1.;
   for (int l = 0; l < level; ++l) scale *= 2.; /* 1 / inv_scale, inv_scale = factor exactly */
   int* xofs = (int*)malloc(sizeof(int) * ocols);

@@ -45,7 +45,9 @@ template<> struct DepthCode< unsigned short > { enum { value = CV_16U }; };
 template<> struct DepthCode< float > { enum { value = CV_32F }; };
 template<> struct DepthCode< double > { enum { value = CV_64F }; };
 
-// Reference-counted dense row-major image: copies are shallow, like cv::Mat.
+// Reference-counted dense row-major image: copies are shallow, like cv::Mat.  `data` / `step` are
+// cv::Mat's raw view (first byte, row stride in BYTES); create() can leave padding behind every row
+// so that strided inputs can be exercised (images made by the stand-in's own functions are continuous).
 template< class T >
 class Mat_
 {
@@ -53,36 +55,49 @@ public:
   typedef T value_type;
   Mat_() : rows( 0 ), cols( 0 ), data( 0 ), step( 0 ) {}
   Mat_( int r, int c ) { create( r, c ); }
-  void create( int r, int c )
+  void create( int r, int c, size_t rowBytes = 0 )
   {
     rows = r; cols = c;
-    m_Buf.reset( new std::vector< T >( size_t( r ) * size_t( c ), T( 0 ) ) );
+    step = rowBytes ? rowBytes : size_t( c ) * sizeof( T );
+    m_Buf.reset( new std::vector< T >( ( step * size_t( r ) + sizeof( T ) - 1 ) / sizeof( T ), T( 0 ) ) );
     data = reinterpret_cast< unsigned char * >( m_Buf->data() );
-    step = size_t( c ) * sizeof( T );
   }
   static Mat_ zeros( int r, int c ) { return Mat_( r, c ); }
   bool empty() const { return !m_Buf || m_Buf->empty(); }
+  bool isContinuous() const { return step == size_t( cols ) * sizeof( T ); }
   int type() const { return DepthCode< T >::value; }
   T * ptr() { return m_Buf ? m_Buf->data() : 0; }
   const T * ptr() const { return m_Buf ? m_Buf->data() : 0; }
-  T & operator()( int r, int c ) { return ( *m_Buf )[ size_t( r ) * size_t( cols ) + size_t( c ) ]; }
-  const T & operator()( int r, int c ) const { return ( *m_Buf )[ size_t( r ) * size_t( cols ) + size_t( c ) ]; }
-  T & operator()( int i ) { return ( *m_Buf )[ size_t( i ) ]; }
+  T & operator()( int r, int c ) { return *reinterpret_cast< T * >( data + step * size_t( r ) + sizeof( T ) * size_t( c ) ); }
+  const T & operator()( int r, int c ) const { return *reinterpret_cast< const T * >( data + step * size_t( r ) + sizeof( T ) * size_t( c ) ); }
+  T & operator()( int i ) { return ( *m_Buf )[ size_t( i ) ]; }                 // continuous images only
   const T & operator()( int i ) const { return ( *m_Buf )[ size_t( i ) ]; }
   // Mat::convertTo(dst, rtype, alpha): dst = saturate_cast<U>( src * alpha ); floating destinations only here
   template< class U >
   void convertTo( Mat_< U > & dst, int /*rtype*/, double alpha = 1. ) const
   {
     Mat_< U > out( rows, cols );
-    for( size_t k = 0; k < size_t( rows ) * size_t( cols ); k++ ) out( int( k ) ) = U( double( ( *m_Buf )[k] ) * alpha );
+    for( int r = 0; r < rows; r++ )
+      for( int c = 0; c < cols; c++ ) out( r, c ) = U( double( ( *this )( r, c ) ) * alpha );
     dst = out;
   }
   int rows, cols;
-  unsigned char * data;   // cv::Mat's raw view: first byte and row stride in bytes (always continuous here)
+  unsigned char * data;
   size_t step;
 private:
   std::shared_ptr< std::vector< T > > m_Buf;
 };
+
+// MatExpr of the apps (FrameAlignment.cpp:77,81: `img = img * 1. / 1000.`): OpenCV folds `e * a` into a
+// scale factor and `e / b` into `e * (1 / b)`, then evaluates once; the stand-in evaluates eagerly with
+// the same roundings for that expression (x * 1. is exact).
+template< class T > inline Mat_< T > operator*( const Mat_< T > & a, double s )
+{
+  Mat_< T > out( a.rows, a.cols );
+  for( int r = 0; r < a.rows; r++ ) for( int c = 0; c < a.cols; c++ ) out( r, c ) = T( double( a( r, c ) ) * s );
+  return out;
+}
+template< class T > inline Mat_< T > operator/( const Mat_< T > & a, double s ) { return a * ( 1. / s ); }
 
 inline void resize( const Mat_< double > & src, Mat_< double > & dst, Size /*dsize*/, double fx, double /*fy*/ )
 {

@@ -80,6 +80,13 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
     s0 = 4u * (unsigned)__ldg(G0 + o00);
     s1 = 4u * (unsigned)__ldg(G1 + o00);
     dv = depth_at<DT>(D + o00, depth_scale);
+  } else if (level == 1) {
+    // cv::resize by exactly 1/2 takes the INTER_AREA path: ((S00 + S01) + S10) + S11 times 0.25
+    // (kernels_pyramid.cu: level_value).  Sizes with cells cut by the border are rejected by the host.
+    s0 = (unsigned)__ldg(G0 + o00) + __ldg(G0 + o00 + 1) + __ldg(G0 + o10) + __ldg(G0 + o10 + 1);
+    s1 = (unsigned)__ldg(G1 + o00) + __ldg(G1 + o00 + 1) + __ldg(G1 + o10) + __ldg(G1 + o10 + 1);
+    dv = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(depth_at<DT>(D + o00, depth_scale), depth_at<DT>(D + o00 + 1, depth_scale)),
+                                       depth_at<DT>(D + o10, depth_scale)), depth_at<DT>(D + o10 + 1, depth_scale)), 0.25);
   } else if (two) {
     s0 = (unsigned)__ldg(G0 + o00) + __ldg(G0 + o00 + 1) + __ldg(G0 + o10) + __ldg(G0 + o10 + 1);
     s1 = (unsigned)__ldg(G1 + o00) + __ldg(G1 + o00 + 1) + __ldg(G1 + o10) + __ldg(G1 + o10 + 1);

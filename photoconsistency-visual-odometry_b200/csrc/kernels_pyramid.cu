@@ -1,6 +1,7 @@
 // kernels_pyramid.cu -- frame setup for the general (any resolution, any config) path:
 // K1 pyramid level from the full-resolution source, K2b Gaussian blur, K2 Scharr.  All level images are fp64, bit-identical
-// to the reference's cv::Mat_<double> pyramids (same operation order, no FMA contraction).
+// to the reference's cv::Mat_<double> pyramids as OpenCV's portable C++ code computes them (same
+// operation order, no FMA contraction; pinned against cv2 with its IPP / SIMD dispatch switched off).
 // Replaces CPhotoconsistencyOdometryAnalytic.h:115-189 (BuildPyramid / BuildDerivativesPyramids).
 // The batched path has its own fused, shared-memory version (kernels_batch.cu).
 #include <math.h>
@@ -45,15 +46,32 @@ __device__ __forceinline__ void linear_axis(int d, double scale, int ssize, bool
   s0 = s; w1 = f;
 }
 
-// K1.  One thread per output pixel.  For the exact factor 2^-level the four taps are the central
-// 2x2 of the pixel's 2^level cell with weights 1/2 (horizontal pair first, then vertical) --
-// cv::resize INTER_LINEAR from the ORIGINAL image, AN:132.  A warp reads one contiguous span of
+// K1.  One thread per output pixel.  For the exact factor 2^-level, level >= 2, the four taps are the
+// central 2x2 of the pixel's 2^level cell with weights 1/2 (horizontal pair first, then vertical) --
+// cv::resize INTER_LINEAR from the ORIGINAL image, AN:132; level 1 is OpenCV's area path (below).  A warp reads one contiguous span of
 // each of two source rows, so every 32-byte sector fetched is used by the warp.
 // value of level pixel (y, x): the conversion of the source pixel at level 0, else cv::resize's four taps
 template <typename T>
 __device__ __forceinline__ double level_value(const void* __restrict__ src, size_t step, double src_scale,
                                               int rows, int cols, int level, double scale, int y, int x) {
   if (level == 0) return load_src<T>(src, step, y, x, src_scale);
+  if (level == 1) {
+    // cv::resize by exactly 1/2 is NOT bilinear: resize.cpp switches INTER_LINEAR to INTER_AREA when
+    // both integer scale factors are 2 (resizeAreaFast_Invoker<double,double>): a whole 2x2 cell is
+    // ((S00 + S01) + S10) + S11 times 0.25f; a cell cut by the right / bottom edge (sizes = 3 mod 4:
+    // the output size is cvRound(size / 2)) sums its taps inside the image in raster order and
+    // divides by their count IN SINGLE PRECISION ((float)sum / count).
+    const int sy0 = 2 * y, sx0 = 2 * x;
+    if (sy0 + 2 <= rows && x < cols / 2) {
+      const double a = load_src<T>(src, step, sy0, sx0, src_scale), b = load_src<T>(src, step, sy0, sx0 + 1, src_scale);
+      const double c = load_src<T>(src, step, sy0 + 1, sx0, src_scale), d = load_src<T>(src, step, sy0 + 1, sx0 + 1, src_scale);
+      return __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a, b), c), d), 0.25);
+    }
+    double sum = 0.; int count = 0;
+    for (int sy = 0; sy < 2 && sy0 + sy < rows; ++sy)
+      for (int sx = 0; sx < 2 && sx0 + sx < cols; ++sx) { sum = __dadd_rn(sum, load_src<T>(src, step, sy0 + sy, sx0 + sx, src_scale)); ++count; }
+    return (double)__fdiv_rn(__double2float_rn(sum), (float)count);
+  }
   int sx, sy; float fx, fy;
   linear_axis(x, scale, cols, true, sx, fx);
   linear_axis(y, scale, rows, false, sy, fy);

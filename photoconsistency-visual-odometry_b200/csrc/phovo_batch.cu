@@ -118,6 +118,10 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
     if (ctx->cfg.max_num_iterations[level] <= 0) continue;
     if (ctx->cfg.blur_filter_size[level] > 1) return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: blurFilterSize > 0 is only supported by the per-pair API");
+    // cv::resize by 1/2 averages cells cut by the image border in single precision (sizes = 3 mod 4):
+    // not representable in the exact integer tap sums the batch records keep
+    if (level == 1 && (rows % 4 == 3 || cols % 4 == 3))
+      return ctx->fail(PHOVO_E_UNSUPPORTED, "batch kernel: level 1 of an image whose size is 3 mod 4 is only supported by the per-pair API");
     int lr, lc;
     level_size(rows, cols, level, &lr, &lc);
     if (lr < 1 || lc < 1) return ctx->fail(PHOVO_E_INVALID, "image too small for the number of pyramid levels");

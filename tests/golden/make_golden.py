@@ -25,6 +25,8 @@ synth = importlib.import_module("photoconsistency-visual-odometry_b200.synth")
 
 
 def golden_cv2_ops():
+    # OpenCV's portable C++ code path (what "OpenCV >= 2.4.5" pins); this build's IPP kernels round differently
+    cv2.setUseOptimized(False)
     rng = np.random.default_rng(11)
     out = {}
     for tag, shape in (("a", (48, 64)), ("b", (45, 77))):
@@ -38,6 +40,7 @@ def golden_cv2_ops():
         out[tag + "_blur3"] = cv2.GaussianBlur(a, (3, 3), 3)
         out[tag + "_blur5"] = cv2.GaussianBlur(a, (5, 5), 3)
     np.savez_compressed(os.path.join(HERE, "cv2_ops.npz"), **out)
+    cv2.setUseOptimized(True)
 
 
 def golden_pair(name, rows, cols, K, levels, iters, min_grad, xi, seed, fixed):

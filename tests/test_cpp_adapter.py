@@ -1,6 +1,13 @@
-"""The C++ drop-in adapter (include/CPhotoconsistencyOdometryCuda.h) driven the way the reference
-apps drive the analytic solver (tests/cpp/frame_alignment_app.cpp mirrors both main()s), checked
-against the CPU oracle.  The binary is compiled against stand-in cv::/Eigen types (tests/cpp/shim)."""
+"""The C++ drop-in adapter (include/CPhotoconsistencyOdometryCuda.h), compiled against the REFERENCE'S OWN
+abstract class and matrix types (/root/reference/phovo/include/CPhotoconsistencyOdometry.h + Matrix.h,
+unmodified; only OpenCV / Eigen are the stand-ins of oracle/shim), checked against the CPU oracle:
+
+  * tests/cpp/frame_alignment_app.cpp -- headless mirror of both apps' main() (strided cv::Mat_ inputs,
+    the VO loop, warpImage through the adapter);
+  * the reference's apps/PhotoconsistencyFrameAlignment/PhotoconsistencyFrameAlignment.cpp ITSELF with
+    exactly the INTEGRATION.md patch applied (USE_PHOTOCONSISTENCY_ODOMETRY_METHOD == 3), built by
+    tests/cpp/build_adapter_test.sh into tests/cpp/_build/ (git-ignored; travels to the GPU box).
+"""
 import os
 import subprocess
 
@@ -12,6 +19,7 @@ from test_gpu_parity import conv_cfg
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 APP = os.path.join(ROOT, "tests", "cpp", "_build", "frame_alignment_app")
+REF_APP = os.path.join(ROOT, "tests", "cpp", "_build", "reference_frame_alignment")
 
 
 def build_app():
@@ -29,6 +37,67 @@ def test_adapter_compiles_and_fails_loudly_without_gpu(phovo, tmp_path):
     args = [app, "align", cfg, "4", "4", "1", "1", "1", "1", "a", "b", "c", "d"]
     r = subprocess.run(args, capture_output=True, text=True)
     assert r.returncode == 3 and "phovo_create" in r.stderr and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+
+
+def write_pgm(path, img):
+    """Binary PGM, 8 bit or 16 bit big endian: the one format the stand-in cv::imread reads."""
+    img = np.ascontiguousarray(img)
+    maxval = 255 if img.dtype == np.uint8 else 65535
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n%d\n" % (img.shape[1], img.shape[0], maxval))
+        f.write(img.tobytes() if img.dtype == np.uint8 else img.astype(">u2").tobytes())
+
+
+def reference_app_inputs(phovo, tmp_path, seed):
+    """Frames for the reference app's own main(): 8-bit gray + 16-bit depth in millimetres, which it
+    scales with `img * 1. / 1000.` (FrameAlignment.cpp:74-81).  Returns the doubles it ends up with."""
+    K = phovo.synth.K_FRAME_ALIGNMENT                       # hard-coded in the app (FrameAlignment.cpp:69-71)
+    g0, d0, g1, d1 = phovo.synth.make_pair(480, 640, K=K, seed=seed)
+    mm0, mm1 = np.rint(d0 * 1000.).astype(np.uint16), np.rint(d1 * 1000.).astype(np.uint16)
+    paths = [str(tmp_path / n) for n in ("gray0.pgm", "depth0.pgm", "gray1.pgm", "depth1.pgm")]
+    for p, img in zip(paths, (g0, mm0, g1, mm1)):
+        write_pgm(p, img)
+    return K, g0, mm0.astype(np.float64) * (1. / 1000.), g1, paths
+
+
+def test_reference_app_with_the_integration_patch_builds_and_fails_loudly_without_gpu(phovo, tmp_path):
+    """The reference's own FrameAlignment main() + the METHOD == 3 branch compiles against the real
+    CPhotoconsistencyOdometry.h / Matrix.h; without a device the adapter's constructor throws (the app
+    has no handler: it terminates, it does not fall back to anything)."""
+    build_app()
+    assert os.access(REF_APP, os.X_OK)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    K, g0, d0, g1, paths = reference_app_inputs(phovo, tmp_path, 22)
+    yml = phovo.configs.write_yaml("config_4_level_optimization_analytic", str(tmp_path))
+    r = subprocess.run([REF_APP, yml] + paths, capture_output=True, text=True)
+    assert r.returncode != 0 and "phovo_create" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_reference_frame_alignment_app_method_3_matches_oracle(phovo, oracle, tmp_path):
+    """apps/PhotoconsistencyFrameAlignment/PhotoconsistencyFrameAlignment.cpp, unmodified but for the
+    INTEGRATION.md patch, run on the GPU: the Rt it prints (:109-110) equals the oracle's."""
+    build_app()
+    K, g0, d0, g1, paths = reference_app_inputs(phovo, tmp_path, 22)
+    name = "config_4_level_optimization_analytic"
+    yml = phovo.configs.write_yaml(name, str(tmp_path))
+    r = subprocess.run([REF_APP, yml] + paths, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    at = lines.index("main::Rt eigen:")
+    Rt = np.array([[float(x) for x in ln.split()] for ln in lines[at + 1:at + 5]])
+    assert any(ln.startswith("Time = ") for ln in lines)
+    cfg = phovo.configs.to_config(name, phovo.capi)
+    o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+    o.set_source(g0, d0)
+    o.set_target(g1)
+    o.set_initial_state(np.zeros(6))
+    o.optimize()
+    assert len(o.iter_stats()) > 0
+    assert np.max(np.abs(Rt - o.rt())) < 1e-10
+    assert np.max(np.abs(Rt[:3, 3] - o.state()[:3])) < 1e-10
 
 
 @pytest.mark.gpu
