@@ -11,9 +11,15 @@ gradient-norm stop at 300), sharded by pair across the GPUs: every rank aligns `
             every pair and the D2H read of the poses are inside the timed region
   roofline: the dominant kernel (k_batch_level, one launch per active level) -- algorithmic bytes per SURVEY 8(d)
             (20 B/px per executed GN iteration + 216 B of sums) / its CUDA-event time, against the
-            measured HBM copy bandwidth in MEASURED_PEAKS.json
+            measured HBM copy bandwidth in MEASURED_PEAKS.json; the kernel is bound by the FP64 pipe
+            (`bound: "fp64"`, `roofline.fp64`), the HBM figure is the contract's number
   cpu_baseline / --impl reference: the CPU oracle (faithful port of the reference's analytic path,
-            the reference itself cannot be built here: no OpenCV/Eigen) on the host cores.
+            the reference itself cannot be built here: no OpenCV/Eigen) on the host cores
+  secondary: (N = 1) the other BASELINE configs measured in the same run, each with its own clock
+            samples and the CPU oracle beside it: one 640x480 pair through SetSourceFrame ->
+            SetTargetFrame -> Optimize from host buffers (configs[0]), the VO loop per frame
+            (configs[1]), config_5_level_optimization_ceres (configs[2]), the 7680x4320 pair on one
+            GPU (configs[4]).  What the reference times: FrameAlignment.cpp:99-101, VisualOdometry.cpp:227-230.
 
 One JSON line on stdout (rank 0).
 """
@@ -131,9 +137,26 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def algorithmic_bytes(cfg, iters, rows, cols):
-    """SURVEY 8(d): 20 B/px per executed GN iteration at a level of N px + 216 B out per iteration;
-    frame setup 1 843 200 B in + 5 images x active px x 4 B out per pair."""
+def rows_read_fraction(cfg, rows):
+    """Fraction of the source rows the active pyramid levels tap: level l >= 1 is decimated from the ORIGINAL
+    image and reads the two central rows of each 2^l-row cell (AN:132), level 0 reads every row."""
+    need = set()
+    for lvl in range(cfg.num_levels):
+        if cfg.max_num_iterations[lvl] <= 0:
+            continue
+        if lvl == 0:
+            return 1.0
+        cell = 1 << lvl
+        for y in range(int(round(rows * 0.5 ** lvl))):
+            need.update((min(y * cell + cell // 2 - 1, rows - 1), min(y * cell + cell // 2, rows - 1)))
+    return len(need) / float(rows)
+
+
+def algorithmic_bytes(cfg, iters, rows, cols, depth_bytes):
+    """20 B/px per executed GN iteration at a level of N px + 216 B out per iteration.
+    Frame set-up (k_batch_pyramid): the COMPULSORY traffic -- the source rows the active levels tap of
+    gray0, gray1 (1 B/px) and depth0 (`depth_bytes` B/px; whole 32-byte sectors, so every column of such
+    a row counts) in, the packed record (f64 D0 + u16 I0 + u16 I1 = 12 B per active-level pixel) out."""
     import numpy as np
     total_iter_bytes, active_px = 0.0, 0
     for lvl in range(cfg.num_levels):
@@ -142,7 +165,7 @@ def algorithmic_bytes(cfg, iters, rows, cols):
         n = int(round(rows * 0.5 ** lvl)) * int(round(cols * 0.5 ** lvl))
         active_px += n
         total_iter_bytes += float(np.sum(iters[:, lvl])) * (20.0 * n + 216.0)
-    setup = iters.shape[0] * (2.0 * rows * cols + 4.0 * rows * cols + 5.0 * 4.0 * active_px)
+    setup = iters.shape[0] * (rows_read_fraction(cfg, rows) * rows * cols * (2.0 + depth_bytes) + 12.0 * active_px)
     return total_iter_bytes, setup
 
 
@@ -153,6 +176,14 @@ def quantise_depth(d_metres):
     """metres -> raw u16 sensor units, the format both reference apps read from disk."""
     import numpy as np
     return np.clip(np.rint(d_metres * 5000.), 0, 65535).astype(np.uint16)
+
+
+def oracle_config(phovo, name):
+    """The named reference configuration as the ORACLE's POD (same layout as phovo_config) -- built without
+    touching capi, so the CPU arm never maps libphovo_b200.so."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    return phovo.configs.to_config(name, oracle_py)
 
 
 def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False, depth="u16"):
@@ -170,7 +201,7 @@ def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False, depth="u1
     reps = (pairs + distinct - 1) // distinct
     g0, d0, g1 = (np.tile(a, (reps, 1, 1))[:pairs] for a in (g0, d0, g1))
     raw = np.tile(raw, (reps, 1, 1))[:pairs] if raw is not None else None
-    cfg = oracle_py.Config.from_buffer_copy(bytes(phovo.configs.to_config(CONFIG, phovo.capi)))
+    cfg = oracle_config(phovo, CONFIG)
     times, opt_times = [], []
     for s in range(warmup + steps):
         st, it, wall, opt = oracle_py.align_batch(cfg, K, g0, d0, g1, num_threads=threads, lean=lean)
@@ -179,7 +210,176 @@ def cpu_reference(phovo, K, pairs, threads, steps, warmup, lean=False, depth="u1
             opt_times.append(opt)
     wall = float(np.mean(times))
     return {"value": pairs / wall, "ms_per_step": wall * 1e3, "optimize_only_pairs_per_core_s": pairs / float(np.mean(opt_times)),
-            "states": st, "iters": it, "inputs": (g0, d0, g1), "raw_depth": raw}
+            "states": st, "iters": it, "inputs": (g0, d0, g1), "raw_depth": raw,
+            "mean_iterations_per_pair": {str(l): float(it[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0}}
+
+
+def workload_config(pairs_per_gpu, depth, world):
+    """`config` of the JSON line: the workload and nothing measured, identical in both arms."""
+    return {"workload": "batched independent 640x480 RGB-D pairs, %s (BASELINE configs[3]), %d pairs per GPU per step" % (CONFIG, pairs_per_gpu),
+            "pairs_per_gpu": pairs_per_gpu, "rows": ROWS, "cols": COLS,
+            "depth_dtype": "u16 raw x 1/5000 m" if depth == "u16" else "f32 metres",
+            "parallelism": "pairs sharded x%d, final pose all_gather" % world,
+            "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (pairs_per_gpu * ROWS * COLS * (2 + (2 if depth == "u16" else 4)) / 1e9)}
+
+
+def pinned_h2d_peak(torch, dev, stream, nbytes=1 << 30, reps=5):
+    """Best-of-`reps` bandwidth of one cudaMemcpyAsync of `nbytes` from pinned host memory to the device:
+    the ceiling `e2e` can be compared with (measured in this run, on this rank's link)."""
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host.fill_(1)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(reps + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        buf.copy_(host, non_blocking=True)
+        b.record(stream)
+        b.synchronize()
+        best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+    del host, buf
+    return best
+
+
+def median(xs):
+    import numpy as np
+    return float(np.median(xs)) if len(xs) else None
+
+
+def secondary_block(phovo, torch, dev, local_rank, frames):
+    """BASELINE configs[0], [1], [2] and [4] through the reference-facing per-pair API, host buffers in -> pose
+    out, each under its own clock sampler, with the single-threaded CPU oracle (the reference is single-threaded)
+    on the same inputs.  Device times are CUDA events recorded by the library around the frame set-up
+    (uploads + pyramid kernels) and around Optimize() -- what the apps' TickMeter brackets."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle_py
+    oracle_py.build()
+    out = {}
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    def timed_alignments(odo, src, tgt, reps, warm):
+        setup, opt, wall = [], [], []
+        sampler = ClockSampler(local_rank)
+        for rep in range(warm + reps):
+            if rep == warm:
+                sampler.start()
+            t0 = time.perf_counter()
+            odo.SetSourceFrame(*src)
+            odo.SetTargetFrame(tgt)
+            odo.SetInitialStateVector(np.zeros(6))
+            odo.Optimize()
+            s = odo.GetOptimalStateVector()
+            t1 = time.perf_counter()
+            if rep >= warm:
+                a, b = odo.Timings()
+                setup.append(a); opt.append(b); wall.append((t1 - t0) * 1e3)
+        return s, setup, opt, wall, sampler.stop()
+
+    def oracle_alignment(cfg_name, K, g0, d0, g1, reps):
+        o = oracle_py.Oracle(oracle_config(phovo, cfg_name), K)
+        t_opt, t_all = [], []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            o.set_source(g0, d0); o.set_target(g1); o.set_initial_state(np.zeros(6))
+            t1 = time.perf_counter()
+            o.optimize()
+            t2 = time.perf_counter()
+            t_opt.append((t2 - t1) * 1e3); t_all.append((t2 - t0) * 1e3)
+        return o, median(t_opt), median(t_all)
+
+    # ---- configs[0]: PhotoconsistencyFrameAlignment, one 640x480 pair (depth cv::Mat_<double>, like the app)
+    for key, cfg_name, reps, what in (
+            ("single_pair_640x480", CONFIG, 200, "BASELINE configs[0]: PhotoconsistencyFrameAlignment, one 640x480 pair, 4-level analytic"),
+            ("ceres_config_640x480", "config_5_level_optimization_ceres", 30, "BASELINE configs[2]: config_5_level_optimization_ceres on a 640x480 pair (levels 0 and 1 optimised); LM restated, Ceres itself absent")):
+        K = phovo.synth.K_FRAME_ALIGNMENT
+        g0, d0, g1, _ = phovo.synth.make_pair(ROWS, COLS, K=K, seed=0)
+        odo = phovo.CPhotoconsistencyOdometryCuda(device=local_rank)
+        odo.SetConfig(phovo.configs.to_config(cfg_name, phovo.capi)); odo.SetIntrinsicMatrix(K)
+        l0 = odo.LaunchCount()
+        s, setup, opt, wall, clocks = timed_alignments(odo, (pin(g0), pin(d0)), pin(g1), reps, 5)
+        launches = (odo.LaunchCount() - l0) / float(reps + 5)
+        log = odo.IterationStats()
+        o, cpu_opt, cpu_all = oracle_alignment(cfg_name, K, g0, d0, g1, 3)
+        out[key] = {"what": what, "iterations": len(log), "driver": odo.LastPath(), "reps": reps,
+                    "optimize_ms_device": median(opt), "setup_ms_device": median(setup), "host_in_pose_out_ms_wall": median(wall),
+                    "host_in_pose_out_ms_wall_p99": float(np.percentile(wall, 99)), "kernel_launches_per_alignment": launches,
+                    "h2d_bytes_per_alignment": int(g0.nbytes + g1.nbytes + d0.nbytes),
+                    "cpu_oracle": {"optimize_ms": cpu_opt, "setframes_plus_optimize_ms": cpu_all, "cores": 1, "kind": "port"},
+                    "iterations_equal_cpu": len(log) == len(o.iter_stats()), "pose_abs_diff_vs_cpu": float(np.max(np.abs(s - o.state()))),
+                    "clocks": clocks}
+        odo.close()
+
+    # ---- configs[1]: PhotoconsistencyVisualOdometry loop, sequential, per-frame latency
+    K = phovo.synth.K_VISUAL_ODOMETRY
+    name = "config_5_level_optimization_analytic"
+    gray, depth = phovo.synth.render_sequence_torch(frames, ROWS, COLS, K, dev)
+    hg = torch.empty(gray.shape, dtype=gray.dtype, pin_memory=True); hg.copy_(gray)
+    hd = torch.empty(depth.shape, dtype=torch.float64, pin_memory=True); hd.copy_(depth.to(torch.float64))   # the app's Mat_<double>
+    del gray, depth
+    torch.cuda.synchronize(dev)
+    odo = phovo.CPhotoconsistencyOdometryCuda(device=local_rank)
+    odo.SetConfig(phovo.configs.to_config(name, phovo.capi)); odo.SetIntrinsicMatrix(K)
+    for rep in range(2):                        # first pass over a short prefix warms up
+        n = min(frames, 20) if rep == 0 else frames
+        lat, states, iters, opt = [], [], 0, []
+        sampler = ClockSampler(local_rank)
+        if rep == 1:
+            sampler.start()
+        odo.SetSourceFrame(hg[0], hd[0])
+        for k in range(1, n):
+            t0 = time.perf_counter()
+            if k > 1:
+                odo.PromoteTargetToSource(hd[k - 1])            # VisualOdometry.cpp:222,256-257 without re-uploading the gray image
+            odo.SetTargetFrame(hg[k])
+            odo.SetInitialStateVector(np.zeros(6))              # :224 (always zero, :175)
+            odo.Optimize()                                      # :227-230 is what the app times
+            states.append(odo.GetOptimalStateVector())
+            lat.append((time.perf_counter() - t0) * 1e3)
+            opt.append(odo.Timings()[1])
+            iters += len(odo.IterationStats())
+        clocks = sampler.stop() if rep == 1 else None
+    o = oracle_py.Oracle(oracle_config(phovo, name), K)
+    cpu, err, it_equal = [], 0.0, True
+    gn, dn = hg.numpy(), hd.numpy()
+    for k in range(1, min(frames, 9)):
+        t0 = time.perf_counter()
+        o.set_source(gn[k - 1], dn[k - 1]); o.set_target(gn[k]); o.set_initial_state(np.zeros(6)); o.optimize()
+        cpu.append((time.perf_counter() - t0) * 1e3)
+        err = max(err, float(np.max(np.abs(o.state() - states[k - 1]))))
+    out["vo_sequence_640x480"] = {"what": "BASELINE configs[1]: PhotoconsistencyVisualOdometry loop, %d synthetic frames, 5-level analytic, sequential on one GPU, target pyramid promoted to source between frames" % frames,
+                                  "frames": frames, "ms_per_frame_wall": median(lat), "ms_per_frame_wall_p99": float(np.percentile(lat, 99)),
+                                  "optimize_ms_device": median(opt), "frames_per_s": 1e3 / float(np.mean(lat)), "mean_iterations_per_frame": iters / float(len(lat)),
+                                  "cpu_oracle": {"ms_per_frame": median(cpu), "cores": 1, "kind": "port", "frames": len(cpu)},
+                                  "pose_abs_diff_vs_cpu_first_frames": err, "clocks": clocks}
+    odo.close()
+    del hg, hd
+
+    # ---- configs[4]: one 7680x4320 pair on ONE GPU (the row-sharded runs are `--workload 8k --gpus N`)
+    K = phovo.synth.K_8K
+    name = "config_6_level_optimization_analytic"
+    g0, d0, g1, _ = phovo.synth.render_batch_torch(1, 4320, 7680, K, dev, seed0=7, chunk=1, xis=phovo.synth.XI_CONFIG1[None])
+    hg0 = torch.empty(g0[0].shape, dtype=torch.uint8, pin_memory=True); hg0.copy_(g0[0])
+    hg1 = torch.empty(g1[0].shape, dtype=torch.uint8, pin_memory=True); hg1.copy_(g1[0])
+    hd0 = torch.empty(d0[0].shape, dtype=torch.float32, pin_memory=True); hd0.copy_(d0[0])
+    del g0, d0, g1
+    torch.cuda.synchronize(dev)
+    odo = phovo.CPhotoconsistencyOdometryCuda(device=local_rank)
+    odo.SetConfig(phovo.configs.to_config(name, phovo.capi)); odo.SetIntrinsicMatrix(K)
+    s, setup, opt, wall, clocks = timed_alignments(odo, (hg0, hd0), hg1, 10, 2)
+    log = odo.IterationStats()
+    o, cpu_opt, cpu_all = oracle_alignment(name, K, hg0.numpy(), hd0.numpy().astype(np.float64), hg1.numpy(), 1)
+    out["single_pair_7680x4320"] = {"what": "BASELINE configs[4] on one GPU: one 7680x4320 pair, config_6_level_optimization_analytic (f32 depth at the boundary)",
+                                    "iterations": len(log), "driver": odo.LastPath(), "reps": 10,
+                                    "optimize_ms_device": median(opt), "setup_ms_device": median(setup), "host_in_pose_out_ms_wall": median(wall),
+                                    "h2d_bytes_per_alignment": int(hg0.numel() + hg1.numel() + 4 * hd0.numel()),
+                                    "cpu_oracle": {"optimize_ms": cpu_opt, "setframes_plus_optimize_ms": cpu_all, "cores": 1, "kind": "port"},
+                                    "iterations_equal_cpu": len(log) == len(o.iter_stats()), "pose_abs_diff_vs_cpu": float(np.max(np.abs(s - o.state()))),
+                                    "clocks": clocks}
+    odo.close()
+    return out
 
 
 def main():
@@ -191,6 +391,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0: 2 per host thread, >= 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per-pair measurements of BASELINE configs[0], [1], [2], [4]")
+    ap.add_argument("--secondary-frames", type=int, default=1000, help="frames of the synthetic VO sequence (BASELINE configs[1])")
     ap.add_argument("--depth", default="u16", choices=["u16", "f32"],
                     help="depth format at the boundary: raw u16 sensor units x 1/5000 m (what the reference apps read, default) or f32 metres")
     args = ap.parse_args()
@@ -212,11 +414,13 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "batched independent 640x480 pairs, %s, bounded sample" % CONFIG,
-                           "pairs_per_step": pairs, "rows": ROWS, "cols": COLS, "depth_dtype": args.depth},
+                "config": workload_config(args.pairs, args.depth, args.gpus),
+                "mean_iterations_per_pair": r["mean_iterations_per_pair"],
                 "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": host_threads, "kind": "port",
-                                 "sample": "%d pairs per step, %d threads x single-threaded alignments (SetSourceFrame+SetTargetFrame+Optimize), faithful cost structure (materialised Nx6 Jacobian, per-pass setZero)" % (pairs, host_threads)},
+                                 "sample": "each step aligns a bounded sample of %d pairs of the workload (32 distinct, %d threads x single-threaded alignments: SetSourceFrame + SetTargetFrame + Optimize), faithful cost structure (materialised Nx6 Jacobian, per-pass setZero); oracle/_ref (the reference's own loop over stand-in Eigen products) is 2-3x slower than this port" % (pairs, host_threads)},
                 "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        # this arm is the CPU implementation alone: the CUDA library must not even be mapped
+        assert "libphovo_b200" not in open("/proc/self/maps").read(), "the reference arm loaded the product library"
         print(json.dumps(line))
         return 0
 
@@ -317,6 +521,15 @@ def main():
     h2d_full = P * (2 * ROWS * COLS + ROWS * COLS * d0.element_size())
     h2d = odo.BatchLastH2DBytes()          # counted by the library from the copies it issued
     d2h = P * (6 * 8 + phovo.MAXL * 4)
+    del hg0, hd0, hg1
+    h2d_peak = pinned_h2d_peak(torch, dev, stream)        # this rank's link, nothing else running on it
+    tp = torch.tensor([h2d_peak], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered_peaks = [torch.zeros_like(tp) for _ in range(world)]
+        dist.all_gather(gathered_peaks, tp)
+        h2d_peaks = [float(x.item()) for x in gathered_peaks]
+    else:
+        h2d_peaks = [h2d_peak]
 
     if rank != 0:
         if world > 1:
@@ -325,7 +538,7 @@ def main():
 
     # ---- roofline of the dominant kernel
     peak, peak_src = hbm_peak()
-    iter_bytes, setup_bytes = algorithmic_bytes(cfg, it_host, ROWS, COLS)
+    iter_bytes, setup_bytes = algorithmic_bytes(cfg, it_host, ROWS, COLS, d0.element_size())
     align_t = float(np.mean(align_ms)) * 1e-3
     pyr_t = float(np.mean(pyr_ms)) * 1e-3
     achieved = iter_bytes / align_t / 1e9
@@ -344,7 +557,7 @@ def main():
         fp64 = {"achieved": rate / 1e12, "peak": prof["fp64_peak_thread_inst_per_s"] / 1e12, "unit": "T fp64 thread-instructions/s",
                 "frac": rate / prof["fp64_peak_thread_inst_per_s"], "inst_per_px_iter": prof["fp64_thread_inst_per_px_iter"],
                 "source": "ncu op counters of %s / executed pixel-iterations; peak = %s" % (prof.get("tag"), prof.get("fp64_peak_source"))}
-    roofline = {"bound": "hbm", "kernel": "k_batch_level (one launch per active pyramid level; figures are the sum over the level launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "fp64", "kernel": "k_batch_level (one launch per active pyramid level; figures are the sum over the level launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": (prof["dram_bytes_per_pair"] * P) if prof.get("dram_bytes_per_pair") else None,
                 "traffic_source": "ncu --set full dram__bytes_read+write of one launch (%s, %d pairs) scaled by pairs" % (prof.get("tag"), prof.get("profiled_pairs", 0)) if prof else None,
@@ -352,11 +565,12 @@ def main():
                 "algorithmic_bytes_per_launch": iter_bytes, "kernel_ms": align_t * 1e3,
                 "share_of_step": align_t / (align_t + pyr_t),
                 "pixel_iterations_per_launch": px_iters,
-                "note": "algorithmic bytes = SURVEY 8(d): 20 B per pixel per executed GN iteration + 216 B of sums; the level is resident in shared memory, so DRAM traffic is the packed record read once and the binding unit is the FP64 pipe (see fp64)",
+                "note": "achieved / peak / frac are the contract's HBM figure: algorithmic bytes = SURVEY 8(d), 20 B per pixel per executed GN iteration + 216 B of sums, over the measured HBM copy bandwidth. The level is resident in shared memory, so DRAM traffic is the packed record read once (traffic) and the unit that binds the kernel is the FP64 pipe: see fp64 (thread-instructions per pixel-iteration from ncu x executed pixel-iterations / kernel time, over the measured DFMA peak)",
                 "fp64": fp64,
                 "other_kernels": {"k_batch_pyramid": {"kernel_ms": pyr_t * 1e3, "algorithmic_bytes_per_launch": setup_bytes,
                                                       "achieved": setup_bytes / pyr_t / 1e9, "frac": setup_bytes / pyr_t / 1e9 / peak,
-                                                      "note": "SURVEY 8(d) counts every input byte; the kernel touches only the 2 of every 4 / 8 rows the central 2x2 taps live in, so compulsory traffic is about half of this"}}}
+                                                      "bound": "hbm", "traffic": (prof["pyramid_dram_bytes_per_pair"] * P) if prof.get("pyramid_dram_bytes_per_pair") else None,
+                                                      "note": "compulsory traffic: the source rows the active levels tap (%.0f%% of the rows) of gray0, gray1 and depth0 (%d B/px) in whole sectors + the 12 B/px packed record out" % (100 * rows_read_fraction(cfg, ROWS), d0.element_size())}}}
     # ---- CPU baseline on this box's host cores, bounded sample of the same workload
     cpu = None
     if not args.no_cpu_baseline:
@@ -374,18 +588,25 @@ def main():
                "sample": "%d pairs, %d threads x single-threaded alignments (SetSourceFrame+SetTargetFrame+Optimize)" % (pairs, host_threads),
                "optimize_only_pairs_per_core_s": r["optimize_only_pairs_per_core_s"],
                "gpu_vs_cpu_iterations_equal": iters_equal, "gpu_vs_cpu_max_pose_abs_diff": pose_err}
+    sec = None
+    if world == 1 and not args.no_secondary:
+        del g0, d0, g1
+        torch.cuda.empty_cache()
+        sec = secondary_block(phovo, torch, dev, local_rank, args.secondary_frames)
+    e2e_step_s = float(te.item()) / e2e_steps * 1e-3
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched independent 640x480 RGB-D pairs, %s (BASELINE configs[3]), %d pairs per GPU per step" % (CONFIG, P),
-                       "pairs_per_gpu": P, "rows": ROWS, "cols": COLS, "depth_dtype": "u16 raw x 1/5000 m" if args.depth == "u16" else "f32 metres", "parallelism": "pairs sharded x%d, final pose all_gather" % world, "host_cpus_bound_to_gpu_numa_node": numa,
-                       "l2_policy": "inputs larger than L2 (%.1f GB of frames per step)" % (h2d_full / 1e9),
-                       "e2e_upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe" % (h2d, h2d_full),
-                       "mean_iterations_per_pair": {str(l): float(it_host[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0}},
+            "config": workload_config(P, args.depth, world),
+            "mean_iterations_per_pair": {str(l): float(it_host[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(te.item()) / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": e2e_step_s * 1e3, "steps": e2e_steps,
+                    "link_gbs": h2d / e2e_step_s / 1e9, "h2d_peak_gbs": min(h2d_peaks), "h2d_peak_gbs_per_rank": h2d_peaks,
+                    "link_frac_of_h2d_peak": h2d / e2e_step_s / 1e9 / min(h2d_peaks),
+                    "host_cpus_bound_to_gpu_numa_node": numa,
+                    "upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe per rank; link_gbs = per-rank H2D bytes / e2e step time (all ranks upload at once), h2d_peak_gbs = one 1 GiB cudaMemcpyAsync from pinned memory measured in this run with the link otherwise idle (slowest rank)" % (h2d, h2d_full)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "latency_us_per_pair_per_sm": align_t / (P / min(P, 148)) * 1e6}
+            "latency_us_per_pair_per_sm": align_t / (P / min(P, 148)) * 1e6, "secondary": sec}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -137,7 +137,13 @@ int phovo_set_intrinsics(phovo_ctx* ctx, const double K[9]);
 /* SetSourceFrame (AN:466-476): gray u8 rows x cols with byte stride gray_step; depth in metres
  * (F64/F32) or raw u16 * depth_scale, byte stride depth_step.  Uploads and builds the intensity and
  * depth pyramids on the device.  Host pointers may be pageable or pinned; device pointers are
- * accepted too (detected with cudaPointerGetAttributes). */
+ * accepted too (detected with cudaPointerGetAttributes) and are read in place.
+ * Ownership, every frame entry point: inputs are borrowed for the duration of the call only -- when
+ * it returns, host buffers have been copied and kernels reading a DEVICE buffer have completed, so
+ * the caller may overwrite or free it.  Stream contract for device inputs: the work runs on the
+ * context's stream (its own non-blocking stream unless phovo_set_stream was called), which is NOT
+ * ordered after whatever produced the buffer.  Either pass the producer's stream to
+ * phovo_set_stream first, or synchronise the producer before the call. */
 int phovo_set_source(phovo_ctx* ctx, const uint8_t* gray, size_t gray_step,
                      const void* depth, int depth_type, size_t depth_step, double depth_scale,
                      int rows, int cols);
@@ -189,7 +195,8 @@ int phovo_eval_residuals(phovo_ctx* ctx, int level, const double state[6], doubl
 int phovo_get_timings(const phovo_ctx* ctx, float* setup_ms, float* optimize_ms);
 /* number of kernels this context has launched so far */
 int64_t phovo_launch_count(const phovo_ctx* ctx);
-/* use a caller-provided stream (e.g. torch's current stream) instead of the ctx-owned one */
+/* use a caller-provided stream (e.g. torch's current stream) instead of the ctx-owned one; required
+ * for ordering when device-resident inputs are produced on that stream (see phovo_set_source) */
 int phovo_set_stream(phovo_ctx* ctx, void* cuda_stream);
 /* 0: plain stream launches with host-side convergence polling; 1 (default): whole Optimize as one
  * CUDA graph with a conditional WHILE node per level (no host sync inside) */

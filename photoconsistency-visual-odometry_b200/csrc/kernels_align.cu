@@ -933,19 +933,21 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
   }
 }
 
-inline int grid_for(int n) {
+inline int grid_for(int n, int sm_count) {
   // one pixel per thread up to 8 CTAs per SM, then a fixed persistent grid (grid-stride loop);
-  // the grid is a pure function of the level size, so the partial-sum order is reproducible.
+  // the grid is a pure function of the level size and the device, so the partial-sum order is reproducible.
   const int want = (n + kBlock - 1) / kBlock;
-  const int cap = 148 * 8;
+  const int cap = sm_count * 8;
   return want < cap ? (want > 0 ? want : 1) : cap;
 }
 
 }  // namespace
 
-int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n) {
-  const size_t want = (n + 255) / 256;
-  const int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+int partials_blocks(int sm_count) { return (sm_count > 0 ? sm_count : 1) * 8; }
+
+int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n, int sm_count) {
+  const size_t want = (n + 255) / 256, cap = (size_t)partials_blocks(sm_count);
+  const int blocks = (int)(want < cap ? (want ? want : 1) : cap);
   k_fill_i32<<<blocks, 256, 0, stream>>>(p, value, n);
   return 1;
 }
@@ -962,15 +964,15 @@ int launch_begin_level(cudaStream_t stream, PoseDev* pose, int max_iters) {
 }
 
 int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, const PoseDev* pose,
-                             double* partials, int* grid_out, double* dump_res, double* dump_jac,
+                             double* partials, int sm_count, int* grid_out, double* dump_res, double* dump_jac,
                              bool clear_winner_first) {
   const int n = L.rows * L.cols;
-  const int grid = grid_for(n);
+  const int grid = grid_for(n, sm_count);
   int launches = 0;
-  if (clear_winner_first) launches += launch_fill_i32(stream, P.winner, -1, (size_t)n);
+  if (clear_winner_first) launches += launch_fill_i32(stream, P.winner, -1, (size_t)n, sm_count);
   if (L.mode == PHOVO_MODE_BIOBJECTIVE) {
     k_winner_bi<<<grid, kBlock, 0, stream>>>(L, P, pose);
-    const int grid2 = grid_for(2 * n);
+    const int grid2 = grid_for(2 * n, sm_count);
     if (dump_res || dump_jac) k_normal_eq_bi<true><<<grid2, kBlock, 0, stream>>>(L, P, pose, partials, dump_res, dump_jac);
     else k_normal_eq_bi<false><<<grid2, kBlock, 0, stream>>>(L, P, pose, partials, nullptr, nullptr);
     *grid_out = grid2;
@@ -997,12 +999,11 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
   return launches + 2;
 }
 
-static int g_coop_blocks_per_sm[3] = {-1, -1, -1};
-
 // One cooperative launch for the whole iteration loop of a level.  Returns the number of launches
 // (1) or -1 if cooperative launch is not available (the caller falls back to the graph path).
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                      phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err) {
+                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err) {
+  int* g_coop_blocks_per_sm = ls->coop_blocks_per_sm;
   const int m = L.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
   void* fn = m == 2 ? (void*)k_level_coop<3> : m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
   if (g_coop_blocks_per_sm[m] < 0) {
@@ -1025,7 +1026,8 @@ int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs
 }
 
 // One cluster per level launch.  Returns 1, 0 if the level does not qualify (mode, size), -1 on a launch error.
-int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, cudaError_t* err) {
+int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, LaunchState* ls,
+                         cudaError_t* err) {
   *err = cudaSuccess;
   const int n = L.rows * L.cols;
   if (n > kClusterMaxPixels || (L.mode != PHOVO_MODE_ANALYTIC_REF && L.mode != PHOVO_MODE_ANALYTIC_FIXED)) return 0;
@@ -1033,7 +1035,7 @@ int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelP
   void (*fn)(LevelParams, LevelPtrs, PoseDev*, phovo_iter_stats*) = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? k_level_cluster<1> : k_level_cluster<0>;
   const int chunk = (n + kClusterSize - 1) / kClusterSize;
   const size_t smem = sizeof(double) * PHOVO_ACC_STRIDE * (kClusterSize + kClusterBlock / 32) + (size_t)chunk * 5 + 16;
-  static bool prepared[2] = {false, false};
+  bool* prepared = ls->cluster_prepared;
   const int m = L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
   if (!prepared[m]) {
     if ((*err = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return -1;
@@ -1051,8 +1053,9 @@ int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelP
 }
 
 int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, int sm_count, cudaError_t* err) {
-  static int blocks_per_sm = -1;
+                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, LaunchState* ls, int sm_count,
+                            cudaError_t* err) {
+  int& blocks_per_sm = ls->ceres_blocks_per_sm;
   void* fn = (void*)k_level_coop_ceres;
   if (blocks_per_sm < 0) {
     int nb = 0;

@@ -128,7 +128,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
     CK(ensure(&ctx->winner, &ctx->winner_cap, 2 * max_px));   // the photometric + depth solver stacks 2N rows
     if (before != ctx->winner) {
       changed = true;
-      launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap);
+      launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap, ctx->sm_count);
       ctx->launches += 1;
     }
   }
@@ -140,7 +140,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
   for (int s = 0; s < 2; ++s) CK(ensure(&ctx->scratch64[s], &ctx->scratch_cap[s], max_px));
   {
     double* before = ctx->partials;
-    CK(ensure(&ctx->partials, &ctx->partials_cap, (size_t)148 * 8 * PHOVO_ACC_STRIDE));
+    CK(ensure(&ctx->partials, &ctx->partials_cap, (size_t)partials_blocks(ctx->sm_count) * PHOVO_ACC_STRIDE));
     if (before != ctx->partials) changed = true;
   }
   if (changed) ctx->invalidate_graph();
@@ -150,7 +150,15 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
 // copy a strided host/device image into a dense device staging buffer (or use it in place)
 static int stage_image(phovo_ctx* ctx, const void* src, size_t step, size_t elt, int rows, int cols,
                        char** stage, size_t* stage_cap, const void** dev_out, size_t* dev_step) {
-  if (is_device_pointer(src)) { *dev_out = src; *dev_step = step; return PHOVO_OK; }
+  if (is_device_pointer(src)) {
+    // used in place; the kernels that read it are drained before the call returns (wait_uploads), so the
+    // caller may overwrite or free the buffer afterwards, exactly as with a host buffer.  Ordering
+    // BEFORE the call is the caller's: the data must be complete on the context's stream
+    // (phovo_set_stream(producer stream)) or the producer stream must have been synchronised.
+    *dev_out = src; *dev_step = step;
+    ctx->device_input_in_flight = true;
+    return PHOVO_OK;
+  }
   const size_t bytes = (size_t)rows * cols * elt;
   CK(ensure(stage, stage_cap, bytes));
   CK(cudaMemcpy2DAsync(*stage, (size_t)cols * elt, src, step, (size_t)cols * elt, rows, cudaMemcpyHostToDevice, ctx->stream));
@@ -170,6 +178,12 @@ static int finish_uploads(phovo_ctx* ctx) {
 }
 
 static int wait_uploads(phovo_ctx* ctx) {
+  if (ctx->device_input_in_flight) {   // kernels are still reading the caller's device buffer: drain them
+    ctx->device_input_in_flight = false;
+    ctx->copy_event_armed = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHOVO_OK;
+  }
   if (ctx->copy_event_armed) { CK(cudaEventSynchronize(ctx->ev_copy)); ctx->copy_event_armed = false; }
   return PHOVO_OK;
 }
@@ -278,7 +292,9 @@ extern "C" int phovo_create(int device, phovo_ctx** out) {
   ctx->device = device;
   {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    memset(&prop, 0, sizeof(prop));
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); prop.multiProcessorCount = 0; prop.cooperativeLaunch = 0; }
+    ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
     if (!prop.cooperativeLaunch) ctx->coop_broken = true;
   }
   phovo_internal_default_config(&ctx->cfg);
@@ -609,7 +625,7 @@ static int optimize_stream(phovo_ctx* ctx) {
       int chunk = M - it < poll ? M - it : poll;
       for (int k = 0; k < chunk; ++k) {
         int grid = 0;
-        ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, nullptr, nullptr, false);
+        ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->sm_count, &grid, nullptr, nullptr, false);
         ctx->launches += launch_reduce_solve(ctx->stream, L, ctx->d_pose, ctx->partials, grid, ctx->d_log, 0ull);
       }
       it += chunk;
@@ -672,7 +688,7 @@ static int build_graph(phovo_ctx* ctx) {
     int per_iter = 0;
     CK(capture(body, false, [&] {
       int grid = 0;
-      per_iter += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, nullptr, nullptr, false);
+      per_iter += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->sm_count, &grid, nullptr, nullptr, false);
       per_iter += launch_reduce_solve(ctx->stream, L, ctx->d_pose, ctx->partials, grid, ctx->d_log, (unsigned long long)handle);
     }));
     ctx->graph_launches_per_iter = per_iter;
@@ -707,7 +723,7 @@ static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
     // and writes the whole PoseDev back when the level ends)
     int grid = 0; cudaError_t e = cudaSuccess;
     if (ctx->execution == 3 && !ctx->cluster_broken) {      // small level: one thread-block cluster, cluster barriers
-      const int rcl = launch_level_cluster(ctx->stream, L, P, ctx->d_pose, ctx->d_log, &e);
+      const int rcl = launch_level_cluster(ctx->stream, L, P, ctx->d_pose, ctx->d_log, &ctx->launch_state, &e);
       if (rcl > 0) { ctx->launches += rcl; continue; }
       if (rcl < 0) {
         cudaGetLastError();
@@ -715,7 +731,7 @@ static int optimize_coop(phovo_ctx* ctx, bool* unavailable) {
         ctx->graph_error = std::string("cluster launch unavailable: ") + cudaGetErrorString(e);
       }
     }
-    const int rc = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, ctx->sm_count, &grid, &e);
+    const int rc = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, &ctx->launch_state, ctx->sm_count, &grid, &e);
     if (rc < 0) {
       cudaGetLastError();
       ctx->graph_error = std::string("cooperative launch unavailable: ") + cudaGetErrorString(e);
@@ -744,7 +760,7 @@ static int optimize_ceres_coop(phovo_ctx* ctx, bool* unavailable) {
                           ctx->cfg.initial_trust_region_radius[level], ctx->cfg.max_trust_region_radius[level],
                           ctx->cfg.min_trust_region_radius[level], ctx->cfg.min_relative_decrease[level]};
     cudaError_t e = cudaSuccess;
-    const int rc = launch_level_coop_ceres(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, lm, M, ctx->sm_count, &e);
+    const int rc = launch_level_coop_ceres(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, lm, M, &ctx->launch_state, ctx->sm_count, &e);
     if (rc < 0) {
       cudaGetLastError();
       ctx->graph_error = std::string("cooperative launch unavailable: ") + cudaGetErrorString(e);
@@ -876,7 +892,7 @@ extern "C" int phovo_warp_image(phovo_ctx* ctx, const uint8_t* gray, size_t gray
   if ((rc = stage_image(ctx, depth, depth_step, depth_elt(depth_type), rows, cols, &ctx->stage_depth, &ctx->stage_depth_cap, &dd, &dds))) return rc;
   const void* dt = nullptr; size_t dts = 0;
   if (target && (rc = stage_image(ctx, target, target_step, 1, rows, cols, &ctx->warp_io[1], &ctx->warp_io_cap[1], &dt, &dts))) return rc;
-  ctx->h2d_pending = false;
+  ctx->h2d_pending = false; ctx->device_input_in_flight = false;   // this call ends with a stream synchronise
   // outputs: write in place for device callers, through a dense device buffer for host callers
   uint8_t* dw = warped; size_t dws = warped_step; uint8_t* ddf = diff; size_t ddfs = diff_step;
   const bool w_host = !is_device_pointer(warped), d_host = diff && !is_device_pointer(diff);
@@ -924,7 +940,7 @@ static int eval_at(phovo_ctx* ctx, int level, const double state[6], phovo_iter_
   const LevelPtrs P = ctx->level_ptrs(level);
   ctx->launches += launch_set_state(ctx->stream, ctx->d_pose, nullptr, state, 0);
   int grid = 0;
-  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, dres, djac, false);
+  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->sm_count, &grid, dres, djac, false);
   ctx->launches += launch_reduce_only(ctx->stream, L, ctx->d_pose, ctx->partials, grid, ctx->d_eval);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_eval, ctx->d_eval, sizeof(phovo_iter_stats), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1140,7 +1156,7 @@ extern "C" int phovo_shard_partial(phovo_ctx* ctx) {
   const LevelParams L = ctx->level_params(ctx->shard_level);
   const LevelPtrs P = ctx->level_ptrs(ctx->shard_level);
   int grid = 0;
-  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, nullptr, nullptr, false);
+  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->sm_count, &grid, nullptr, nullptr, false);
   ctx->launches += launch_reduce_to_buffer(ctx->stream, ctx->partials, grid, ctx->d_shard);
   CK(cudaGetLastError());
   return PHOVO_OK;
@@ -1193,7 +1209,7 @@ extern "C" int phovo_shard_partial_exchange(phovo_ctx* ctx) {
   const LevelParams L = ctx->level_params(ctx->shard_level);
   const LevelPtrs P = ctx->level_ptrs(ctx->shard_level);
   int grid = 0;
-  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, &grid, nullptr, nullptr, false);
+  ctx->launches += launch_iteration_kernels(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->sm_count, &grid, nullptr, nullptr, false);
   ctx->xchg_epoch += 1;
   ctx->launches += launch_reduce_exchange(ctx->stream, ctx->d_pose, ctx->partials, grid, ctx->d_shard, ctx->xchg_peers_dev,
                                           ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch);

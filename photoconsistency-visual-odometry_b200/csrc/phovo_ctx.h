@@ -85,6 +85,8 @@ struct phovo_ctx {
   // bookkeeping
   cudaEvent_t ev_copy = nullptr; cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};
   bool h2d_pending = false, copy_event_armed = false, setup_timed = false;
+  bool device_input_in_flight = false;   // a Set*Frame call was given a device pointer and its kernels are queued
+  phovo::LaunchState launch_state;       // per-DEVICE function attributes / occupancy of the persistent kernels
   int64_t launches = 0;
 
   phovo_batch_state* batch = nullptr;

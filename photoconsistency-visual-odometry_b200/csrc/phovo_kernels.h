@@ -64,8 +64,17 @@ int launch_begin_level(cudaStream_t stream, PoseDev* pose, int max_iters);
 // K3a + K3b (+ optional dense residual / Jacobian dump) for one iteration; respects pose->done.
 // partials: [grid][PHOVO_ACC_STRIDE] doubles.  Returns kernels launched; *grid_out = blocks of K3b.
 int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, const PoseDev* pose,
-                             double* partials, int* grid_out, double* dump_res, double* dump_jac,
+                             double* partials, int sm_count, int* grid_out, double* dump_res, double* dump_jac,
                              bool clear_winner_first);
+// blocks the per-pixel kernels may use on a device with `sm_count` SMs = rows of `partials` to allocate
+int partials_blocks(int sm_count);
+// What the launchers of the persistent kernels cache per DEVICE (function attributes are per device
+// and per function; a context lives on one device, so the cache lives in the context).
+struct LaunchState {
+  int coop_blocks_per_sm[3] = {-1, -1, -1};   // k_level_coop<0>, <1>, <3>
+  int ceres_blocks_per_sm = -1;
+  bool cluster_prepared[2] = {false, false};  // k_level_cluster<0>, <1>
+};
 // K4: fixed-order sum of the partials, 6x6 solve, state update, termination test, stats log.
 // cond_handle != 0: also drives the CUDA-graph WHILE node (cudaGraphSetConditional).
 int launch_reduce_solve(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* partials, int grid,
@@ -77,20 +86,21 @@ int launch_reduce_only(cudaStream_t stream, const LevelParams& L, const PoseDev*
 int launch_reduce_to_buffer(cudaStream_t stream, const double* partials, int grid, double* buffer);
 int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* buffer,
                              phovo_iter_stats* log);
-int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n);
+int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n, int sm_count);
 // persistent cooperative kernel: the whole iteration loop of one level in one launch (analytic modes)
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                      phovo_iter_stats* log, int sm_count, int* grid_out, cudaError_t* err);
+                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err);
 
 // thread-block-cluster kernel for small levels (analytic modes, <= 8 192 px): the loop of one level inside ONE
 // cluster of 16 CTAs, winner map in distributed shared memory.  Returns 1 (launched), 0 (level does not
 // qualify: use launch_level_coop), -1 (launch error in *err).
-int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, cudaError_t* err);
+int launch_level_cluster(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, phovo_iter_stats* log, LaunchState* ls, cudaError_t* err);
 
 // Ceres mode: the restated LM loop of one level in one cooperative launch.  lm_params: function, gradient, parameter
 // tolerance, initial / max / min trust-region radius, min relative decrease (CE:464-477).
 int launch_level_coop_ceres(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, int sm_count, cudaError_t* err);
+                            phovo_iter_stats* log, const double lm_params[7], int max_iterations, LaunchState* ls, int sm_count,
+                            cudaError_t* err);
 
 // Exchange area of the fused peer-store all-reduce (one per rank, IPC-shared with the peers).
 struct ShardExchange {

@@ -58,6 +58,19 @@ class CPhotoconsistencyOdometryCuda:
         K = np.ascontiguousarray(intrinsicMatrix, dtype=np.float64).reshape(9)
         self._check(self._L.phovo_set_intrinsics(self._h, K.ctypes.data_as(capi._dp)))
 
+    def _follow_producer_stream(self, *images):
+        """A CUDA tensor is produced on torch's current stream of its device: run the context on that
+        stream, so that the library's kernels are ordered after the producer (the C ABI reads device
+        pointers in place on the context's stream, include/phovo_b200.h: phovo_set_source)."""
+        for img in images:
+            if img is None or isinstance(img, np.ndarray) or not getattr(img, "is_cuda", False):
+                continue
+            import torch
+            stream = torch.cuda.current_stream(img.device).cuda_stream
+            if getattr(self, "_bound_stream", None) != stream:
+                self.SetStream(stream)
+            return
+
     @staticmethod
     def _depth_args(depthImage, depth_scale):
         if isinstance(depthImage, np.ndarray):
@@ -89,6 +102,7 @@ class CPhotoconsistencyOdometryCuda:
         return img, img.stride(0), img.data_ptr(), tuple(img.shape)
 
     def SetSourceFrame(self, intensityImage, depthImage, depth_scale=1.0):   # AN:466-476
+        self._follow_producer_stream(intensityImage, depthImage)
         g, gstep, gptr, shape = self._gray_args(intensityImage)
         d, dtype, dstep, dptr = self._depth_args(depthImage, depth_scale)
         if tuple(d.shape) != tuple(shape):
@@ -99,6 +113,7 @@ class CPhotoconsistencyOdometryCuda:
     def SetTargetFrame(self, intensityImage, depthImage=None, depth_scale=1.0):
         """AN:479-491: the analytic and Ceres solvers ignore the target depth (AN:484); the photometric +
         depth solver (MODE_BIOBJECTIVE, BiObjective.h:567-579) needs it."""
+        self._follow_producer_stream(intensityImage, depthImage)
         g, gstep, gptr, shape = self._gray_args(intensityImage)
         self._check(self._L.phovo_set_target(self._h, gptr, gstep, shape[0], shape[1]))
         if depthImage is not None and self.GetConfig().mode == capi.MODE_BIOBJECTIVE:
@@ -162,6 +177,7 @@ class CPhotoconsistencyOdometryCuda:
 
     def SetStream(self, cuda_stream):
         self._check(self._L.phovo_set_stream(self._h, cuda_stream))
+        self._bound_stream = cuda_stream
 
     def SetExecution(self, path):
         """2 persistent cooperative kernel per level (default), 3 the same with small levels inside one
@@ -178,6 +194,7 @@ class CPhotoconsistencyOdometryCuda:
         return (self._L.phovo_graph_error(self._h) or b"").decode()
 
     def PromoteTargetToSource(self, depthImage, depth_scale=1.0):
+        self._follow_producer_stream(depthImage)
         d, dtype, dstep, dptr = self._depth_args(depthImage, depth_scale)
         self._check(self._L.phovo_promote_target_to_source(self._h, dptr, dtype, dstep, float(depth_scale)))
 
@@ -240,8 +257,10 @@ class CPhotoconsistencyOdometryCuda:
         return states, iters
 
     def BatchAlignDevice(self, gray0, depth0, gray1, states_out, iters_out, initial_states=None, depth_scale=1.0):
-        """All torch device tensors; asynchronous on the context stream."""
+        """All torch device tensors; asynchronous on the context stream (torch's current stream of the
+        tensors' device: inputs are ordered after their producers, outputs before their consumers)."""
         import torch
+        self._follow_producer_stream(gray0)
         P, R, Cc = tuple(gray0.shape)
         dtype = {torch.float64: capi.DEPTH_F64, torch.float32: capi.DEPTH_F32, torch.uint16: capi.DEPTH_U16,
                  torch.int16: capi.DEPTH_U16}[depth0.dtype]

@@ -63,6 +63,10 @@ class RowShardedAlignment:
         import torch
         import torch.distributed as dist
         self.odo, self.rank, self.world, self.group, self.exchange, self.poll = odo, rank, world, group, exchange, poll
+        # The collectives of the "allreduce" / "allgather" exchanges read and write the library's buffer on
+        # torch's current stream (NCCL orders itself after that stream): the context must run on the SAME
+        # stream, or ShardPartial / the collective / ShardStep are unordered with respect to each other.
+        odo.SetStream(torch.cuda.current_stream(torch.device("cuda", device_index)).cuda_stream)
         odo.ShardConfigure(rank, world)
         self.buf = torch.as_tensor(_DeviceBuffer(odo.ShardBuffer(), device_index), device=torch.device("cuda", device_index))
         if exchange == "peer" and world > 1:

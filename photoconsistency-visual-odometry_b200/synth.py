@@ -111,10 +111,43 @@ def make_sequence_frame(k, rows=480, cols=640, K=K_VISUAL_ODOMETRY, n=1000, dept
     return g, d
 
 
-def render_batch_torch(num_pairs, rows, cols, K, device, seed0=0, chunk=64, depth_dtype=None):
+def render_sequence_torch(num_frames, rows, cols, K, device, seed=0, chunk=32, depth_dtype=None):
+    """GPU synthesis of the config-2 sequence (same scene and Lissajous path as make_sequence_frame,
+    noise and holes from torch's generator): gray u8 [N,R,C] and depth [N,R,C] on the device."""
+    import torch
+    depth_dtype = depth_dtype or torch.float32
+    gen = torch.Generator(device=device)
+    gen.manual_seed(4321 + seed)
+    fx, fy, ox, oy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    gray = torch.empty((num_frames, rows, cols), dtype=torch.uint8, device=device)
+    depth = torch.empty((num_frames, rows, cols), dtype=depth_dtype, device=device)
+    c = torch.arange(cols, dtype=torch.float64, device=device)[None, None, :]
+    r = torch.arange(rows, dtype=torch.float64, device=device)[None, :, None]
+    dx, dy = (c - ox) / fx, (r - oy) / fy
+    n0 = torch.tensor(PLANE_N, dtype=torch.float64, device=device)
+    for a in range(0, num_frames, chunk):
+        b = min(num_frames, a + chunk)
+        Rt = torch.tensor(np.stack([state_to_rt(lissajous_pose(k, num_frames)) for k in range(a, b)]), dtype=torch.float64, device=device)
+        R, t = Rt[:, :3, :3], Rt[:, :3, 3]
+        n1 = torch.einsum("bij,j->bi", R, n0)
+        num = (PLANE_D + (n1 * t).sum(-1))[:, None, None]
+        s = num / (n1[:, 0, None, None] * dx + n1[:, 1, None, None] * dy + n1[:, 2, None, None])
+        X1 = torch.stack([s * dx, s * dy, s], dim=-1) - t[:, None, None, :]
+        X0 = torch.einsum("brck,bkj->brcj", X1, R)
+        T = texture(X0[..., 0], X0[..., 1], xp=torch)
+        noise = torch.randn(T.shape, generator=gen, device=device, dtype=torch.float64)
+        gray[a:b] = torch.clamp(torch.round(255. * T + noise), 0, 255).to(torch.uint8)
+        d = s.clone()
+        d[torch.rand(T.shape, generator=gen, device=device) < 0.03] = 0.
+        depth[a:b] = d.to(depth_dtype)
+    return gray, depth
+
+
+def render_batch_torch(num_pairs, rows, cols, K, device, seed0=0, chunk=64, depth_dtype=None, xis=None):
     """GPU synthesis of `num_pairs` pairs (same scene/motion law as make_batch; noise and holes
     come from torch's generator, so values differ from the numpy version).  Returns device
-    tensors gray0 u8 [P,R,C], depth0 f32 [P,R,C], gray1 u8 [P,R,C] and the motions [P,6] (cpu)."""
+    tensors gray0 u8 [P,R,C], depth0 f32 [P,R,C], gray1 u8 [P,R,C] and the motions [P,6] (cpu);
+    `xis` overrides the random motions."""
     import torch
     depth_dtype = depth_dtype or torch.float32
     gen = torch.Generator(device=device)
@@ -123,7 +156,7 @@ def render_batch_torch(num_pairs, rows, cols, K, device, seed0=0, chunk=64, dept
     g0 = torch.empty((num_pairs, rows, cols), dtype=torch.uint8, device=device)
     g1 = torch.empty_like(g0)
     d0 = torch.empty((num_pairs, rows, cols), dtype=depth_dtype, device=device)
-    xis = np.stack([random_motion(seed0 + p) for p in range(num_pairs)])
+    xis = np.stack([random_motion(seed0 + p) for p in range(num_pairs)]) if xis is None else np.asarray(xis, dtype=np.float64).reshape(num_pairs, 6)
     c = torch.arange(cols, dtype=torch.float64, device=device)[None, None, :]
     r = torch.arange(rows, dtype=torch.float64, device=device)[None, :, None]
     dx, dy = (c - ox) / fx, (r - oy) / fy

@@ -11,17 +11,20 @@ import csv, io, json, subprocess, sys
 def main(rep, log, peak, tag):
     raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
     u = dict(zip(raw[0], raw[1]))
-    launches = [dict(zip(raw[0], r)) for r in raw[2:]]       # one k_batch_level launch per active pyramid level
+    every = [dict(zip(raw[0], r)) for r in raw[2:]]
+    launches = [L for L in every if "k_batch_level" in L.get("Kernel Name", "")]       # one k_batch_level launch per active pyramid level
+    pyramid = [L for L in every if "k_batch_pyramid" in L.get("Kernel Name", "")]     # present when captured with -k regex:k_batch
     d = launches[0]
     line = json.loads([l for l in open(log) if l.startswith("{")][-1])
     pairs = line["config"]["pairs_per_gpu"]
-    it = line["config"]["mean_iterations_per_pair"]
+    it = line.get("mean_iterations_per_pair") or line["config"]["mean_iterations_per_pair"]
     rows, cols = line["config"]["rows"], line["config"]["cols"]
     px_iters = pairs * sum(v * round(rows * 0.5 ** int(l)) * round(cols * 0.5 ** int(l)) for l, v in it.items())
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
-    fp64 = dram = dur = 0.0
+    fp64 = dram = dur = l2 = 0.0
     for L in launches:
+        l2 += float(L["lts__t_bytes.sum"]) * scale[u["lts__t_bytes.sum"]]
         cycles = float(L["sm__cycles_elapsed.avg"])
         fp64 += sum(float(L["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k]) for k in ("dfma", "dmul", "dadd")) * cycles
         dram += sum(float(L["dram__bytes_%s.sum" % k]) * scale[u["dram__bytes_%s.sum" % k]] for k in ("read", "write"))
@@ -32,7 +35,15 @@ def main(rep, log, peak, tag):
            "dram_bytes_per_pair": dram / pairs, "fp64_thread_inst_per_px_iter": fp64 / px_iters,
            "fp64_pipe_active_pct_of_active_per_launch": [float(L["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]) for L in launches],
            "fp64_peak_thread_inst_per_s": best, "fp64_peak_source": "tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.jsonl), DFMA issue rate",
+           "l2_bytes_per_pair": l2 / pairs, "l2_gbs": l2 / (dur * 1e-3) / 1e9, "dram_gbs": dram / (dur * 1e-3) / 1e9,
            "registers_per_thread": int(d["launch__registers_per_thread"])}
+    if pyramid:
+        Lp = pyramid[0]
+        pd = sum(float(Lp["dram__bytes_%s.sum" % k]) * scale[u["dram__bytes_%s.sum" % k]] for k in ("read", "write"))
+        pt = float(Lp["gpu__time_duration.sum"]) * tscale[u["gpu__time_duration.sum"]]
+        pl2 = float(Lp["lts__t_bytes.sum"]) * scale[u["lts__t_bytes.sum"]]
+        out.update({"pyramid_dram_bytes_per_pair": pd / pairs, "pyramid_profiled_duration_ms": pt,
+                    "pyramid_dram_gbs": pd / (pt * 1e-3) / 1e9, "pyramid_l2_gbs": pl2 / (pt * 1e-3) / 1e9})
     print(json.dumps(out, indent=1))
 
 
