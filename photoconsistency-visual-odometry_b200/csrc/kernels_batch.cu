@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(256) k_batch_pyramid(const __grid_constant__ B
   ((uint16_t*)(rec + bp.off_I0[a]))[q] = (uint16_t)s0;
   ((uint16_t*)(rec + bp.off_I1[a]))[q] = (uint16_t)s1;
   ((double*)(rec + bp.off_D0[a]))[q] = dv;
+  // fp32 copy for phase A's estimate; the strict range test of AN:279-280 is decided HERE, in fp64, and
+  // encoded as 0 (NaN compares false, so a NaN depth is invalid too); a valid depth that would round
+  // to 0 in fp32 cannot occur: the host enables the fp32 estimate only for min_depth >= 2^-100
+  ((float*)(rec + bp.off_D32[a]))[q] = (bp.min_depth < dv) & (dv < bp.max_depth) ? (float)dv : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -120,7 +124,9 @@ struct BatchLevelParams {
   int num_pairs, rows, cols, n;
   int level, max_iters, first, log_cap;          // first: coarsest active level (starts from the caller's state)
   int exact_always, force_generic;
-  unsigned long long off_I0, off_I1, off_D0, record_bytes;
+  int est32;                                     // fp32 estimate of phase A usable for this level (see gn_level)
+  int prev_level;                                // pyramid level of the previous (coarser) active level, -1 for the first
+  unsigned long long off_I0, off_I1, off_D0, off_D32, record_bytes;
   double fx, fy, ox, oy, inv_fx, inv_fy;
   double lambda, min_grad, grad_k;
   double min_depth, max_depth;
@@ -131,11 +137,76 @@ static BatchLevelParams level_params(const BatchParams& bp, int a) {
   lv.num_pairs = bp.num_pairs; lv.rows = bp.lrows[a]; lv.cols = bp.lcols[a]; lv.n = lv.rows * lv.cols;
   lv.level = bp.level[a]; lv.max_iters = bp.max_iters[a]; lv.first = a == 0; lv.log_cap = bp.log_cap;
   lv.exact_always = bp.exact_always; lv.force_generic = bp.force_generic;
-  lv.off_I0 = bp.off_I0[a]; lv.off_I1 = bp.off_I1[a]; lv.off_D0 = bp.off_D0[a]; lv.record_bytes = bp.record_bytes;
+  lv.off_I0 = bp.off_I0[a]; lv.off_I1 = bp.off_I1[a]; lv.off_D0 = bp.off_D0[a]; lv.off_D32 = bp.off_D32[a]; lv.record_bytes = bp.record_bytes;
+  // the fp32 estimate keeps 14 fraction bits of the displacement in a float: |displacement| < 256 px, so every
+  // in-bounds target of a level of at most 256 x 256 px is representable (warp_estimate32)
+  lv.est32 = lv.rows <= 256 && lv.cols <= 256 && bp.min_depth >= 0x1p-100 && bp.max_depth <= 0x1p100;
+  lv.prev_level = a > 0 ? bp.level[a - 1] : -1;
   lv.fx = bp.fx[a]; lv.fy = bp.fy[a]; lv.ox = bp.ox[a]; lv.oy = bp.oy[a]; lv.inv_fx = bp.inv_fx[a]; lv.inv_fy = bp.inv_fy[a];
   lv.lambda = bp.lambda[a]; lv.min_grad = bp.min_grad[a]; lv.grad_k = bp.grad_k[a];
   lv.min_depth = bp.min_depth; lv.max_depth = bp.max_depth;
   return lv;
+}
+
+__device__ __forceinline__ float ldg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float rcp_approx_f32(float x) {   // MUFU.RCP: at most 1 ulp
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A in SINGLE precision (column-fixed kernels).  The fp64 estimate (warp_estimate) costs ~17
+// instructions of the FP64 pipe per pixel, and an instruction of that pipe costs more than two issue
+// cycles (tools/issue_probe.cu: nothing issues in its shadow) -- a third of what the kernel is bound by.
+// fp32 cannot resolve t = f X'/Z' + o to the 2^-14 px the certainty test needs (24 bits, |t| < 2^8), but
+// it can resolve the DISPLACEMENT t - c of the pixel from its own position, which is small:
+//   t_c - c = fx (X' - cxi Z') / Z' + (fx cxi + ox - c),        X' - cxi Z' = d D0 + (x - cxi z),
+//   D0 = (R00 cxi + R02) - cxi (R20 cxi + R22) + ryi (R01 - R21 cxi)                      [O(rotation)]
+//   t_r - r = fy (Y' - ryi Z') / Z',                            Y' - ryi Z' = d D1 + (y - ryi z),
+//   D1 = (R10 cxi + R12) + ryi (R11 - R22 - R20 cxi) - ryi^2 R21
+//   Z' = d + (d (M2 - 1) + z),  M2 - 1 = (R20 cxi + R22 - 1) + R21 ryi
+// A thread's column is fixed, so the cxi-dependent coefficients are per-thread constants of the
+// iteration (computed in fp64, rounded once); the ryi-dependent ones come from a float4 row table.
+// floor((displacement + 0.5) 2^14) is read off the mantissa of  q fxs + (0.5 * 2^14 + 1.5 * 2^23)  evaluated
+// with round-down (one FFMA.RM): bits 0..13 are the fraction, bits 14.. the whole pixels + 0x12D00.
+// Values outside [-2^22, 2^22) leave the binade [2^23, 2^24): the bits then decode to a target >= 256 px
+// away, which is out of bounds for a level of at most 256 x 256 px -- as the true target is.
+//
+// Error budget (u = 2^-24; a valid pixel that passes the guard Z' > d / 2 has d >= dmin = min_depth):
+//   every D / M2 - 1 is within 4 u B of its exact value, B = the sum of the magnitudes of its terms
+//     (coefficient rounding, ryi rounding, the fused multiply-add, the final add);
+//   |num - num*| <= u (6 d B + 2 emax)      (d rounded to fp32, the offset rounded, the fma);   / Z' <= u (12 B + 4 emax / dmin)
+//   |Z' - Z'*| / Z' <= u GZ,  GZ = 2 (7 B2 + 1) + 4 |z| / dmin + 1;   reciprocal 2 u, product u, fxs u
+//   |displacement| <= D = f (2 B + 2 emax / dmin)
+//   E = f u (12 B + 4 emax / dmin) + D u (GZ + 4) + 2^-36          px; the last term covers the ~10 roundings of
+//                                                                   the reference's own fp64 evaluation and fx cxi vs c - ox
+// A fraction is trusted when it lies at least e = ceil(E 2^14) + 1 units from both ends of [0, 2^14).
+// Returns the margins; 2^14 (nothing trusted) if anything is not finite.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFrac32Bits = 14;
+constexpr unsigned kFrac32One = 1u << kFrac32Bits;
+constexpr float kMagic32 = 12582912.f + 8192.f;          // 1.5 * 2^23 + 0.5 * 2^14
+constexpr int kMagic32Whole = 0x4B400000 >> kFrac32Bits;  // what bits 14.. of the mantissa trick carry for a zero displacement
+
+__device__ __forceinline__ void est32_margins(const Pose& T, double fx, double fy, double rx, double ry, double dmin, unsigned& ex, unsigned& ey) {
+  const double u = 0x1p-24;
+  const double B0 = (fabs(T.R00 - T.R22) * rx + fabs(T.R20) * rx * rx + fabs(T.R02)) + (fabs(T.R01) + fabs(T.R21) * rx) * ry;
+  const double B1 = (fabs(T.R10) * rx + fabs(T.R12)) + (fabs(T.R11 - T.R22) + fabs(T.R20) * rx) * ry + fabs(T.R21) * ry * ry;
+  const double B2 = fabs(T.R20) * rx + fabs(T.R22 - 1.0) + fabs(T.R21) * ry;
+  const double idmin = 1.0 / dmin;
+  const double e0m = fabs(T.x) + rx * fabs(T.z), e1m = fabs(T.y) + ry * fabs(T.z);
+  const double GZ = 2.0 * (7.0 * B2 + 1.0) + 4.0 * fabs(T.z) * idmin + 1.0;
+  const double Dx = fabs(fx) * (2.0 * B0 + 2.0 * e0m * idmin), Dy = fabs(fy) * (2.0 * B1 + 2.0 * e1m * idmin);
+  const double Ex = fabs(fx) * u * (12.0 * B0 + 4.0 * e0m * idmin) + Dx * u * (GZ + 4.0) + 0x1p-36;
+  const double Ey = fabs(fy) * u * (12.0 * B1 + 4.0 * e1m * idmin) + Dy * u * (GZ + 4.0) + 0x1p-36;
+  const double sx = Ex * (double)kFrac32One, sy = Ey * (double)kFrac32One;
+  ex = (sx < 4096.0) ? (unsigned)ceil(sx) + 1u : kFrac32One;     // NaN compares false: nothing trusted
+  ey = (sy < 4096.0) ? (unsigned)ceil(sy) + 1u : kFrac32One;
 }
 
 struct BatchShared {
@@ -145,7 +216,17 @@ struct BatchShared {
   int iteration;
   int pair;
   int pad;
+  unsigned ex, ey;       // margins of phase A's fp32 estimate for the current iterate (est32_margins), written with the pose
 };
+
+// largest |cxi|, |ryi| of a level: the ray bounds the margins are computed from
+__device__ __forceinline__ void est32_publish(const BatchLevelParams& lv, const Pose& P, BatchShared* sh) {
+  const double rx = fmax(fabs(lv.ox), fabs((double)(lv.cols - 1) - lv.ox)) * fabs(lv.inv_fx);
+  const double ry = fmax(fabs(lv.oy), fabs((double)(lv.rows - 1) - lv.oy)) * fabs(lv.inv_fy);
+  unsigned ex, ey;
+  est32_margins(P, lv.fx, lv.fy, rx, ry, lv.min_depth, ex, ey);
+  sh->ex = ex; sh->ey = ey;
+}
 
 // Gauss-Newton step by ONE warp (AN:538-549 + AN:376-392).  Lane L enters with total[L]
 // ([0..20] upper triangle of J^T J, [21..26] J^T r, [27] sum r^2, [28] count).  The totals go through
@@ -194,6 +275,7 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchLe
 #pragma unroll
     for (int k = 0; k < 6; ++k) sh->pose.state[k] = s_out[k];
     pose_store(P, &sh->pose);
+    est32_publish(lv, P, sh);
     sh->done = done;
     sh->iteration = it + 1;
   }
@@ -214,10 +296,11 @@ struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
   double2* row;                   // [rows + pad][kRowEntries]
+  float4* rowf;                   // [rows + pad] per ITERATION, fp32 estimate of phase A: {ryi, y - ryi z, R21 ryi, -R21 ryi^2}
 };
 __host__ __device__ inline int table_pad_rows(int cols, int threads) { return (3 * threads + cols - 1) / cols; }
 __host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
-  return 2 * (rows + cols) + 4 * cols + 2 * kRowEntries * (rows + table_pad_rows(cols, threads));
+  return 2 * (rows + cols) + 4 * cols + (2 * kRowEntries + 2) * (rows + table_pad_rows(cols, threads));
 }
 // shared-memory slots of the three per-pixel arrays: the level plus `threads` slots of padding
 __host__ __device__ inline int padded_slots(int n, int threads) { return (n + threads + 7) & ~7; }
@@ -339,7 +422,7 @@ __device__ __forceinline__ void jacobian_row(const IterConst& K, const ColRegs& 
 
 struct LevelCtx {
   int pair;
-  const double* gD0; const unsigned short* gI0;
+  const double* gD0; const float* gD32; const unsigned short* gI0;
   unsigned* sWin; const unsigned* sG; const unsigned short* sI1; double* sRed;
   unsigned sWinAddr, sDummyAddr;
   Tables tb;
@@ -387,9 +470,14 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
   // The first trip of both phases reads the same two pixels in every iteration.  Their loads are
   // issued a whole reduction + solve ahead (before the loop / at the end of phase B) instead of behind
   // the barrier that opens phase A, where every warp of the CTA would wait out the L2 latency at once.
-  double first_d[4]; unsigned first_u[4];
+  // (column-fixed kernels: phase A reads the fp32 copy of the depth, phase B the fp64 one)
+  double first_d[COLFIX ? 2 : 4]; float first_f[4]; unsigned first_u[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { first_d[j] = ldg_f64(L.gD0 + tid + j * BT); first_u[j] = ldg_u16(L.gI0 + tid + j * BT); }
+  for (int j = 0; j < 4; ++j) {
+    if (COLFIX) first_f[j] = ldg_f32(L.gD32 + tid + j * BT);
+    if (!COLFIX || j < 2) first_d[j] = ldg_f64(L.gD0 + tid + j * BT);
+    first_u[j] = ldg_u16(L.gI0 + tid + j * BT);
+  }
 
   for (int it = 0; it < max_iters; ++it) {
     Pose T;
@@ -429,7 +517,8 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
         tb.row[kRowEntries * r + 1] = make_double2(fma(T.R21, v, T.R22), -fma(T.sp * T.sr, v, T.sp * T.cr));
         tb.row[kRowEntries * r + 2] = make_double2(fma(T.R22, v, -T.R21), fma(T.R02, v, -T.R01));
         tb.row[kRowEntries * r + 3] = make_double2(fma(T.R12, v, -T.R11), 0.);
-        tb.row[kRowEntries * r + 4] = make_double2(K.fxs * e0, K.fys * e1);
+        if (COLFIX) tb.rowf[r] = make_float4((float)v, (float)fma(-v, T.z, T.y), (float)(T.R21 * v), (float)(-(T.R21 * v) * v));
+        else tb.row[kRowEntries * r + 4] = make_double2(K.fxs * e0, K.fys * e1);
       }
     }
     ColRegs mycol;
@@ -448,7 +537,84 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     // back there is masked by the in-range tests.
     unsigned long long valid = 0ull;
     const int quads = (trips + 1) >> 1;          // four-pixel trips of this thread
-    {
+    if (COLFIX) {
+      // ---- fp32 estimate (see est32_margins).  Per-thread constants of the iteration, rounded once ----
+      unsigned ex = sh->ex, ey = sh->ey;             // computed once, by the thread that published the pose
+      if (!(lv.est32 && ordinary && finite_pose) || lv.exact_always) ex = ey = kFrac32One;   // nothing trusted: every pixel takes warp_exact
+      const unsigned limx = ex < kFrac32One / 2 ? kFrac32One - 2u * ex : 0u, limy = ey < kFrac32One / 2 ? kFrac32One - 2u * ey : 0u;
+      const float a0f = (float)(fma(T.R00, my_cxi, T.R02) - my_cxi * fma(T.R20, my_cxi, T.R22)), b0f = (float)fma(-T.R21, my_cxi, T.R01);
+      const float a1f = (float)fma(T.R10, my_cxi, T.R12), b1f = (float)((T.R11 - T.R22) - T.R20 * my_cxi);
+      const float a2f = (float)fma(T.R20, my_cxi, T.R22 - 1.0), e0f = (float)fma(-my_cxi, T.z, T.x), ztf = (float)T.z;
+      const float fxsf = (float)(fx * (double)kFrac32One), fysf = (float)(fy * (double)kFrac32One);
+      const int dr1 = BT / cols;                   // rows between two consecutive pixels of a thread
+      const int cprime = c0_first - kMagic32Whole;
+      int rprime = r0_first - kMagic32Whole;       // row of the trip's first pixel, mantissa offset folded in
+      const char* rq = (const char*)(tb.rowf + r0_first);
+      const int rq_step = 4 * dr1 * (int)sizeof(float4);
+      const float* pf = L.gD32 + tid;
+      const unsigned short* pu = L.gI0 + tid;
+      float p[4], f[4]; unsigned u[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { p[j] = first_f[j]; u[j] = first_u[j]; f[j] = 0.f; w[j] = 0u; }
+      unsigned vhi = 0u, vlo = 0u, uhi = 0u, ulo = 0u;   // validity / "needs the exact warp" bits, shifted in at the top
+      unsigned bid = (unsigned)(tid + 1) << 16;
+      auto trip = [&](const float (&cd)[4], const unsigned (&cu)[4], float (&nd)[4], unsigned (&nu)[4], const int i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { nd[j] = ldg_f32(pf + (4 + j) * BT); nu[j] = ldg_u16(pu + (4 + j) * BT); }
+        pf += 4 * BT; pu += 4 * BT;
+        unsigned vbits = 0u, ubits = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 rf = *(const float4*)(rq + j * dr1 * (int)sizeof(float4));
+          const float d = cd[j];
+          const float D0 = fmaf(b0f, rf.x, a0f);
+          const float D1 = fmaf(b1f, rf.x, a1f) + rf.w;
+          const float Z = d + fmaf(d, a2f + rf.z, ztf);
+          const float iz = rcp_approx_f32(Z);
+          const unsigned ux = __float_as_uint(__fmaf_rd(fmaf(d, D0, e0f) * iz, fxsf, kMagic32));
+          const unsigned uy = __float_as_uint(__fmaf_rd(fmaf(d, D1, rf.y) * iz, fysf, kMagic32));
+          const bool dep = (d > 0.f) & (j == 0 || i + j * BT < n);                    // range test of AN:279-280, decided by the pyramid kernel
+          const bool sure = (((ux & (kFrac32One - 1u)) - ex) < limx) & (((uy & (kFrac32One - 1u)) - ey) < limy) & (fmaf(d, -0.5f, Z) > 0.f);
+          const int tj = (int)(ux >> kFrac32Bits) + cprime, ti = (int)(uy >> kFrac32Bits) + rprime + j * dr1;
+          const bool ok = dep & sure & ((unsigned)tj < (unsigned)cols) & ((unsigned)ti < (unsigned)rows);
+          smem_red_max(ok ? L.sWinAddr + 4u * (unsigned)(ti * cols + tj) : dummy, bid + ((unsigned)(j * BT) << 16) + cu[j]);
+          vbits |= (unsigned)ok << (28 + j);
+          ubits |= (unsigned)(dep & !sure) << (28 + j);
+        }
+        bid += (unsigned)(4 * BT) << 16;
+        vlo = __funnelshift_r(vlo, vhi, 4); vhi = (vhi >> 4) | vbits;
+        ulo = __funnelshift_r(ulo, uhi, 4); uhi = (uhi >> 4) | ubits;
+        rq += rq_step; rprime += 4 * dr1;
+      };
+      int i = tid;
+      if (quads & 1) {
+        trip(p, u, f, w, i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { p[j] = f[j]; u[j] = w[j]; }
+        i += 4 * BT;
+      }
+      for (; i < n; i += 8 * BT) {
+        trip(p, u, f, w, i);
+        trip(f, w, p, u, i + 4 * BT);
+      }
+      valid = ((unsigned long long)vhi << 32) | vlo;
+      valid = quads > 0 ? valid >> (64 - 4 * quads) : 0ull;
+      unsigned long long unsure = ((unsigned long long)uhi << 32) | ulo;
+      unsure = quads > 0 ? unsure >> (64 - 4 * quads) : 0ull;
+      // ---- the pixels the estimate could not decide (a few per warp and iteration): the reference's own arithmetic ----
+      while (unsure) {
+        const int k = __ffsll((long long)unsure) - 1;
+        unsure &= unsure - 1ull;
+        const int px = tid + k * BT;
+        const double d = __ldg(L.gD0 + px);
+        const WarpA a = warp_exact(&sh->pose, my_cx, tb.ry[px / cols], d, fx, fy, ox, oy, inv_fx, inv_fy);
+        const bool ok = ((unsigned)a.tj < (unsigned)cols) & ((unsigned)a.ti < (unsigned)rows) & (min_depth < d) & (d < max_depth);
+        if (ok) {
+          smem_red_max(L.sWinAddr + 4u * (unsigned)(a.ti * cols + a.tj), ((unsigned)(px + 1) << 16) + (unsigned)__ldg(L.gI0 + px));
+          valid |= 1ull << k;
+        }
+      }
+    } else {
       int rr[4], cc[4];
       const double2* rp[4];                       // COLFIX: the thread's column never changes, the row pointers
 #pragma unroll                                    // advance by a constant (rows past the level are zero padding)
@@ -589,7 +755,11 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     }
     // first trip of the next iteration: in flight during the reduction and the solve
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { first_d[j] = ldg_f64(L.gD0 + tid + j * BT); first_u[j] = ldg_u16(L.gI0 + tid + j * BT); }
+    for (int j = 0; j < 4; ++j) {
+      if (COLFIX) first_f[j] = ldg_f32(L.gD32 + tid + j * BT);
+      if (!COLFIX || j < 2) first_d[j] = ldg_f64(L.gD0 + tid + j * BT);
+      first_u[j] = ldg_u16(L.gI0 + tid + j * BT);
+    }
     // ---- deterministic reduction: 31 shuffle-adds per warp, warps summed in index order ----
     {
       double x[32];
@@ -646,12 +816,28 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
   unsigned* sDummy = (unsigned*)(sh + 1);            // 32 slots that absorb the bids of pixels without a target
   const int tid = threadIdx.x;
 
+  // The launches of consecutive levels overlap (programmatic dependent launch): the next level's grid may start
+  // as soon as every CTA of this one is running, its CTAs get an SM when this level's persistent CTAs retire, and
+  // it waits PER PAIR (below) -- so the SMs that run dry in the tail of this launch (iteration counts differ 4x
+  // between pairs) start on the next level instead of idling.  Every CTA of this grid is resident before any
+  // CTA of the next one can be scheduled, so the waits below cannot starve this grid.
+  asm volatile("griddepcontrol.launch_dependents;");
   for (;;) {
     __syncthreads();   // the previous pair's outputs have been read from shared memory
     if (tid == 0) {
       const int pair = (int)atomicAdd(next_pair, 1u);
       sh->pair = pair;
       if (pair < lv.num_pairs) {
+        if (lv.prev_level >= 0) {
+          // the coarser level publishes its iteration count (>= 1) for the pair LAST, with release semantics
+          const int32_t* flag = iters + (size_t)pair * PHOVO_MAX_LEVELS + lv.prev_level;
+          int v;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v != 0) break;
+            __nanosleep(200);
+          }
+        }
         double s[6];
         const double* src = lv.first ? init_states : states;     // the first level starts from the caller's state
         for (int k = 0; k < 6; ++k) s[k] = src ? src[(size_t)pair * 6 + k] : 0.;
@@ -659,6 +845,7 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
         pose_from_state(s, P);
         for (int k = 0; k < 6; ++k) sh->pose.state[k] = s[k];
         pose_store(P, &sh->pose);
+        est32_publish(lv, P, sh);
         sh->pose.log_count = (lv.first || !log_counts) ? 0 : log_counts[pair];
         sh->done = 0; sh->iteration = 0;
       }
@@ -671,6 +858,7 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     LevelCtx L;
     L.pair = pair;
     L.gD0 = (const double*)(rec + lv.off_D0);
+    L.gD32 = (const float*)(rec + lv.off_D32);
     L.gI0 = (const unsigned short*)(rec + lv.off_I0);
     L.sWin = sWin; L.sG = sG; L.sI1 = sI1; L.sRed = sRed;
     L.sWinAddr = (unsigned)__cvta_generic_to_shared(sWin);
@@ -678,7 +866,8 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
     const int pad_rows = table_pad_rows(cols, BT);
     Tables& tb = L.tb;
     tb.colA = (double2*)sTab; tb.colB = tb.colA + cols; tb.row = tb.colB + cols;
-    tb.cx = (double*)(tb.row + kRowEntries * (rows + pad_rows)); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
+    tb.rowf = (float4*)(tb.row + kRowEntries * (rows + pad_rows));
+    tb.cx = (double*)(tb.rowf + rows + pad_rows); tb.ry = tb.cx + cols; tb.cxi = tb.ry + rows; tb.ryi = tb.cxi + cols;
     {
       // record -> shared memory, 16-byte vectors (record offsets are 16-byte aligned)
       const double ox = lv.ox, oy = lv.oy, inv_fx = lv.inv_fx, inv_fy = lv.inv_fy;
@@ -689,6 +878,7 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       for (int k = tid; k < nw; k += BT) w4[k] = make_uint4(0, 0, 0, 0);                 // level + padding: no winners
       for (int k = n + tid; k < nal; k += BT) sG[k] = 0u;                               // padding slots (read, then masked)
       for (int k = kRowEntries * rows + tid; k < kRowEntries * (rows + pad_rows); k += BT) tb.row[k] = make_double2(0., 0.);
+      for (int k = rows + tid; k < rows + pad_rows; k += BT) tb.rowf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = tid; k < cols; k += BT) { const double v = __dsub_rn((double)k, ox); tb.cx[k] = v; tb.cxi[k] = v * inv_fx; }   // AN:282
       for (int k = tid; k < rows; k += BT) { const double v = __dsub_rn((double)k, oy); tb.ry[k] = v; tb.ryi[k] = v * inv_fy; }   // AN:286
     }
@@ -710,12 +900,17 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       }
     }
     // (the first barrier inside gn_level orders these writes before the pixel loops)
-    if (BT % cols == 0 && !lv.force_generic) gn_level<MODE, true, BT, STATS>(lv, L, sh, STATS ? log : nullptr);
+    if (BT % cols == 0 && !lv.force_generic && lv.est32) gn_level<MODE, true, BT, STATS>(lv, L, sh, STATS ? log : nullptr);
     else gn_level<MODE, false, BT, STATS>(lv, L, sh, STATS ? log : nullptr);
     __syncthreads();
-    if (tid == 0 && iters) iters[(size_t)pair * PHOVO_MAX_LEVELS + lv.level] = sh->iteration;
     if (tid < 6) states[(size_t)pair * 6 + tid] = sh->pose.state[tid];
     if (tid == 0 && log_counts) log_counts[pair] = sh->pose.log_count;
+    __syncthreads();
+    if (tid == 0) {   // the pair is ready for the next level: state, log count (and the log) are visible before the count
+      __threadfence();
+      const int done_iterations = sh->iteration;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(iters + (size_t)pair * PHOVO_MAX_LEVELS + lv.level), "r"(done_iterations) : "memory");
+    }
   }
 }
 
@@ -777,8 +972,14 @@ int launch_batch_align(cudaStream_t stream, const BatchParams& bp, int sm_count,
     // STATS: the kernel that also accumulates sum r^2 and writes the iteration log
 #define PHOVO_LAUNCH_LEVEL(MODE, BT, MINB, grid)                                                                                        \
   do {                                                                                                                                  \
-    if (log) k_batch_level<MODE, BT, MINB, true><<<grid, BT, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);   \
-    else k_batch_level<MODE, BT, MINB, false><<<grid, BT, smem, stream>>>(lv, store, init_states, states, iters, log, log_counts, next_pair + a);      \
+    cudaLaunchConfig_t cfg = {};                                                                                                        \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;                                \
+    cudaLaunchAttribute attr[1];                                                                                                        \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                                    \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                                                             \
+    cfg.attrs = attr; cfg.numAttrs = a > 0 ? 1 : 0;   /* levels after the first may start while the previous one drains */             \
+    if (log) cudaLaunchKernelEx(&cfg, k_batch_level<MODE, BT, MINB, true>, lv, store, init_states, states, iters, log, log_counts, next_pair + a);   \
+    else cudaLaunchKernelEx(&cfg, k_batch_level<MODE, BT, MINB, false>, lv, store, init_states, states, iters, log, log_counts, next_pair + a);      \
   } while (0)
     if (batch_level_is_small(rows, cols)) {
       const int grid = min(bp.num_pairs, 3 * sm_count);

@@ -135,6 +135,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
     bp->off_D0[a] = off; off += n64;
     bp->off_I0[a] = off; off += n16;
     bp->off_I1[a] = off; off += n16;
+    bp->off_D32[a] = off; off += ((unsigned long long)n * 4 + 15) & ~15ull;
     // CPhotoconsistencyOdometryAnalytic.h:203-209
     const double scaleFactor = 1.0 / pow(2, level);
     bp->fx[a] = ctx->K[0] * scaleFactor; bp->fy[a] = ctx->K[4] * scaleFactor;

@@ -15,7 +15,7 @@ constexpr int kBatchSmallLevelPixels = 6400; // largest level that runs 3 CTAs p
 constexpr int kBatchMaxLevelPixels = 22528; // 10 B/px of shared memory + tables + scratch must fit 227 KB (checked exactly
                                             // by the host); also <= 64 * kBatchThreads (validity mask) and < 65535
 
-// The level kernel prefetches D0 / I0 up to 8 * kBatchThreads pixels past the end of a level without
+// The level kernel prefetches D0 / D32 / I0 up to 8 * kBatchThreads pixels past the end of a level without
 // bounds guards (the values are masked); the allocation behind the last record must cover that.
 constexpr size_t kBatchStoreSlackBytes = 8 * (size_t)kBatchThreads * sizeof(double) + 1024;
 
@@ -33,6 +33,7 @@ struct BatchParams {
   int max_iters[PHOVO_MAX_LEVELS];
   int px_offset[PHOVO_MAX_LEVELS + 1];  // prefix sum of level pixel counts (pyramid kernel indexing)
   unsigned long long off_I0[PHOVO_MAX_LEVELS], off_I1[PHOVO_MAX_LEVELS], off_D0[PHOVO_MAX_LEVELS];
+  unsigned long long off_D32[PHOVO_MAX_LEVELS];   // fp32 copy of D0, 0 where the depth fails the range test (phase A's estimate)
   unsigned long long record_bytes;      // bytes of one pair's packed level record in HBM
   double fx[PHOVO_MAX_LEVELS], fy[PHOVO_MAX_LEVELS], ox[PHOVO_MAX_LEVELS], oy[PHOVO_MAX_LEVELS];
   double inv_fx[PHOVO_MAX_LEVELS], inv_fy[PHOVO_MAX_LEVELS];
