@@ -280,6 +280,15 @@ int phovo_shard_finish(phovo_ctx* ctx);                          /* read back st
 int phovo_shard_peer_export(phovo_ctx* ctx, void* handle_out /* PHOVO_IPC_HANDLE_BYTES */);
 int phovo_shard_peer_import(phovo_ctx* ctx, int peer_rank, const void* handle);
 int phovo_shard_partial_exchange(phovo_ctx* ctx);
+/* The whole row-sharded Optimize() (AN:500-563) in ONE call, one persistent cooperative launch per active level on
+ * every rank: phase A over the level, phase B over this rank's band of source rows, and the 29 sums exchanged INSIDE
+ * the kernel over the imported NVLink exchange areas (flags as the cross-GPU barrier); every rank takes the same
+ * step redundantly, nothing returns to the host between iterations.  A level with fewer than `min_shard_pixels`
+ * pixels is not sharded: every rank runs the whole level (identical results, no exchange) -- small levels are
+ * bound by the latency of an iteration, to which an exchange only adds.  All ranks must call this with the same
+ * frames, configuration, initial state and min_shard_pixels; blocks until this rank's result is back.
+ * Analytic modes; needs phovo_shard_configure and, for world > 1, the peer areas of every rank imported. */
+int phovo_shard_optimize(phovo_ctx* ctx, int min_shard_pixels);
 
 #ifdef __cplusplus
 }

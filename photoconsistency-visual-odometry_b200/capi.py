@@ -114,6 +114,7 @@ SIGNATURES = {
     "phovo_shard_peer_export": (C.c_int, [_vp, _vp]),
     "phovo_shard_peer_import": (C.c_int, [_vp, C.c_int, _vp]),
     "phovo_shard_partial_exchange": (C.c_int, [_vp]),
+    "phovo_shard_optimize": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None

@@ -440,9 +440,22 @@ __device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, cons
   J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
 }
 
+// Row-sharded use (one 8K pair over several GPUs): `S.world` > 1.  Every rank runs phase A over the
+// whole level (the winner map needs every source pixel), phase B over ITS band of source rows [L.row_begin,
+// L.row_end), sums its partials as before -- and then the ranks exchange the 29 sums INSIDE the kernel: CTA 0
+// stores them into every peer's exchange area over NVLink and releases a flag, every CTA of every rank waits for
+// the `world` flags in its own area and adds the slots in rank order.  All CTAs of all ranks end up with bitwise
+// the same totals and take the same step: no broadcast, no third grid barrier, no host in the loop.  The exchange
+// areas are double-buffered by epoch parity; a rank can run at most one exchange ahead of the slowest one.
+struct ShardArgs {
+  ShardExchange* const* peers;     // device array [world] of exchange areas (own one included), or nullptr
+  int rank, world;
+  unsigned long long epoch_base;   // epoch of iteration `it` of this launch is epoch_base + it + 1
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
-                                                               phovo_iter_stats* log) {
+                                                               phovo_iter_stats* log, ShardArgs S) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
@@ -506,7 +519,8 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
         accumulate_row(acc, J, res);
       }
     } else {
-      for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+      const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;   // the whole level unless row-sharded
+      for (int i = i_begin + blockIdx.x * kCoopBlock + tid; i < i_end; i += stride) {
         const int win = __ldcg(P.winner + i);
         P.winner[i] = -1;
         double res = 0.;
@@ -519,6 +533,11 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
         analytic_jacobian_row<MODE>(L, P, T, spsr, spcr, i, J);
         accumulate_row(acc, J, res);
         acc[28] += 1.;
+      }
+      // row-sharded: the slots outside the band were bid for as well and must be clean for the next iteration
+      if (i_begin > 0 || i_end < n) {
+        for (int i = blockIdx.x * kCoopBlock + tid; i < i_begin; i += stride) P.winner[i] = -1;
+        for (int i = i_end + blockIdx.x * kCoopBlock + tid; i < n; i += stride) P.winner[i] = -1;
       }
     }
     {
@@ -537,6 +556,36 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
         double t = 0.;
 #pragma unroll
         for (int k = 0; k < kCoopBlock / 32; ++k) t += smem[k * PHOVO_ACC_STRIDE + tid];
+        s_tot[tid] = t;
+      }
+      __syncthreads();
+    }
+    // ---- row-sharded: all-reduce of the 29 sums over NVLink peer memory, in rank order ----
+    if (S.world > 1) {
+      const unsigned long long epoch = S.epoch_base + (unsigned long long)it + 1ull;
+      const int parity = (int)(epoch & 1ull);
+      ShardExchange* mine = S.peers[S.rank];
+      if (blockIdx.x == 0) {
+        const int w = tid >> 5, v = tid & 31;
+        if (w < S.world) {
+          ShardExchange* peer = S.peers[w];
+          peer->slots[parity][S.rank][v] = v < PHOVO_NACC ? s_tot[v] : 0.;
+          __threadfence_system();
+          __syncwarp();
+          if (v == 0) st_release_sys(&peer->flags[S.rank], epoch);
+        }
+      }
+      if (tid < S.world) {
+        long long spins = 0;
+        while (ld_acquire_sys(&mine->flags[tid]) < epoch) {
+          if (++spins > (1ll << 24)) { mine->error = 1; break; }   // seconds: a peer never arrived
+          __nanosleep(20);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        double t = 0.;
+        for (int r = 0; r < S.world; ++r) t += __ldcg(&mine->slots[parity][r][tid]);
         s_tot[tid] = t;
       }
       __syncthreads();
@@ -1002,7 +1051,8 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
 // One cooperative launch for the whole iteration loop of a level.  Returns the number of launches
 // (1) or -1 if cooperative launch is not available (the caller falls back to the graph path).
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err) {
+                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err,
+                      ShardExchange* const* peers_dev, int rank, int world, unsigned long long epoch_base) {
   int* g_coop_blocks_per_sm = ls->coop_blocks_per_sm;
   const int m = L.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
   void* fn = m == 2 ? (void*)k_level_coop<3> : m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
@@ -1018,7 +1068,8 @@ int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   LevelParams Lc = L; LevelPtrs Pc = P;
-  void* args[] = {&Lc, &Pc, &pose, &partials, &log};
+  ShardArgs Sc; Sc.peers = peers_dev; Sc.rank = rank; Sc.world = peers_dev ? world : 1; Sc.epoch_base = epoch_base;
+  void* args[] = {&Lc, &Pc, &pose, &partials, &log, &Sc};
   *err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopBlock), args, 0, stream);
   if (*err != cudaSuccess) return -1;
   *grid_out = grid;

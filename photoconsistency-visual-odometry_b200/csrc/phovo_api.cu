@@ -1100,6 +1100,8 @@ static int optimize_ceres(phovo_ctx* ctx) {
 // row-sharded single pair (BASELINE config 5): each rank evaluates a band of source rows; the
 // caller all-reduces the 32-double buffer between phovo_shard_partial and phovo_shard_step.
 // ---------------------------------------------------------------------------------------------
+static int upload_peer_table(phovo_ctx* ctx);
+
 extern "C" int phovo_shard_configure(phovo_ctx* ctx, int rank, int world) {
   if (!ctx || world < 1 || rank < 0 || rank >= world) return PHOVO_E_INVALID;
   ctx->shard_rank = rank; ctx->shard_world = world;
@@ -1197,15 +1199,8 @@ extern "C" int phovo_shard_peer_import(phovo_ctx* ctx, int peer_rank, const void
 extern "C" int phovo_shard_partial_exchange(phovo_ctx* ctx) {
   if (!ctx || ctx->shard_level < 0) return PHOVO_E_INVALID;
   if (ctx->shard_world > PHOVO_SHARD_MAX_WORLD) return ctx->fail(PHOVO_E_UNSUPPORTED, "peer exchange supports up to 8 ranks");
-  for (int r = 0; r < ctx->shard_world; ++r)
-    if (!ctx->xchg_peer[r]) return ctx->fail(PHOVO_E_INVALID, "peer exchange areas are not all imported (phovo_shard_peer_export / _import)");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->xchg_peers_dev) CK(cudaMalloc((void**)&ctx->xchg_peers_dev, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD));
-  if (ctx->xchg_table_dirty) {
-    CK(cudaMemcpyAsync(ctx->xchg_peers_dev, ctx->xchg_peer, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->xchg_table_dirty = false;
-  }
+  { int rc = upload_peer_table(ctx); if (rc) return rc; }
   const LevelParams L = ctx->level_params(ctx->shard_level);
   const LevelPtrs P = ctx->level_ptrs(ctx->shard_level);
   int grid = 0;
@@ -1215,6 +1210,57 @@ extern "C" int phovo_shard_partial_exchange(phovo_ctx* ctx) {
                                           ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch);
   CK(cudaGetLastError());
   return PHOVO_OK;
+}
+
+static int upload_peer_table(phovo_ctx* ctx) {
+  for (int r = 0; r < ctx->shard_world; ++r)
+    if (!ctx->xchg_peer[r]) return ctx->fail(PHOVO_E_INVALID, "peer exchange areas are not all imported (phovo_shard_peer_export / _import)");
+  if (!ctx->xchg_peers_dev) CK(cudaMalloc((void**)&ctx->xchg_peers_dev, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD));
+  if (ctx->xchg_table_dirty) {
+    CK(cudaMemcpyAsync(ctx->xchg_peers_dev, ctx->xchg_peer, sizeof(ShardExchange*) * PHOVO_SHARD_MAX_WORLD, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->xchg_table_dirty = false;
+  }
+  return PHOVO_OK;
+}
+
+extern "C" int phovo_shard_optimize(phovo_ctx* ctx, int min_shard_pixels) {
+  if (!ctx) return PHOVO_E_INVALID;
+  int rc = ready_to_solve(ctx);
+  if (rc) return rc;
+  if (ctx->cfg.mode != PHOVO_MODE_ANALYTIC_REF && ctx->cfg.mode != PHOVO_MODE_ANALYTIC_FIXED)
+    return ctx->fail(PHOVO_E_UNSUPPORTED, "the row-sharded loop implements the analytic solver only");
+  if (ctx->coop_broken) return ctx->fail(PHOVO_E_UNSUPPORTED, "cooperative launch is not available on this device");
+  if (ctx->shard_world > PHOVO_SHARD_MAX_WORLD) return ctx->fail(PHOVO_E_UNSUPPORTED, "peer exchange supports up to 8 ranks");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->shard_world > 1 && (rc = upload_peer_table(ctx))) return rc;
+  if ((rc = ensure_log(ctx, total_iterations(ctx) + 1))) return rc;
+  ctx->setup_timed = false;
+  CK(cudaEventRecord(ctx->ev_time[2], ctx->stream));
+  ctx->launches += launch_set_state(ctx->stream, ctx->d_pose, nullptr, ctx->state, ctx->log_cap);
+  for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {   // AN:502-503
+    const int M = ctx->cfg.max_num_iterations[level];
+    if (M <= 0) continue;
+    LevelParams L = ctx->level_params(level);                          // carries this rank's row band
+    const LevelPtrs P = ctx->level_ptrs(level);
+    const bool shard = ctx->shard_world > 1 && (long long)L.rows * L.cols >= (long long)min_shard_pixels;
+    if (!shard) { L.row_begin = 0; L.row_end = L.rows; }
+    int grid = 0; cudaError_t e = cudaSuccess;
+    const int n = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, &ctx->launch_state, ctx->sm_count, &grid, &e,
+                                    shard ? ctx->xchg_peers_dev : nullptr, ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch);
+    if (n < 0) { cudaGetLastError(); return ctx->cuda_fail("cooperative launch of the sharded level loop", e); }
+    ctx->launches += n;
+    if (shard) ctx->xchg_epoch += (unsigned long long)M;               // every rank advances by the same amount
+  }
+  CK(cudaGetLastError());
+  ctx->last_path = 2;
+  rc = read_back(ctx);
+  if (ctx->xchg_own) {
+    int err = 0;
+    CK(cudaMemcpy(&err, &ctx->xchg_own->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return ctx->fail(PHOVO_E_CUDA, "peer exchange timed out waiting for another rank");
+  }
+  return rc;
 }
 
 extern "C" int phovo_shard_step(phovo_ctx* ctx, int* done) {

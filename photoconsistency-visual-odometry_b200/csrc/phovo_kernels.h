@@ -88,8 +88,12 @@ int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev*
                              phovo_iter_stats* log);
 int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n, int sm_count);
 // persistent cooperative kernel: the whole iteration loop of one level in one launch (analytic modes)
+struct ShardExchange;
+// peers_dev != nullptr and world > 1: the row-sharded loop (L.row_begin / row_end = this rank's band) with the sums
+// exchanged inside the kernel over NVLink peer memory; epochs epoch_base + 1 ... epoch_base + L.max_iters are used.
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
-                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err);
+                      phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err,
+                      ShardExchange* const* peers_dev = nullptr, int rank = 0, int world = 1, unsigned long long epoch_base = 0);
 
 // thread-block-cluster kernel for small levels (analytic modes, <= 8 192 px): the loop of one level inside ONE
 // cluster of 16 CTAs, winner map in distributed shared memory.  Returns 1 (launched), 0 (level does not

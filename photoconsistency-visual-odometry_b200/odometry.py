@@ -371,3 +371,8 @@ class CPhotoconsistencyOdometryCuda:
 
     def ShardPartialExchange(self):
         self._check(self._L.phovo_shard_partial_exchange(self._h))
+
+    def ShardOptimize(self, min_shard_pixels=0):
+        """The whole row-sharded Optimize() in one call: persistent kernel per level, sums exchanged inside the kernel
+        over NVLink peer memory; levels below `min_shard_pixels` run unsharded on every rank."""
+        self._check(self._L.phovo_shard_optimize(self._h, int(min_shard_pixels)))

@@ -77,6 +77,21 @@ class RowShardedAlignment:
                 odo.ShardPeerImport(r, h)
             dist.barrier(group=group)
 
+    def optimize_fused(self, initial_state=None, min_shard_pixels=262144):
+        """Optimize() with the sharded loop INSIDE the persistent kernel (exchange "peer" only): one cooperative launch
+        per active level on every rank, the 29 sums exchanged in the kernel over NVLink peer memory, no host in the
+        loop.  Levels below `min_shard_pixels` run unsharded on every rank (an exchange costs more than it saves
+        there).  Returns (state, executed iterations per level dict)."""
+        if self.world > 1 and self.exchange != "peer":
+            raise ValueError('the fused loop needs exchange="peer"')
+        odo = self.odo
+        odo.SetInitialStateVector(np.zeros(6) if initial_state is None else initial_state)
+        odo.ShardOptimize(min_shard_pixels)
+        executed = {}
+        for e in odo.IterationStats():
+            executed[e["level"]] = executed.get(e["level"], 0) + 1
+        return odo.GetOptimalStateVector(), executed
+
     def optimize(self, initial_state=None):
         """Returns (state, executed iterations per level dict).  Lock step: every rank executes the
         same number of exchanges because every rank holds the same state."""
