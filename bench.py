@@ -661,14 +661,23 @@ def main():
     h2d = odo.BatchLastH2DBytes()          # counted by the library from the copies it issued
     d2h = P * (6 * 8 + phovo.MAXL * 4)
     del hg0, hd0, hg1
-    h2d_peak = pinned_h2d_peak(torch, dev, stream)        # this rank's link, nothing else running on it
-    tp = torch.tensor([h2d_peak], dtype=torch.float64, device=dev)
+    # the ceiling `e2e` can be held against, measured in this run: one big copy from pinned memory per rank,
+    # (a) one rank at a time with the other links idle, (b) all ranks at once (what the e2e steps do)
+    h2d_solo = 0.0
+    for r in range(world):
+        barrier()
+        if r == rank:
+            h2d_solo = pinned_h2d_peak(torch, dev, stream, reps=3)
+    barrier()
+    h2d_peak = pinned_h2d_peak(torch, dev, stream)
+    tp = torch.tensor([h2d_peak, h2d_solo], dtype=torch.float64, device=dev)
     if world > 1:
         gathered_peaks = [torch.zeros_like(tp) for _ in range(world)]
         dist.all_gather(gathered_peaks, tp)
-        h2d_peaks = [float(x.item()) for x in gathered_peaks]
+        h2d_peaks = [float(x[0].item()) for x in gathered_peaks]
+        h2d_solos = [float(x[1].item()) for x in gathered_peaks]
     else:
-        h2d_peaks = [h2d_peak]
+        h2d_peaks, h2d_solos = [h2d_peak], [h2d_solo]
 
     if rank != 0:
         if world > 1:
@@ -741,9 +750,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_step_s * 1e3, "steps": e2e_steps,
                     "link_gbs": h2d / e2e_step_s / 1e9, "h2d_peak_gbs": min(h2d_peaks), "h2d_peak_gbs_per_rank": h2d_peaks,
+                    "h2d_peak_gbs_per_rank_alone": h2d_solos, "h2d_aggregate_gbs": h2d * world / e2e_step_s / 1e9,
+                    "h2d_aggregate_peak_gbs": sum(h2d_peaks),
                     "link_frac_of_h2d_peak": h2d / e2e_step_s / 1e9 / min(h2d_peaks),
                     "host_cpus_bound_to_gpu_numa_node": numa,
-                    "upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe per rank; link_gbs = per-rank H2D bytes / e2e step time (all ranks upload at once), h2d_peak_gbs = one 1 GiB cudaMemcpyAsync from pinned memory measured in this run with the link otherwise idle (slowest rank)" % (h2d, h2d_full)},
+                    "upload": "rows no active level reads are not uploaded: %d of %d input bytes cross PCIe per rank; link_gbs = per-rank H2D bytes / e2e step time (all ranks upload at once), h2d_peak_gbs = one 1 GiB cudaMemcpyAsync from pinned memory per rank, all ranks copying at once (slowest rank; per rank in h2d_peak_gbs_per_rank), h2d_peak_gbs_per_rank_alone = the same copy with the other ranks idle: the gap between the two is the host fabric (PCIe root complexes / memory), not this library" % (h2d, h2d_full)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "latency_us_per_pair_per_sm": align_t / (P / min(P, 148)) * 1e6, "secondary": sec}
     print(json.dumps(line))

@@ -447,13 +447,32 @@ __device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, cons
 // the `world` flags in its own area and adds the slots in rank order.  All CTAs of all ranks end up with bitwise
 // the same totals and take the same step: no broadcast, no third grid barrier, no host in the loop.  The exchange
 // areas are double-buffered by epoch parity; a rank can run at most one exchange ahead of the slowest one.
+//
+// Phase A is sharded too: a source pixel at row r lands at most h rows away, h = ceil(fy (dmin B1 + e1max) / Zlow) + 2
+// from the current pose (B1 bounds the coefficient of d in Y' - ryi Z', e1max the offset, Zlow = dmin m2min - |z| <= Z'
+// for every valid pixel; (d B1 + e1max) / (d m2min - |z|) decreases in d, so the smallest valid depth of the level
+// -- measured once per frame, `dmin` -- gives the maximum).  A rank therefore warps the source rows of its band
+// +- h only: every pixel that can bid for a slot of the band is among them; the slots outside the band that those
+// pixels may have bid for (+- 2 h) are cleaned after phase B.  No bound (Zlow <= 0, state not finite) => the whole level.
 struct ShardArgs {
   ShardExchange* const* peers;     // device array [world] of exchange areas (own one included), or nullptr
   int rank, world;
   unsigned long long epoch_base;   // epoch of iteration `it` of this launch is epoch_base + it + 1
+  const double* dmin;              // smallest depth of the level inside (min_depth, max_depth); nullptr: no halo bound
 };
 
-template <int MODE>
+__device__ __forceinline__ int shard_halo_rows(const LevelParams& L, const Pose& T, double dmin) {
+  const double rx = fmax(fabs(L.ox), fabs((double)(L.cols - 1) - L.ox)) * fabs(L.inv_fx);
+  const double ry = fmax(fabs(L.oy), fabs((double)(L.rows - 1) - L.oy)) * fabs(L.inv_fy);
+  const double B1 = (fabs(T.R10) * rx + fabs(T.R12)) + (fabs(T.R11 - T.R22) + fabs(T.R20) * rx) * ry + fabs(T.R21) * ry * ry;
+  const double e1m = fabs(T.y) + ry * fabs(T.z);
+  const double zlow = dmin * (T.R22 - fabs(T.R20) * rx - fabs(T.R21) * ry) - fabs(T.z);
+  const double dy = fabs(L.fy) * (dmin * B1 + e1m) / zlow * (1.0 + 0x1p-20) + 0x1p-10;
+  if (!(zlow > 0.) || !(dy < (double)L.rows)) return L.rows;      // NaN compares false: no bound
+  return (int)ceil(dy) + 2;
+}
+
+template <int MODE, bool SHARD>
 __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
                                                                phovo_iter_stats* log, ShardArgs S) {
   namespace cg = cooperative_groups;
@@ -477,7 +496,14 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
     // reference arithmetic runs only for the pixels whose estimate lies next to a rounding boundary
     // (~2e-4 of them); the graph / stream drivers (k_winner) run it for every pixel ----
     const EstimateConst E = estimate_const(L, T);
-    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+    // row-sharded: the source rows that can reach this rank's band (see ShardArgs); otherwise the whole level
+    int halo = 0, a_begin = 0, a_end = n;
+    if (SHARD && (L.row_begin > 0 || L.row_end < L.rows)) {
+      halo = S.dmin ? shard_halo_rows(L, T, __ldg(S.dmin)) : L.rows;
+      a_begin = max(0, L.row_begin - halo) * L.cols;
+      a_end = min(L.rows, L.row_end + halo) * L.cols;
+    }
+    for (int i = a_begin + blockIdx.x * kCoopBlock + tid; i < a_end; i += stride) {
       const double d = __ldg(P.D0 + i);
       const int r = i / L.cols, c = i - r * L.cols;
       const bool dep = (L.min_depth < d) & (d < L.max_depth);                  // strict bounds, AN:279-280
@@ -534,10 +560,11 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
         accumulate_row(acc, J, res);
         acc[28] += 1.;
       }
-      // row-sharded: the slots outside the band were bid for as well and must be clean for the next iteration
-      if (i_begin > 0 || i_end < n) {
-        for (int i = blockIdx.x * kCoopBlock + tid; i < i_begin; i += stride) P.winner[i] = -1;
-        for (int i = i_end + blockIdx.x * kCoopBlock + tid; i < n; i += stride) P.winner[i] = -1;
+      // row-sharded: slots outside the band that the warped rows may have bid for must be clean for the next iteration
+      if (SHARD && (i_begin > 0 || i_end < n)) {
+        const int c_begin = max(0, L.row_begin - 2 * halo) * L.cols, c_end = min(L.rows, L.row_end + 2 * halo) * L.cols;
+        for (int i = c_begin + blockIdx.x * kCoopBlock + tid; i < i_begin; i += stride) P.winner[i] = -1;
+        for (int i = i_end + blockIdx.x * kCoopBlock + tid; i < c_end; i += stride) P.winner[i] = -1;
       }
     }
     {
@@ -561,7 +588,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       __syncthreads();
     }
     // ---- row-sharded: all-reduce of the 29 sums over NVLink peer memory, in rank order ----
-    if (S.world > 1) {
+    if (SHARD && S.world > 1) {
       const unsigned long long epoch = S.epoch_base + (unsigned long long)it + 1ull;
       const int parity = (int)(epoch & 1ull);
       ShardExchange* mine = S.peers[S.rank];
@@ -982,6 +1009,17 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
   }
 }
 
+// smallest depth of a level inside (lo, hi), as the bits of a positive double (ordered like unsigned integers)
+__global__ void __launch_bounds__(256) k_min_valid_depth(const double* __restrict__ D, int n, double lo, double hi, unsigned long long* out) {
+  unsigned long long m = 0x7ff0000000000000ull;   // +inf: no valid pixel
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double d = __ldg(D + i);
+    if ((lo < d) & (d < hi) & (d > 0.)) m = min(m, (unsigned long long)__double_as_longlong(d));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(out, m);
+}
+
 inline int grid_for(int n, int sm_count) {
   // one pixel per thread up to 8 CTAs per SM, then a fixed persistent grid (grid-stride loop);
   // the grid is a pure function of the level size and the device, so the partial-sum order is reproducible.
@@ -998,6 +1036,13 @@ int launch_fill_i32(cudaStream_t stream, int* p, int value, size_t n, int sm_cou
   const size_t want = (n + 255) / 256, cap = (size_t)partials_blocks(sm_count);
   const int blocks = (int)(want < cap ? (want ? want : 1) : cap);
   k_fill_i32<<<blocks, 256, 0, stream>>>(p, value, n);
+  return 1;
+}
+
+int launch_min_valid_depth(cudaStream_t stream, const double* D, int n, double lo, double hi, double* out, int sm_count) {
+  cudaMemsetAsync(out, 0xff, sizeof(double), stream);                 // all ones: larger than any positive double's bits
+  const int want = (n + 255) / 256, cap = partials_blocks(sm_count);
+  k_min_valid_depth<<<want < cap ? (want > 0 ? want : 1) : cap, 256, 0, stream>>>(D, n, lo, hi, (unsigned long long*)out);
   return 1;
 }
 
@@ -1052,10 +1097,13 @@ int launch_iteration_kernels(cudaStream_t stream, const LevelParams& L, const Le
 // (1) or -1 if cooperative launch is not available (the caller falls back to the graph path).
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err,
-                      ShardExchange* const* peers_dev, int rank, int world, unsigned long long epoch_base) {
+                      ShardExchange* const* peers_dev, int rank, int world, unsigned long long epoch_base, const double* level_dmin) {
   int* g_coop_blocks_per_sm = ls->coop_blocks_per_sm;
-  const int m = L.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
-  void* fn = m == 2 ? (void*)k_level_coop<3> : m ? (void*)k_level_coop<1> : (void*)k_level_coop<0>;
+  const bool shard = peers_dev != nullptr && world > 1 && L.mode != PHOVO_MODE_BIOBJECTIVE;
+  const int m = shard ? (L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 4 : 3)
+                      : L.mode == PHOVO_MODE_BIOBJECTIVE ? 2 : L.mode == PHOVO_MODE_ANALYTIC_FIXED ? 1 : 0;
+  void* fn = m == 4 ? (void*)k_level_coop<1, true> : m == 3 ? (void*)k_level_coop<0, true>
+           : m == 2 ? (void*)k_level_coop<3, false> : m ? (void*)k_level_coop<1, false> : (void*)k_level_coop<0, false>;
   if (g_coop_blocks_per_sm[m] < 0) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kCoopBlock, 0) != cudaSuccess) nb = 0;
@@ -1068,7 +1116,7 @@ int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   LevelParams Lc = L; LevelPtrs Pc = P;
-  ShardArgs Sc; Sc.peers = peers_dev; Sc.rank = rank; Sc.world = peers_dev ? world : 1; Sc.epoch_base = epoch_base;
+  ShardArgs Sc; Sc.peers = shard ? peers_dev : nullptr; Sc.rank = rank; Sc.world = shard ? world : 1; Sc.epoch_base = epoch_base; Sc.dmin = level_dmin;
   void* args[] = {&Lc, &Pc, &pose, &partials, &log, &Sc};
   *err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopBlock), args, 0, stream);
   if (*err != cudaSuccess) return -1;

@@ -337,7 +337,7 @@ extern "C" int phovo_destroy(phovo_ctx* ctx) {
   cudaFree(ctx->d_gain);
   cudaFree(ctx->winner); cudaFree(ctx->valid); cudaFree(ctx->scratch64[0]); cudaFree(ctx->scratch64[1]); cudaFree(ctx->partials);
   cudaFree(ctx->stage_gray[0]); cudaFree(ctx->stage_gray[1]); cudaFree(ctx->stage_depth);
-  cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_eval);
+  cudaFree(ctx->d_pose); cudaFree(ctx->d_log); cudaFree(ctx->d_state_in); cudaFree(ctx->d_shard); cudaFree(ctx->d_level_dmin); cudaFree(ctx->d_eval);
   cudaFree(ctx->dump_res); cudaFree(ctx->dump_jac);
   cudaFree(ctx->warp_keys); for (int k = 0; k < 3; ++k) cudaFree(ctx->warp_io[k]);
   for (int r = 0; r < 8; ++r)
@@ -486,6 +486,7 @@ extern "C" int phovo_set_source(phovo_ctx* ctx, const uint8_t* gray, size_t gray
   CK(cudaEventRecord(ctx->ev_time[1], ctx->stream));
   ctx->have_src = true;
   ctx->setup_timed = true;
+  ctx->level_dmin_valid = false;
   return wait_uploads(ctx);
 }
 
@@ -559,6 +560,7 @@ extern "C" int phovo_promote_target_to_source(phovo_ctx* ctx, const void* depth,
   if ((rc = finish_uploads(ctx))) return rc;
   if ((rc = build_depth(ctx, dd, depth_type, dds, depth_type == PHOVO_DEPTH_U16 ? depth_scale : 1.0))) return rc;
   ctx->have_src = true; ctx->have_tgt = false; ctx->setup_timed = true;
+  ctx->level_dmin_valid = false;
   return wait_uploads(ctx);
 }
 
@@ -1235,6 +1237,14 @@ extern "C" int phovo_shard_optimize(phovo_ctx* ctx, int min_shard_pixels) {
   CK(cudaSetDevice(ctx->device));
   if (ctx->shard_world > 1 && (rc = upload_peer_table(ctx))) return rc;
   if ((rc = ensure_log(ctx, total_iterations(ctx) + 1))) return rc;
+  if (ctx->shard_world > 1 && !ctx->level_dmin_valid) {   // once per source frame: what bounds the row displacement (ShardArgs)
+    if (!ctx->d_level_dmin) CK(cudaMalloc((void**)&ctx->d_level_dmin, sizeof(double) * PHOVO_MAX_LEVELS));
+    for (int level = 0; level < ctx->cfg.num_levels; ++level)
+      if (ctx->cfg.max_num_iterations[level] > 0)
+        ctx->launches += launch_min_valid_depth(ctx->stream, ctx->D0[level], ctx->lrows[level] * ctx->lcols[level], ctx->cfg.min_depth,
+                                                ctx->cfg.max_depth, ctx->d_level_dmin + level, ctx->sm_count);
+    ctx->level_dmin_valid = true;
+  }
   ctx->setup_timed = false;
   CK(cudaEventRecord(ctx->ev_time[2], ctx->stream));
   ctx->launches += launch_set_state(ctx->stream, ctx->d_pose, nullptr, ctx->state, ctx->log_cap);
@@ -1247,7 +1257,8 @@ extern "C" int phovo_shard_optimize(phovo_ctx* ctx, int min_shard_pixels) {
     if (!shard) { L.row_begin = 0; L.row_end = L.rows; }
     int grid = 0; cudaError_t e = cudaSuccess;
     const int n = launch_level_coop(ctx->stream, L, P, ctx->d_pose, ctx->partials, ctx->d_log, &ctx->launch_state, ctx->sm_count, &grid, &e,
-                                    shard ? ctx->xchg_peers_dev : nullptr, ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch);
+                                    shard ? ctx->xchg_peers_dev : nullptr, ctx->shard_rank, ctx->shard_world, ctx->xchg_epoch,
+                                    shard ? ctx->d_level_dmin + level : nullptr);
     if (n < 0) { cudaGetLastError(); return ctx->cuda_fail("cooperative launch of the sharded level loop", e); }
     ctx->launches += n;
     if (shard) ctx->xchg_epoch += (unsigned long long)M;               // every rank advances by the same amount

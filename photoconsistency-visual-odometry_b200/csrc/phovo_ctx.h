@@ -74,6 +74,8 @@ struct phovo_ctx {
   // row sharding
   int shard_rank = 0, shard_world = 1, shard_level = -1;
   double* d_shard = nullptr;
+  double* d_level_dmin = nullptr;          // [PHOVO_MAX_LEVELS] smallest valid depth per level of the current source frame
+  bool level_dmin_valid = false;
   // fused peer-store exchange: own area (cudaMalloc, IPC-exported), peers' areas (IPC-opened)
   phovo::ShardExchange* xchg_own = nullptr;
   phovo::ShardExchange* xchg_peer[8] = {nullptr};

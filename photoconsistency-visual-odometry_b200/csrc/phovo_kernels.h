@@ -71,7 +71,7 @@ int partials_blocks(int sm_count);
 // What the launchers of the persistent kernels cache per DEVICE (function attributes are per device
 // and per function; a context lives on one device, so the cache lives in the context).
 struct LaunchState {
-  int coop_blocks_per_sm[3] = {-1, -1, -1};   // k_level_coop<0>, <1>, <3>
+  int coop_blocks_per_sm[5] = {-1, -1, -1, -1, -1};   // k_level_coop<0>, <1>, <3>, and the row-sharded <0>, <1>
   int ceres_blocks_per_sm = -1;
   bool cluster_prepared[2] = {false, false};  // k_level_cluster<0>, <1>
 };
@@ -93,7 +93,11 @@ struct ShardExchange;
 // exchanged inside the kernel over NVLink peer memory; epochs epoch_base + 1 ... epoch_base + L.max_iters are used.
 int launch_level_coop(cudaStream_t stream, const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                       phovo_iter_stats* log, LaunchState* ls, int sm_count, int* grid_out, cudaError_t* err,
-                      ShardExchange* const* peers_dev = nullptr, int rank = 0, int world = 1, unsigned long long epoch_base = 0);
+                      ShardExchange* const* peers_dev = nullptr, int rank = 0, int world = 1, unsigned long long epoch_base = 0,
+                      const double* level_dmin = nullptr);
+// out[0] = the smallest depth of the level inside (lo, hi) (+inf / all-ones bits if there is none): the row-sharded loop
+// bounds how far a pixel can move between rows with it
+int launch_min_valid_depth(cudaStream_t stream, const double* D, int n, double lo, double hi, double* out, int sm_count);
 
 // thread-block-cluster kernel for small levels (analytic modes, <= 8 192 px): the loop of one level inside ONE
 // cluster of 16 CTAs, winner map in distributed shared memory.  Returns 1 (launched), 0 (level does not
