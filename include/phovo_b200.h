@@ -229,6 +229,17 @@ int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int cols,
                       const uint8_t* gray1,
                       const double* initial_states /* [P][6] or NULL = zeros */,
                       double* states, int32_t* iterations);
+/* Which implementation the last batch call took: 1 = the shared-memory-resident batch kernels (analytic solvers, no blur,
+ * active levels up to ~22 K px: one streaming pyramid pass + one persistent launch per level), 2 = everything else
+ * (Ceres-mode and photometric + depth solver, blurred levels, larger levels): the pairs go one by one through the
+ * general path on a pool of 4 per-pair contexts, one host thread each -- same results as a loop over the per-pair API. */
+int phovo_batch_last_path(const phovo_ctx* ctx);
+/* phovo_batch_align for the photometric + depth solver (PHOVO_MODE_BIOBJECTIVE), which also reads the TARGET depth
+ * (depth1 [P][rows][cols], same type / scale as depth0; BiObjective.h:567-579).  Other modes ignore depth1. */
+int phovo_batch_align_with_target_depth(phovo_ctx* ctx, int num_pairs, int rows, int cols,
+                                        const uint8_t* gray0, const void* depth0, int depth_type, double depth_scale,
+                                        const uint8_t* gray1, const void* depth1,
+                                        const double* initial_states, double* states, int32_t* iterations);
 /* Same work with device-resident inputs and outputs left on the device (states_dev [P][6] f64,
  * iters_dev [P][PHOVO_MAX_LEVELS] i32); asynchronous on the context stream. */
 int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows, int cols,

@@ -94,6 +94,8 @@ SIGNATURES = {
     "phovo_graph_error": (C.c_char_p, [_vp]),
     "phovo_set_build_all_levels": (C.c_int, [_vp, C.c_int]),
     "phovo_batch_align": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
+    "phovo_batch_align_with_target_depth": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "phovo_batch_last_path": (C.c_int, [_vp]),
     "phovo_batch_align_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
     "phovo_batch_set_record_stats": (C.c_int, [_vp, C.c_int]),
     "phovo_batch_get_iter_stats": (C.c_int, [_vp, C.c_int, C.c_int, _stp]),

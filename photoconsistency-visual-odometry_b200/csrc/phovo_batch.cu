@@ -9,6 +9,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "phovo_batch.h"
@@ -42,6 +46,10 @@ struct phovo_batch_state {
   int sm_count = 0;
   cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // before pyramid / between / after align
   bool timed = false;
+  // batches the shared-memory-resident kernels cannot take (Ceres / photometric + depth solver, blurred levels, levels
+  // beyond the shared-memory budget) run pair by pair on a small pool of per-pair contexts, one host thread each
+  std::vector<phovo_ctx*> pool;
+  int last_path = 0;                                   // 1: shared-memory-resident batch kernels, 2: pool of per-pair contexts
 };
 
 #define CK(call)                                                      \
@@ -72,6 +80,7 @@ void phovo_batch_release(phovo_ctx* ctx) {
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   cudaFreeHost(b->h_states_pinned); cudaFreeHost(b->h_iters_pinned);
+  for (phovo_ctx* c : b->pool) phovo_destroy(c);
   delete b;
   ctx->batch = nullptr;
 }
@@ -106,7 +115,7 @@ static int make_params(phovo_ctx* ctx, int num_pairs, int rows, int cols, int lo
   if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
   if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
   if (ctx->cfg.mode == PHOVO_MODE_CERES || ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE)
-    return ctx->fail(PHOVO_E_UNSUPPORTED, "the batch kernel implements the analytic solver only");
+    return ctx->fail(PHOVO_E_UNSUPPORTED, "the shared-memory-resident batch kernels implement the analytic solver only");
   memset(bp, 0, sizeof(*bp));
   bp->num_pairs = num_pairs; bp->rows = rows; bp->cols = cols;
   bp->mode = ctx->cfg.mode; bp->log_cap = log_cap;
@@ -261,6 +270,95 @@ static int prepare_log(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int*
   return PHOVO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The pool path.  phovo_batch_align never refuses a configuration: what the shared-memory-resident kernels cannot
+// take goes, pair by pair, through the general path (phovo_set_source / phovo_set_target / phovo_optimize: the
+// persistent cooperative kernels of kernels_align.cu) on kPoolContexts child contexts of the same device, each driven
+// by its own host thread, so that the frame set-up of one pair overlaps the iteration loop of another.  Same results
+// as calling the per-pair API in a loop, by construction.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPoolContexts = 4;
+
+static bool host_readable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type != cudaMemoryTypeDevice;
+}
+
+static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                         const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
+                         const double* initial_states, double* states, int32_t* iterations) {
+  if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
+  if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
+  if (ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE && !depth1)
+    return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth: use phovo_batch_align_with_target_depth");
+  const int workers = std::min(kPoolContexts, num_pairs);
+  while ((int)b->pool.size() < workers) {
+    phovo_ctx* c = nullptr;
+    if (phovo_create(ctx->device, &c) != PHOVO_OK) return ctx->fail(PHOVO_E_CUDA, std::string("batch pool: ") + phovo_last_error(nullptr));
+    b->pool.push_back(c);
+  }
+  std::vector<double> init_host;
+  if (initial_states && !host_readable(initial_states)) {
+    init_host.resize((size_t)num_pairs * 6);
+    CK(cudaMemcpy(init_host.data(), initial_states, sizeof(double) * init_host.size(), cudaMemcpyDeviceToHost));
+    initial_states = init_host.data();
+  }
+  const size_t frame = (size_t)rows * cols, delt = depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2;
+  std::atomic<int> next(0), first_rc(PHOVO_OK);
+  std::mutex mu; std::string message;
+  auto work = [&](phovo_ctx* c) {
+    auto fail = [&](int rc) {
+      std::lock_guard<std::mutex> g(mu);
+      if (first_rc.load() == PHOVO_OK) { first_rc.store(rc); message = phovo_last_error(c); }
+    };
+    int rc = phovo_set_config(c, &ctx->cfg);
+    if (!rc) rc = phovo_set_intrinsics(c, ctx->K);
+    if (!rc) rc = phovo_set_execution(c, ctx->execution);
+    if (rc) { fail(rc); return; }
+    const double zeros[6] = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+      const int p = next.fetch_add(1);
+      if (p >= num_pairs || first_rc.load() != PHOVO_OK) return;
+      rc = phovo_set_source(c, gray0 + (size_t)p * frame, cols, (const char*)depth0 + (size_t)p * frame * delt, depth_type, cols * delt,
+                            depth_scale, rows, cols);
+      if (!rc) rc = phovo_set_target(c, gray1 + (size_t)p * frame, cols, rows, cols);
+      if (!rc && ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE)
+        rc = phovo_set_target_depth(c, (const char*)depth1 + (size_t)p * frame * delt, depth_type, cols * delt, depth_scale);
+      if (!rc) rc = phovo_set_initial_state(c, initial_states ? initial_states + (size_t)p * 6 : zeros);
+      if (!rc) rc = phovo_optimize(c);
+      if (rc && rc != PHOVO_E_NUMERIC) { fail(rc); return; }     // a non-finite state is a result (the reference returns NaN too)
+      if (states) phovo_get_state(c, states + (size_t)p * 6);
+      if (iterations) {
+        int32_t* it = iterations + (size_t)p * PHOVO_MAX_LEVELS;
+        for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) it[l] = 0;
+        phovo_iter_stats e;
+        const int n = phovo_num_iter_stats(c);
+        for (int k = 0; k < n; ++k)
+          if (phovo_get_iter_stats(c, k, &e) == PHOVO_OK && e.level >= 0 && e.level < PHOVO_MAX_LEVELS) it[e.level] += 1;
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int w = 1; w < workers; ++w) threads.emplace_back(work, b->pool[w]);
+  work(b->pool[0]);
+  for (auto& t : threads) t.join();
+  for (int w = 0; w < workers; ++w) ctx->launches += b->pool[w]->launches, b->pool[w]->launches = 0;
+  b->last_pairs = 0; b->log_fetched = false; b->last_h2d_bytes = 0; b->timed = false; b->last_path = 2;
+  if (first_rc.load() != PHOVO_OK) return ctx->fail(first_rc.load(), "batch pool: " + message);
+  return PHOVO_OK;
+}
+
+// true if the batch must take the pool path (see make_params for what the shared-memory-resident kernels accept)
+static bool needs_pool(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, size_t* smem, int* rc_out) {
+  if (ctx->cfg.mode == PHOVO_MODE_CERES || ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE) { *rc_out = PHOVO_OK; return true; }
+  *rc_out = make_params(ctx, num_pairs, rows, cols, log_cap, bp, smem);
+  if (*rc_out == PHOVO_E_UNSUPPORTED) { *rc_out = PHOVO_OK; return true; }
+  return false;
+}
+
+extern "C" int phovo_batch_last_path(const phovo_ctx* ctx) { return ctx && ctx->batch ? ctx->batch->last_path : 0; }
+
 extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows, int cols, const uint8_t* gray0,
                                         const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1,
                                         const double* initial_states, double* states, int32_t* iters) {
@@ -272,7 +370,18 @@ extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows,
   int log_cap = 0;
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
   BatchParams bp; size_t smem = 0;
-  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
+  if (needs_pool(ctx, num_pairs, rows, cols, log_cap, &bp, &smem, &rc)) {
+    // pool path: synchronous; results go to the caller's device arrays through host temporaries
+    std::vector<double> hs((size_t)num_pairs * 6); std::vector<int32_t> hi((size_t)num_pairs * PHOVO_MAX_LEVELS);
+    CK(cudaStreamSynchronize(ctx->stream));      // the inputs may still be in production on the context's stream
+    if ((rc = batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, hs.data(), hi.data()))) return rc;
+    CK(cudaMemcpyAsync(states, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(iters, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHOVO_OK;
+  }
+  if (rc) return rc;
+  b->last_path = 1;
   CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs + kBatchStoreSlackBytes));
   return run_device(ctx, b, bp, smem, ctx->stream, gray0, depth0, depth_type, depth_scale, gray1, b->store,
                     initial_states, states, iters, log_cap ? b->log : nullptr, log_cap ? b->log_counts : nullptr);
@@ -295,7 +404,10 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
   int log_cap = 0;
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
   BatchParams bp; size_t smem = 0;
-  if ((rc = make_params(ctx, num_pairs, rows, cols, log_cap, &bp, &smem))) return rc;
+  if (needs_pool(ctx, num_pairs, rows, cols, log_cap, &bp, &smem, &rc))
+    return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, states, iterations);
+  if (rc) return rc;
+  b->last_path = 1;
   CK(ensure(&b->states, &b->states_cap, (size_t)num_pairs * 6));
   CK(ensure(&b->iters, &b->iters_cap, (size_t)num_pairs * PHOVO_MAX_LEVELS));
   CK(ensure(&b->store, &b->store_cap, (size_t)bp.record_bytes * num_pairs + kBatchStoreSlackBytes));
@@ -400,4 +512,17 @@ extern "C" int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int in
   if (index < 0 || index >= n) return PHOVO_E_INVALID;
   *out = ctx->batch->h_log[(size_t)pair * ctx->batch->log_per_pair + index];
   return PHOVO_OK;
+}
+
+extern "C" int phovo_batch_align_with_target_depth(phovo_ctx* ctx, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                                                   const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1,
+                                                   const void* depth1, const double* initial_states, double* states, int32_t* iterations) {
+  if (!ctx || !gray0 || !depth0 || !gray1 || !depth1) return PHOVO_E_INVALID;
+  if (depth_type < 0 || depth_type > 2) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
+  if (ctx->cfg.mode != PHOVO_MODE_BIOBJECTIVE)      // the other solvers ignore the target depth, like the reference (AN:484)
+    return phovo_batch_align(ctx, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, initial_states, states, iterations);
+  CK(cudaSetDevice(ctx->device));
+  phovo_batch_state* b; int rc = get_state(ctx, &b);
+  if (rc) return rc;
+  return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
 }

@@ -238,8 +238,14 @@ class CPhotoconsistencyOdometryCuda:
         self._check(self._L.phovo_synchronize(self._h))
 
     # batch of independent pairs --------------------------------------------------------------
-    def BatchAlign(self, gray0, depth0, gray1, initial_states=None, depth_scale=1.0):
-        """Host (numpy / pinned torch) or device (torch) arrays [P,R,C]; returns (states[P,6], iterations[P,MAXL])."""
+    def BatchLastPath(self):
+        """1: the shared-memory-resident batch kernels ran; 2: the pool of per-pair contexts (Ceres / photometric + depth
+        solver, blurred or large levels)."""
+        return int(self._L.phovo_batch_last_path(self._h))
+
+    def BatchAlign(self, gray0, depth0, gray1, initial_states=None, depth_scale=1.0, depth1=None):
+        """Host (numpy / pinned torch) or device (torch) arrays [P,R,C]; returns (states[P,6], iterations[P,MAXL]).
+        `depth1` (target depth, same type as depth0) is read by the photometric + depth solver only."""
         P, R, Cc = tuple(gray0.shape)
         if isinstance(depth0, np.ndarray):
             dtype = {np.dtype(np.float64): capi.DEPTH_F64, np.dtype(np.float32): capi.DEPTH_F32,
@@ -251,6 +257,11 @@ class CPhotoconsistencyOdometryCuda:
         states = np.zeros((P, 6))
         iters = np.zeros((P, capi.MAXL), dtype=np.int32)
         init = None if initial_states is None else np.ascontiguousarray(initial_states, dtype=np.float64)
+        if depth1 is not None:
+            self._check(self._L.phovo_batch_align_with_target_depth(self._h, P, R, Cc, capi._ptr(gray0), capi._ptr(depth0), dtype,
+                                                                    float(depth_scale), capi._ptr(gray1), capi._ptr(depth1), capi._ptr(init),
+                                                                    states.ctypes.data, iters.ctypes.data))
+            return states, iters
         self._check(self._L.phovo_batch_align(self._h, P, R, Cc, capi._ptr(gray0), capi._ptr(depth0), dtype,
                                               float(depth_scale), capi._ptr(gray1), capi._ptr(init),
                                               states.ctypes.data, iters.ctypes.data))

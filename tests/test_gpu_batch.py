@@ -121,11 +121,9 @@ def test_batch_shortcuts_do_not_change_results(phovo, shape, cfg_name):
     runs = []
     for flags in (0, 1, 2, 3):
         odo.BatchSetDebugFlags(flags)
-        try:
-            st, it = odo.BatchAlign(g0, d0.astype(np.float32), g1)
-        except phovo.PhovoError as e:
-            assert e.code == phovo.capi.E_UNSUPPORTED
-            pytest.skip("level does not fit the batch kernel")
+        st, it = odo.BatchAlign(g0, d0.astype(np.float32), g1)
+        if odo.BatchLastPath() != 1:
+            pytest.skip("a level does not fit the shared-memory-resident kernels: the pool path ran (no shortcuts to switch off)")
         logs = [odo.BatchIterationStats(p) for p in range(P)]
         runs.append((st, it, logs))
     odo.BatchSetDebugFlags(0)
@@ -247,34 +245,44 @@ def test_batch_unusual_depth_values_and_ranges(phovo, oracle):
                 assert np.array_equal(np.isnan(st[p]), np.isnan(o.state()))
 
 
-def test_batch_unsupported_configurations_fail_loudly(phovo):
+def test_batch_configurations_beyond_the_resident_kernels_take_the_pool_path(phovo):
+    """phovo_batch_align never refuses a configuration: a level that does not fit in shared memory, blurred levels and the
+    Ceres-mode solver go pair by pair through the general path on a pool of per-pair contexts -- bitwise the states
+    and iteration counts of the per-pair API."""
     K = phovo.synth.K_FRAME_ALIGNMENT
-    g0, d0, g1, _ = phovo.synth.make_batch(1, 480, 640, K=K, seed0=1)
+    P = 6
+    g0, d0, g1, _ = phovo.synth.make_batch(P, 480, 640, K=K, seed0=1)
     d0 = d0.astype(np.float32)
+    cases = []
     cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
     cfg.max_num_iterations[1] = 3          # level 1 = 240x320 = 76 800 px does not fit in shared memory
-    odo = make_odo(phovo, cfg, K)
-    with pytest.raises(phovo.PhovoError) as e:
-        odo.BatchAlign(g0, d0, g1)
-    assert e.value.code == phovo.capi.E_UNSUPPORTED
+    cases.append(cfg)
     cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
     cfg.blur_filter_size[3] = 3
-    odo.SetConfig(cfg)
-    with pytest.raises(phovo.PhovoError) as e:
-        odo.BatchAlign(g0, d0, g1)
-    assert e.value.code == phovo.capi.E_UNSUPPORTED
-    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
-    odo.SetConfig(cfg)
-    with pytest.raises(phovo.PhovoError) as e:
-        odo.BatchAlign(g0, d0, g1)
-    assert e.value.code == phovo.capi.E_UNSUPPORTED
+    cases.append(cfg)
+    cases.append(phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi))
+    odo = make_odo(phovo, cases[0], K)
+    for cfg in cases:
+        odo.SetConfig(cfg)
+        st, it = odo.BatchAlign(g0, d0, g1)
+        assert odo.BatchLastPath() == 2
+        single = make_odo(phovo, cfg, K)
+        for p in range(P):
+            single.SetSourceFrame(g0[p], d0[p]); single.SetTargetFrame(g1[p]); single.SetInitialStateVector(np.zeros(6))
+            single.Optimize()
+            assert np.array_equal(st[p], single.GetOptimalStateVector()), (cfg.mode, p)
+            assert int(it[p].sum()) == len(single.IterationStats()) > 0
+    # back on the resident kernels
+    odo.SetConfig(phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi))
+    odo.BatchAlign(g0, d0, g1)
+    assert odo.BatchLastPath() == 1
     # all levels inactive: states pass through
     cfg = phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi)
     for l in range(4):
         cfg.max_num_iterations[l] = 0
     odo.SetConfig(cfg)
-    st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((1, 6), 0.01))
-    assert np.array_equal(st, np.full((1, 6), 0.01)) and not it.any()
+    st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((P, 6), 0.01))
+    assert np.array_equal(st, np.full((P, 6), 0.01)) and not it.any()
 
 
 def test_batch_at_scale_matches_general_path(phovo):

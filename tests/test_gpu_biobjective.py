@@ -64,7 +64,7 @@ def test_biobjective_matches_reference_source_live_640x480(phovo, tmp_path):
     assert np.max(np.abs(s - sref)) < 1e-9
 
 
-def test_biobjective_needs_target_depth_and_is_not_batched(phovo):
+def test_biobjective_needs_target_depth_also_in_a_batch(phovo):
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, d1 = phovo.synth.make_pair(120, 160, K=K, seed=1)
     cfg = phovo.configs.to_config("test_3_level_all_active", phovo.capi, mode=phovo.MODE_BIOBJECTIVE)
@@ -78,5 +78,13 @@ def test_biobjective_needs_target_depth_and_is_not_batched(phovo):
         odo.Optimize()
     assert e.value.code == phovo.capi.E_INVALID
     with pytest.raises(phovo.PhovoError) as e:
-        odo.BatchAlign(g0[None], d0[None], g1[None])
-    assert e.value.code == phovo.capi.E_UNSUPPORTED
+        odo.BatchAlign(g0[None], d0[None], g1[None])           # the batch entry needs the target depth too
+    assert e.value.code == phovo.capi.E_INVALID
+    # with it, the batch goes pair by pair through the general path (pool of per-pair contexts): same as the per-pair API
+    odo.SetTargetFrame(g1, d1)
+    odo.Optimize()
+    st, it = odo.BatchAlign(np.stack([g0, g0, g0]), np.stack([d0, d0, d0]), np.stack([g1, g1, g1]), depth1=np.stack([d1, d1, d1]))
+    assert odo.BatchLastPath() == 2
+    for p in range(3):
+        assert np.array_equal(st[p], odo.GetOptimalStateVector())
+        assert int(it[p].sum()) == len(odo.IterationStats()) > 0

@@ -171,6 +171,7 @@ def test_cuda_ceres_matches_reference_functor_live(phovo, tmp_path):
         shape = odo.LevelImage(0, lvl).shape
         for st in (np.zeros(6), phovo.synth.XI_CONFIG1 * 0.7):
             res_ref, jac_ref = ref.evaluate(shape, st)
+            res_ref = res_ref.ravel()
             res, jac = odo.EvalResiduals(lvl, st, shape)
             assert np.array_equal(np.abs(res) > 1e-9, np.abs(res_ref) > 1e-9)          # same scatter, also at the identity
             assert np.max(np.abs(res - res_ref)) <= 1e-13
