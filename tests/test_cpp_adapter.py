@@ -4,8 +4,9 @@ unmodified; only OpenCV / Eigen are the stand-ins of oracle/shim), checked again
 
   * tests/cpp/frame_alignment_app.cpp -- headless mirror of both apps' main() (strided cv::Mat_ inputs,
     the VO loop, warpImage through the adapter);
-  * the reference's apps/PhotoconsistencyFrameAlignment/PhotoconsistencyFrameAlignment.cpp ITSELF with
-    exactly the INTEGRATION.md patch applied (USE_PHOTOCONSISTENCY_ODOMETRY_METHOD == 3), built by
+  * the reference's apps/PhotoconsistencyFrameAlignment/PhotoconsistencyFrameAlignment.cpp and
+    apps/PhotoconsistencyVisualOdometry/PhotoconsistencyVisualOdometry.cpp THEMSELVES with exactly the
+    INTEGRATION.md patch applied (USE_PHOTOCONSISTENCY_ODOMETRY_METHOD == 3), built by
     tests/cpp/build_adapter_test.sh into tests/cpp/_build/ (git-ignored; travels to the GPU box).
 """
 import os
@@ -20,6 +21,7 @@ from test_gpu_parity import conv_cfg
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 APP = os.path.join(ROOT, "tests", "cpp", "_build", "frame_alignment_app")
 REF_APP = os.path.join(ROOT, "tests", "cpp", "_build", "reference_frame_alignment")
+REF_VO_APP = os.path.join(ROOT, "tests", "cpp", "_build", "reference_visual_odometry")
 
 
 def build_app():
@@ -173,3 +175,48 @@ def test_visual_odometry_app_trajectory_matches_oracle(phovo, oracle, tmp_path):
                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
         assert abs(np.linalg.norm(q) - 1) < 1e-12 and np.max(np.abs(R - pose[:3, :3])) < 1e-9
+
+
+@pytest.mark.gpu
+def test_reference_visual_odometry_app_method_3_trajectory_matches_oracle(phovo, oracle, tmp_path):
+    """apps/PhotoconsistencyVisualOdometry/PhotoconsistencyVisualOdometry.cpp, unmodified but for the INTEGRATION.md
+    patch, on a recorded sequence (rgb.txt / depth.txt + image files read by the reference's own CCameraRecord /
+    CImageReader): the TUM trajectory it writes (:240-243) equals the oracle's frame-by-frame loop."""
+    build_app()
+    K = phovo.synth.K_VISUAL_ODOMETRY                      # hard-coded in the app (VisualOdometry.cpp:171-173)
+    n = 5
+    os.makedirs(tmp_path / "rgb"); os.makedirs(tmp_path / "depth")
+    frames, stamps = [], []
+    with open(tmp_path / "rgb.txt", "w") as fr, open(tmp_path / "depth.txt", "w") as fd:
+        fr.write("# color images\n# timestamp filename\n"); fd.write("# depth maps\n# timestamp filename\n")
+        for k in range(n):
+            g, d = phovo.synth.make_sequence_frame(k, 480, 640, K=K)
+            raw = np.rint(d * 5000.).astype(np.uint16)                     # the app scales by 1/5000 (:163)
+            write_pgm(str(tmp_path / "rgb" / ("%04d.pgm" % k)), g)
+            write_pgm(str(tmp_path / "depth" / ("%04d.pgm" % k)), raw)
+            stamp = 1305031102.175304 + 0.033 * k
+            fr.write("%.6f rgb/%04d.pgm\n" % (stamp, k)); fd.write("%.6f depth/%04d.pgm\n" % (stamp, k))
+            frames.append((g, raw.astype(np.float64) * (1. / 5000.))); stamps.append(stamp)
+    name = "config_5_level_optimization_analytic"
+    yml = phovo.configs.write_yaml(name, str(tmp_path))
+    traj = str(tmp_path / "out" / "trajectory.txt")                       # the app creates the directory (:109-116)
+    r = subprocess.run([REF_VO_APP, yml, str(tmp_path), traj], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.loadtxt(traj)
+    assert got.shape == (n - 1, 8)
+    cfg = phovo.configs.to_config(name, phovo.capi)
+    pose = np.eye(4)
+    for k in range(1, n):
+        o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+        o.set_source(*frames[k - 1])
+        o.set_target(frames[k][0])
+        o.set_initial_state(np.zeros(6))
+        o.optimize()
+        pose = pose @ np.linalg.inv(o.rt())
+        assert abs(got[k - 1, 0] - stamps[k]) < 1e-5
+        assert np.max(np.abs(got[k - 1, 1:4] - pose[:3, 3])) < 1e-9
+        x, y, z, w = got[k - 1, 4:8]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.max(np.abs(R - pose[:3, :3])) < 1e-9
