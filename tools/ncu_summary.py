@@ -9,7 +9,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__cycles_elapsed.avg", "smsp__cycles_active.avg", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
         "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
@@ -28,6 +28,15 @@ def main(rep):
         for k in KEYS:
             if k in d:
                 print("  %-72s %s %s" % (k, d[k], u[k]))
+        try:   # achieved DRAM and L2 bandwidth of the launch (north star: both against the ~8 TB/s HBM peak / the L2 roofline)
+            sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            ts = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+            t = float(d["gpu__time_duration.sum"]) * ts[u["gpu__time_duration.sum"]]
+            dram = sum(float(d["dram__bytes_%s.sum" % k]) * sc[u["dram__bytes_%s.sum" % k]] for k in ("read", "write"))
+            sect = float(d["lts__t_sectors.sum"]) * {"sector": 1.0, "Ksector": 1e3, "Msector": 1e6, "Gsector": 1e9}.get(u["lts__t_sectors.sum"], 1.0)
+            print("  %-72s %.1f GB/s DRAM, %.1f GB/s L2 (32 B sectors)" % ("achieved bandwidth", dram / t / 1e9, sect * 32 / t / 1e9))
+        except Exception:
+            pass
         st = {k: float(v) for k, v in d.items() if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")}
         print("  stall reasons (warps per issue-active cycle): " + ", ".join(
             "%s %.2f" % (k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v) for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]))

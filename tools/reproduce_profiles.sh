@@ -12,14 +12,15 @@ python bench.py > "$OUT/${TAG}_bench.json"
 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_reference_arm.json"
 # python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 3 > "$OUT/${TAG}_bench_8gpu.json"
 
-# 2. ncu: launch list of the default bench command, then the full capture of the two level kernels
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null
+# 2. ncu: launch list of the default bench command, then the full capture of one step's three batch kernels
+#    (k_batch_pyramid + one k_batch_level per active level; under ncu the overlapped level launches are serialised)
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_batch --csv --log-file "$OUT/${TAG}_launches_default_bench.csv" \
-    python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null
-python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/prof_${TAG}_bench.log"
-ncu --set full --clock-control none --import-source on -k regex:k_batch_level --launch-skip 6 -c 2 -f -o "$OUT/prof_${TAG}" \
-    python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null
-python tools/ncu_summary.py "$OUT/prof_${TAG}.ncu-rep" > "$OUT/${TAG}_k_batch_level_ncu_full.txt"
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null
+python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > "$OUT/prof_${TAG}_bench.log"
+ncu --set full --clock-control none --import-source on -k regex:k_batch --launch-skip 9 -c 3 -f -o "$OUT/prof_${TAG}" \
+    python bench.py --pairs 2368 --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null
+python tools/ncu_summary.py "$OUT/prof_${TAG}.ncu-rep" > "$OUT/${TAG}_k_batch_ncu_full.txt"
 python tools/make_roofline_inputs.py "$OUT/prof_${TAG}.ncu-rep" "$OUT/prof_${TAG}_bench.log" profiles/r01_fp64_peak.jsonl "$TAG" > "$OUT/roofline_inputs.json"
 
 # 3. parity sweeps (GPU vs the CPU oracle)
@@ -32,10 +33,11 @@ python tools/bench_latency.py --mode single > "$OUT/${TAG}_latency_single_pair.j
 python tools/bench_latency.py --mode single --path 3 > "$OUT/${TAG}_latency_single_pair_cluster_driver.json"
 python tools/bench_latency.py --mode vo --frames 1000 > "$OUT/${TAG}_latency_vo_sequence_1000frames.json"
 python tools/bench_latency.py --mode ceres > "$OUT/${TAG}_latency_ceres_config.json"
+python bench.py --workload 8k > "$OUT/${TAG}_bench_8k_1gpu.json"     # N > 1: torchrun ... bench.py --workload 8k --gpus N
 python tools/run_row_sharded.py > "$OUT/${TAG}_row_sharded_8k_1gpu.json"
 python tools/bench_dataset.py > "$OUT/${TAG}_dataset_vo_on_disk.json"
 
 # 5. hardware probes the rooflines lean on
-for p in fp64_peak fp64_latency dmma_probe; do
+for p in fp64_peak fp64_latency dmma_probe issue_probe; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o "tools/$p" "tools/$p.cu" && "./tools/$p" > "$OUT/${TAG}_$p.jsonl"
 done
