@@ -515,8 +515,8 @@ def run_8k(args, phovo, rank, world, local_rank, host_threads):
                 "max_abs_state_diff_vs_single_gpu": float(np.max(np.abs(st - s_single))), "iterations_equal_single_gpu": executed == per_level,
                 "ranks_bitwise_identical": bool((gathered == gathered[0]).all().item()),
                 "nccl_allreduce_32_doubles_us": nccl_us,
-                "e2e": {"value": wall, "unit": "ms", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": int(odo.GetConfig().num_levels) * 0 + 192 + 392 * iters,
-                        "note": "the call a user makes (SetInitialStateVector + ShardOptimize + GetOptimalStateVector) timed on the host; the frames are set once and stay resident, per step the initial state goes up and the state + iteration log come back"},
+                "e2e": {"value": wall, "unit": "ms", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 48 + 256 + 352 * iters,
+                        "note": "the call a user makes (SetInitialStateVector + ShardOptimize + GetOptimalStateVector) timed on the host; the frames are set once and stay resident, per step the initial state (48 B) goes up and the device pose block (256 B) + one 352-byte log entry per executed iteration come back"},
                 "gpu_launches": int(len(executed) + 1), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
@@ -729,6 +729,7 @@ def main():
                 "algorithmic_bytes_per_launch": iter_bytes, "kernel_ms": align_t * 1e3,
                 "share_of_step": align_t / (align_t + pyr_t),
                 "pixel_iterations_per_launch": px_iters,
+                "ncu_dram_gbs": prof.get("dram_gbs"), "ncu_l2_gbs": prof.get("l2_gbs"),       # achieved DRAM / L2 bandwidth of the level kernels under ncu (north star: both beside the HBM peak)
                 "note": "achieved / peak / frac are the contract's HBM figure: algorithmic bytes = SURVEY 8(d), 20 B per pixel per executed GN iteration + 216 B of sums, over the measured HBM copy bandwidth. The level is resident in shared memory, so DRAM traffic is the packed record read once (traffic) and the unit that binds the kernel is the FP64 pipe together with the issue slots it blocks: see fp64 (thread-instructions per pixel-iteration from ncu x executed pixel-iterations / kernel time, over the measured DFMA peak) and issue (issue cycles the kernel's instruction counts need at the least / scheduler cycles it takes)",
                 "fp64": fp64, "issue": issue,
                 "other_kernels": {"k_batch_pyramid": {"kernel_ms": pyr_t * 1e3, "algorithmic_bytes_per_launch": setup_bytes,

@@ -381,6 +381,7 @@ extern "C" int phovo_set_config(phovo_ctx* ctx, const phovo_config* cfg) {
   ctx->cfg = *cfg;
   for (int l = cfg->num_levels; l < PHOVO_MAX_LEVELS; ++l) ctx->cfg.max_num_iterations[l] = 0;
   ctx->have_src = ctx->have_tgt = false;  // pyramids depend on the config (AN:474: m_NumOptimizationLevels)
+  ctx->level_dmin_valid = false;
   ctx->invalidate_graph();
   return PHOVO_OK;
 }
@@ -420,6 +421,7 @@ extern "C" int phovo_set_mode(phovo_ctx* ctx, int mode) {
 extern "C" int phovo_set_depth_range(phovo_ctx* ctx, double min_depth, double max_depth) {
   if (!ctx) return PHOVO_E_INVALID;
   ctx->cfg.min_depth = min_depth; ctx->cfg.max_depth = max_depth;
+  ctx->level_dmin_valid = false;     // the smallest VALID depth of a level depends on the range
   ctx->invalidate_graph();
   return PHOVO_OK;
 }

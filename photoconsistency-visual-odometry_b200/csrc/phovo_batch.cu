@@ -292,6 +292,8 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
   if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
   if (ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE && !depth1)
     return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth: use phovo_batch_align_with_target_depth");
+  // the pool's contexts run on their own streams: device-resident inputs produced on this context's stream must be complete
+  CK(cudaStreamSynchronize(ctx->stream));
   const int workers = std::min(kPoolContexts, num_pairs);
   while ((int)b->pool.size() < workers) {
     phovo_ctx* c = nullptr;
@@ -373,7 +375,6 @@ extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows,
   if (needs_pool(ctx, num_pairs, rows, cols, log_cap, &bp, &smem, &rc)) {
     // pool path: synchronous; results go to the caller's device arrays through host temporaries
     std::vector<double> hs((size_t)num_pairs * 6); std::vector<int32_t> hi((size_t)num_pairs * PHOVO_MAX_LEVELS);
-    CK(cudaStreamSynchronize(ctx->stream));      // the inputs may still be in production on the context's stream
     if ((rc = batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, hs.data(), hi.data()))) return rc;
     CK(cudaMemcpyAsync(states, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(iters, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice, ctx->stream));
