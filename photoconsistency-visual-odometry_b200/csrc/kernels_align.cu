@@ -210,16 +210,11 @@ __global__ void __launch_bounds__(kBlock) k_winner_bi(LevelParams L, LevelPtrs P
 // Jacobian row k of the stacked 2N-row system of the photometric + depth solver (see the comment
 // above k_winner_bi); returns false for a zero row.  CG: read the validity flags with ld.global.cg
 // (they were written by other SMs inside the same cooperative launch).
-template <bool CG>
-__device__ __forceinline__ bool bi_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
-                                                double gain, int n, int k, double J[6]) {
-  int p = -1; bool depth_row = false;
-  const bool vk = k < n && (CG ? __ldcg(P.valid + k) : P.valid[k]);
-  if (k > 0 && vk) p = k;
-  else if ((k & 1) == 0 && (CG ? __ldcg(P.valid + (k >> 1)) : P.valid[k >> 1])) { p = k >> 1; depth_row = true; }
-  if (p < 0) return false;
+// Row of pixel p (depth row or intensity row) from values already loaded: d = D0[p], (gx, gy) = the gradient of the
+// target intensity (intensity row) or of the target depth / max_depth (depth row) at index p.
+__device__ __forceinline__ void bi_jacobian_core(const LevelParams& L, const Pose& T, double spsr, double spcr, double gain,
+                                                 int p, bool depth_row, double d, double gx, double gy, double J[6]) {
   const int r = p / L.cols, c = p - r * L.cols;
-  const double d = __ldg(P.D0 + p);
   const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
   const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
   const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
@@ -231,7 +226,6 @@ __device__ __forceinline__ bool bi_jacobian_row(const LevelParams& L, const Leve
   const double dp0 = T.cy * q2, dp1 = T.sy * q2;
   const double dr0 = fma(T.R02, py, -(T.R01 * d)), dr1 = fma(T.R12, py, -(T.R11 * d)), dr2 = fma(T.R22, py, -(T.R21 * d));
   // v = gradient * projection Jacobian (:380-400), then v * jacobianRt
-  const double gx = depth_row ? __ldg(P.GxD + p) : __ldg(P.Gx + p), gy = depth_row ? __ldg(P.GyD + p) : __ldg(P.Gy + p);
   const double v0 = gx * L.fx * iz, v1 = gy * L.fy * iz;
   const double v2 = -(fma(gx * L.fx, X, gy * L.fy * Y) * iz * iz);
   J[0] = v0; J[1] = v1; J[2] = v2;
@@ -242,6 +236,25 @@ __device__ __forceinline__ bool bi_jacobian_row(const LevelParams& L, const Leve
     J[0] = gain * J[0]; J[1] = gain * J[1]; J[2] = gain * (J[2] - 1.);
     J[3] = gain * J[3]; J[4] = gain * (J[4] - Zp); J[5] = gain * (J[5] - dr2);
   }
+}
+
+// Which pixel's row is Jacobian row k of the stacked 2N-row system (see the comment above k_winner_bi): vk = pixel k is
+// valid (false for k >= N), vh = pixel k/2 is valid.  Returns the pixel or -1 for a zero row.
+__device__ __forceinline__ int bi_row_owner(int k, bool vk, bool vh, bool* depth_row) {
+  *depth_row = false;
+  if (k > 0 && vk) return k;
+  if ((k & 1) == 0 && vh) { *depth_row = true; return k >> 1; }
+  return -1;
+}
+
+// Jacobian row k, loads included (the stream / graph drivers).
+__device__ __forceinline__ bool bi_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
+                                                double gain, int n, int k, double J[6]) {
+  bool depth_row;
+  const int p = bi_row_owner(k, k < n && P.valid[k], P.valid[k >> 1] != 0, &depth_row);
+  if (p < 0) return false;
+  const double gx = depth_row ? __ldg(P.GxD + p) : __ldg(P.Gx + p), gy = depth_row ? __ldg(P.GyD + p) : __ldg(P.Gy + p);
+  bi_jacobian_core(L, T, spsr, spcr, gain, p, depth_row, __ldg(P.D0 + p), gx, gy, J);
   return true;
 }
 
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(kBlock) k_normal_eq_bi(LevelParams L, LevelPtr
     if (DUMP && dump_res) dump_res[k] = res;
     if (k < n && P.valid[k]) acc[28] += 1.;
     double J[6];
-    if (!bi_jacobian_row<false>(L, P, T, spsr, spcr, gain, n, k, J)) continue;
+    if (!bi_jacobian_row(L, P, T, spsr, spcr, gain, n, k, J)) continue;
     accumulate_row(acc, J, res);
     if (DUMP && dump_jac) for (int a = 0; a < 6; ++a) dump_jac[(size_t)k * 6 + a] = J[a];
   }
@@ -418,16 +431,15 @@ constexpr int kCoopBlock = 256;
 // Jacobian row of a valid source pixel i (analytic modes): compact closed form of AN:243-342 with
 // the image gradient folded in.  Shared by the cooperative and the cluster kernel.
 template <int MODE>
-__device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
-                                                      int i, double J[6]) {
+__device__ __forceinline__ void analytic_jacobian_core(const LevelParams& L, const Pose& T, double spsr, double spcr,
+                                                       int i, double d, double gx, double gy, double J[6]) {
   const int r = i / L.cols, c = i - r * L.cols;
-  const double d = __ldg(P.D0 + i);
   const double px = ((double)c - L.ox) * d * L.inv_fx, py = ((double)r - L.oy) * d * L.inv_fy;
   const double q0 = fma(T.R00, px, fma(T.R01, py, T.R02 * d));
   const double q1 = fma(T.R10, px, fma(T.R11, py, T.R12 * d));
   const double q2 = fma(T.R20, px, fma(T.R21, py, T.R22 * d));
   const double iz = rcp_1ulp(q2 + T.z);
-  const double ga = __ldg(P.Gx + i) * L.fx * iz, gb = __ldg(P.Gy + i) * L.fy * iz;
+  const double ga = gx * L.fx * iz, gb = gy * L.fy * iz;
   const double A = MODE == 0 ? fma(px, T.x, q0) : q0 + T.x;   // AN:253 bug-compatible / Maxima-exact
   const double B = q1 + T.y;
   J[0] = ga;
@@ -438,6 +450,12 @@ __device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, cons
   J[4] = fma(q2, fma(ga, T.cy, gb * T.sy), Zp * J[2]);
   const double Zr = fma(T.R22, py, -(T.R21 * d));
   J[5] = fma(ga, fma(T.R02, py, -(T.R01 * d)), fma(gb, fma(T.R12, py, -(T.R11 * d)), Zr * J[2]));
+}
+
+template <int MODE>
+__device__ __forceinline__ void analytic_jacobian_row(const LevelParams& L, const LevelPtrs& P, const Pose& T, double spsr, double spcr,
+                                                      int i, double J[6]) {
+  analytic_jacobian_core<MODE>(L, T, spsr, spcr, i, __ldg(P.D0 + i), __ldg(P.Gx + i), __ldg(P.Gy + i), J);
 }
 
 // Row-sharded use (one 8K pair over several GPUs): `S.world` > 1.  Every rank runs phase A over the
@@ -472,11 +490,18 @@ __device__ __forceinline__ int shard_halo_rows(const LevelParams& L, const Pose&
   return (int)ceil(dy) + 2;
 }
 
-template <int MODE, bool SHARD>
-__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
-                                                               phovo_iter_stats* log, ShardArgs S) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+// SLOT: the same loop run by ONE CTA on its own pair (the batch slot kernels below): the grid barriers become
+// block barriers, the CTA is "block 0 of a grid of 1".
+template <bool SLOT>
+__device__ __forceinline__ void level_barrier() {
+  if (SLOT) __syncthreads();
+  else cooperative_groups::this_grid().sync();
+}
+
+template <int MODE, bool SHARD, bool SLOT>
+__device__ __forceinline__ void level_loop(const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                                           phovo_iter_stats* log, const ShardArgs& S) {
+  const int bid = SLOT ? 0 : (int)blockIdx.x, nblk = SLOT ? 1 : (int)gridDim.x;
   __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
   __shared__ double s_tot[32];
   __shared__ PoseDev s_pose;
@@ -487,7 +512,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
   int log_count = s_pose.log_count;
   const int log_capacity = s_pose.log_capacity;
   const int n = L.rows * L.cols;
-  const int stride = gridDim.x * kCoopBlock;
+  const int stride = nblk * kCoopBlock;
   int it = 0;
   for (; it < L.max_iters; ++it) {
     Pose T;
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       a_begin = max(0, L.row_begin - halo) * L.cols;
       a_end = min(L.rows, L.row_end + halo) * L.cols;
     }
-    for (int i = a_begin + blockIdx.x * kCoopBlock + tid; i < a_end; i += stride) {
+    for (int i = a_begin + bid * kCoopBlock + tid; i < a_end; i += stride) {
       const double d = __ldg(P.D0 + i);
       const int r = i / L.cols, c = i - r * L.cols;
       const bool dep = (L.min_depth < d) & (d < L.max_depth);                  // strict bounds, AN:279-280
@@ -521,7 +546,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       } else if (ok) atomicMax(P.winner + t, i);
       P.valid[i] = ok;
     }
-    grid.sync();
+    level_barrier<SLOT>();
     // ---- phase B: residual + Jacobian + normal equations ----
     double acc[PHOVO_NACC];
 #pragma unroll
@@ -529,54 +554,71 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
     const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
     if (MODE == 3) {
       const double gain = __ldg(P.gain);
-      for (int k = blockIdx.x * kCoopBlock + tid; k < 2 * n; k += stride) {
+      for (int k = bid * kCoopBlock + tid; k < 2 * n; k += stride) {
+        // every array the row may read is loaded BEFORE anything depends on a loaded value: one or two memory round trips
+        // per row instead of six in a chain (winner -> I0[src]; valid[k] -> valid[k/2] -> D0[p] -> gradient), at the price
+        // of loads whose values are not used (the loop is latency-bound, not bandwidth-bound)
+        const int kh = k >> 1;
+        const bool lo = k < n;
         const int wkey = __ldcg(P.winner + k);
+        const bool vk = lo && __ldcg(P.valid + k) != 0;
+        const bool vh = __ldcg(P.valid + kh) != 0;
+        const double i1 = lo ? __ldg(P.I1 + k) : 0., d1 = __ldg(P.D1 + kh);
+        const double d0k = lo ? __ldg(P.D0 + k) : 0., d0h = __ldg(P.D0 + kh);
+        const double gxk = lo ? __ldg(P.Gx + k) : 0., gyk = lo ? __ldg(P.Gy + k) : 0.;
+        const double gxh = __ldg(P.GxD + kh), gyh = __ldg(P.GyD + kh);
         P.winner[k] = -1;
         double res = 0.;
         if (wkey > 0) {
           const int src = (wkey - 1) >> 1;
-          if (((wkey - 1) & 1) == 0) res = __ldg(P.I1 + k) - __ldg(P.I0 + src);
-          else res = gain * (__ldg(P.D1 + (k >> 1)) - __ldg(P.D0 + src));
+          if (((wkey - 1) & 1) == 0) res = i1 - __ldg(P.I0 + src);                 // slot k = t
+          else res = gain * (d1 - __ldg(P.D0 + src));                               // slot k = 2 t
           acc[27] = fma(res, res, acc[27]);
         }
-        if (k < n && __ldcg(P.valid + k)) acc[28] += 1.;
+        if (vk) acc[28] += 1.;
+        bool depth_row;
+        const int p = bi_row_owner(k, vk, vh, &depth_row);
+        if (p < 0) continue;
         double J[6];
-        if (!bi_jacobian_row<true>(L, P, T, spsr, spcr, gain, n, k, J)) continue;
+        bi_jacobian_core(L, T, spsr, spcr, gain, p, depth_row, depth_row ? d0h : d0k, depth_row ? gxh : gxk, depth_row ? gyh : gyk, J);
         accumulate_row(acc, J, res);
       }
     } else {
       const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;   // the whole level unless row-sharded
-      for (int i = i_begin + blockIdx.x * kCoopBlock + tid; i < i_end; i += stride) {
+      for (int i = i_begin + bid * kCoopBlock + tid; i < i_end; i += stride) {
+        // everything indexed by i is loaded up front (coalesced, independent); only I0[winner] waits for a loaded value
         const int win = __ldcg(P.winner + i);
+        const bool ok = __ldcg(P.valid + i) != 0;
+        const double i1 = __ldg(P.I1 + i), d = __ldg(P.D0 + i), gx = __ldg(P.Gx + i), gy = __ldg(P.Gy + i);
         P.winner[i] = -1;
         double res = 0.;
         if (win >= 0) {
-          res = __ldg(P.I1 + i) - __ldg(P.I0 + win);
+          res = i1 - __ldg(P.I0 + win);
           acc[27] = fma(res, res, acc[27]);
         }
-        if (!__ldcg(P.valid + i)) continue;
+        if (!ok) continue;
         double J[6];
-        analytic_jacobian_row<MODE>(L, P, T, spsr, spcr, i, J);
+        analytic_jacobian_core<MODE>(L, T, spsr, spcr, i, d, gx, gy, J);
         accumulate_row(acc, J, res);
         acc[28] += 1.;
       }
       // row-sharded: slots outside the band that the warped rows may have bid for must be clean for the next iteration
       if (SHARD && (i_begin > 0 || i_end < n)) {
         const int c_begin = max(0, L.row_begin - 2 * halo) * L.cols, c_end = min(L.rows, L.row_end + 2 * halo) * L.cols;
-        for (int i = c_begin + blockIdx.x * kCoopBlock + tid; i < i_begin; i += stride) P.winner[i] = -1;
-        for (int i = i_end + blockIdx.x * kCoopBlock + tid; i < c_end; i += stride) P.winner[i] = -1;
+        for (int i = c_begin + bid * kCoopBlock + tid; i < i_begin; i += stride) P.winner[i] = -1;
+        for (int i = i_end + bid * kCoopBlock + tid; i < c_end; i += stride) P.winner[i] = -1;
       }
     }
     {
       const double total = block_reduce<kCoopBlock>(acc, smem);
-      if (tid < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + tid] = total;
+      if (tid < PHOVO_NACC) partials[(size_t)bid * PHOVO_ACC_STRIDE + tid] = total;
     }
-    grid.sync();
+    level_barrier<SLOT>();
     // ---- every CTA: fixed-order sum of all partials (group g of 8 takes blocks g, g+8, ...) ----
     {
       const int v = tid & 31, g = tid >> 5;
       double s = 0.;
-      for (int b = g; b < (int)gridDim.x; b += kCoopBlock / 32) s += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
+      for (int b = g; b < nblk; b += kCoopBlock / 32) s += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
       smem[g * PHOVO_ACC_STRIDE + v] = s;
       __syncthreads();
       if (tid < 32) {
@@ -592,7 +634,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       const unsigned long long epoch = S.epoch_base + (unsigned long long)it + 1ull;
       const int parity = (int)(epoch & 1ull);
       ShardExchange* mine = S.peers[S.rank];
-      if (blockIdx.x == 0) {
+      if (bid == 0) {
         const int w = tid >> 5, v = tid & 31;
         if (w < S.world) {
           ShardExchange* peer = S.peers[w];
@@ -625,7 +667,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
       for (int k = 0; k < 6; ++k) s_out[k] = s_in[k] - L.lambda * step[k];
       const double gnorm = sqrt(n2);
       const int done = (it + 1 >= L.max_iters) || (gnorm < L.min_grad_norm);
-      if (blockIdx.x == 0 && log && log_count < log_capacity) {
+      if (bid == 0 && log && log_count < log_capacity) {
         phovo_iter_stats* e = log + log_count;
         e->level = L.level; e->iteration = it; e->num_valid = (int)s_tot[28]; e->accepted = 1;
         for (int k = 0; k < 21; ++k) e->H[k] = s_tot[k];
@@ -642,13 +684,19 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, Lev
     __syncthreads();
     if (s_done) { ++it; break; }
   }
-  if (blockIdx.x == 0 && tid == 0) {
+  if (bid == 0 && tid == 0) {
     s_pose.iteration = it;
     s_pose.iters_per_level[L.level] = it;
     s_pose.done = 1;
     s_pose.log_count = log_count;
     *pose = s_pose;
   }
+}
+
+template <int MODE, bool SHARD>
+__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
+                                                               phovo_iter_stats* log, ShardArgs S) {
+  level_loop<MODE, SHARD, false>(L, P, pose, partials, log, S);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -791,12 +839,6 @@ __global__ void __launch_bounds__(kClusterBlock, 1) k_level_cluster(LevelParams 
 // broadcast.  CTA 0 writes the log.  The decision code mirrors the host loop in phovo_api.cu
 // (optimize_ceres), statement for statement.
 // ---------------------------------------------------------------------------------------------
-struct LmParams {
-  double function_tolerance, gradient_tolerance, parameter_tolerance;
-  double initial_radius, max_radius, min_radius, min_relative_decrease;
-  int max_iterations;
-};
-
 struct LmState {
   double x[6], xn[6], scale[6], step_norm, x_norm, model_cost_change;
   double H[21], g[6], cost;       // `cur`
@@ -864,10 +906,10 @@ __device__ bool lm_next_step(const LevelParams& L, const LmParams& lm, LmState& 
   return true;
 }
 
-__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
-                                                                     phovo_iter_stats* log, LmParams lm) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+template <bool SLOT>
+__device__ __forceinline__ void level_loop_ceres(const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
+                                                 phovo_iter_stats* log, const LmParams& lm) {
+  const int bid = SLOT ? 0 : (int)blockIdx.x, nblk = SLOT ? 1 : (int)gridDim.x;
   __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
   __shared__ double s_tot[32];
   __shared__ PoseDev s_pose;
@@ -882,7 +924,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
   int log_count = s_pose.log_count;
   const int log_capacity = s_pose.log_capacity;
   const int n = L.rows * L.cols;
-  const int stride = gridDim.x * kCoopBlock;
+  const int stride = nblk * kCoopBlock;
   for (;;) {
     // ---- pose of the state to evaluate (every CTA, thread 0) ----
     if (tid == 0) {
@@ -895,18 +937,18 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
     Pose T;
     pose_load(&s_pose, T);
     // ---- phase A: winner of each (truncated) target slot, CE:250-254, 261 ----
-    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+    for (int i = bid * kCoopBlock + tid; i < n; i += stride) {
       const double d = __ldg(P.D0 + i);
       const int r = i / L.cols, c = i - r * L.cols;
       Warped w;
       if (warp_pixel<true>(L, T, r, c, d, w)) atomicMax(P.winner + w.t, i);
     }
-    grid.sync();
+    level_barrier<SLOT>();
     // ---- phase B: CE:156-269 residual + Jacobian rows of the surviving pixels ----
     double acc[PHOVO_NACC];
 #pragma unroll
     for (int v = 0; v < PHOVO_NACC; ++v) acc[v] = 0.;
-    for (int i = blockIdx.x * kCoopBlock + tid; i < n; i += stride) {
+    for (int i = bid * kCoopBlock + tid; i < n; i += stride) {
       const int r = i / L.cols, c = i - r * L.cols;
       const double d = __ldg(P.D0 + i);
       Warped w;
@@ -930,13 +972,13 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
     }
     {
       const double total = block_reduce<kCoopBlock>(acc, smem);
-      if (tid < PHOVO_NACC) partials[(size_t)blockIdx.x * PHOVO_ACC_STRIDE + tid] = total;
+      if (tid < PHOVO_NACC) partials[(size_t)bid * PHOVO_ACC_STRIDE + tid] = total;
     }
-    grid.sync();   // partials complete, every winner slot back to -1
+    level_barrier<SLOT>();   // partials complete, every winner slot back to -1
     {
       const int v = tid & 31, g = tid >> 5;
       double sum = 0.;
-      for (int b = g; b < (int)gridDim.x; b += kCoopBlock / 32) sum += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
+      for (int b = g; b < nblk; b += kCoopBlock / 32) sum += __ldcg(partials + (size_t)b * PHOVO_ACC_STRIDE + v);
       smem[g * PHOVO_ACC_STRIDE + v] = sum;
       __syncthreads();
       if (tid < 32) {
@@ -996,7 +1038,7 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
     log_count = s_pose.log_count;
     if (S.done) break;
   }
-  if (blockIdx.x == 0 && tid == 0) {
+  if (bid == 0 && tid == 0) {
     Pose Pn;
     pose_from_state(S.x, Pn);
     for (int k = 0; k < 6; ++k) s_pose.state[k] = S.x[k];
@@ -1007,6 +1049,55 @@ __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams 
     s_pose.log_count = log_count;
     *pose = s_pose;
   }
+}
+
+__global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop_ceres(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
+                                                                     phovo_iter_stats* log, LmParams lm) {
+  level_loop_ceres<false>(L, P, pose, partials, log, lm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batch slot kernels (phovo_batch.cu, wave path): ONE CTA runs the whole coarse-to-fine alignment of ONE pair --
+// every active level, every iteration -- on the pair's own pyramids in global memory (a "slot" = the device
+// buffers of a child context).  Same loops as the cooperative kernels above with block barriers instead of grid
+// barriers, so a wave of several hundred pairs runs with no grid-wide synchronisation at all and pairs that stop
+// early make room for the next CTA.  Used for what the shared-memory-resident kernels (kernels_batch.cu) do not
+// take: Ceres mode, the photometric + depth solver, blurred or large levels.
+// ---------------------------------------------------------------------------------------------
+#ifndef PHOVO_SLOT_MINB
+#define PHOVO_SLOT_MINB 2
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kCoopBlock, PHOVO_SLOT_MINB) k_align_slots(const __grid_constant__ SlotLevels LS, const SlotArgs* __restrict__ slots,
+                                                                const double* __restrict__ init_states) {
+  const SlotArgs& A = slots[blockIdx.x];
+  if (threadIdx.x == 0) {   // k_set_state for this slot: the caller's initial state (zero if none), counters cleared, no log
+    double s[6];
+    for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)blockIdx.x * 6 + k] : 0.;
+    Pose P0;
+    pose_from_state(s, P0);
+    PoseDev* pose = A.pose;
+    for (int k = 0; k < 6; ++k) pose->state[k] = s[k];
+    pose_store(P0, pose);
+    pose->iteration = 0; pose->done = 0; pose->log_count = 0; pose->log_capacity = 0;
+    for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) pose->iters_per_level[l] = 0;
+  }
+  __syncthreads();
+  for (int a = 0; a < LS.count; ++a) {
+    const LevelParams& L = LS.L[a];
+    if (MODE == PHOVO_MODE_CERES) level_loop_ceres<true>(L, A.P[L.level], A.pose, A.partials, nullptr, LS.lm[a]);
+    else level_loop<MODE, false, true>(L, A.P[L.level], A.pose, A.partials, nullptr, ShardArgs{nullptr, 0, 1, 0ull, nullptr});
+    __syncthreads();   // the level's PoseDev is in global memory (written and re-read by thread 0); shared scratch is free again
+  }
+}
+
+// state + executed iterations per level of every slot -> two dense arrays (one D2H copy per wave)
+__global__ void k_gather_slots(const SlotArgs* __restrict__ slots, int n, double* __restrict__ states, int32_t* __restrict__ iters) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const PoseDev* p = slots[s].pose;
+  for (int k = 0; k < 6; ++k) states[(size_t)s * 6 + k] = p->state[k];
+  for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) iters[(size_t)s * PHOVO_MAX_LEVELS + l] = p->iters_per_level[l];
 }
 
 // smallest depth of a level inside (lo, hi), as the bits of a positive double (ordered like unsigned integers)
@@ -1203,6 +1294,22 @@ int launch_reduce_exchange(cudaStream_t stream, const PoseDev* pose, const doubl
 int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev* pose, const double* buffer,
                              phovo_iter_stats* log) {
   k_solve_from_buffer<<<1, 32, 0, stream>>>(L, pose, buffer, log);
+  return 1;
+}
+
+int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states) {
+  if (num_slots < 1 || LS.count < 1) return 0;
+  switch (mode) {
+    case PHOVO_MODE_ANALYTIC_REF:   k_align_slots<0><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
+    case PHOVO_MODE_ANALYTIC_FIXED: k_align_slots<1><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
+    case PHOVO_MODE_CERES:          k_align_slots<2><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
+    default:                        k_align_slots<3><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
+  }
+  return 1;
+}
+
+int launch_gather_slots(cudaStream_t stream, const SlotArgs* slots, int num_slots, double* states, int32_t* iters) {
+  k_gather_slots<<<(num_slots + 127) / 128, 128, 0, stream>>>(slots, num_slots, states, iters);
   return 1;
 }
 

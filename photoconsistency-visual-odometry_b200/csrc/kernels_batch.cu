@@ -292,13 +292,17 @@ __device__ __forceinline__ void warp_gn_step(double tot, int lane, const BatchLe
 // last (four-pixel) trip of phase A may lie up to 3 `threads` pixels past the level and are read
 // (and masked) without a guard.
 constexpr int kRowEntries = 5;
+#ifndef PHOVO_PHASE_A_WIDTH
+#define PHOVO_PHASE_A_WIDTH 4
+#endif
+constexpr int kPhaseAWidth = PHOVO_PHASE_A_WIDTH;   // pixels per trip of the fp32 phase A (column-fixed kernels)
 struct Tables {
   double* cx; double* ry; double* cxi; double* ryi;
   double2* colA; double2* colB;   // [cols]
   double2* row;                   // [rows + pad][kRowEntries]
   float4* rowf;                   // [rows + pad] per ITERATION, fp32 estimate of phase A: {ryi, y - ryi z, R21 ryi, -R21 ryi^2}
 };
-__host__ __device__ inline int table_pad_rows(int cols, int threads) { return (3 * threads + cols - 1) / cols; }
+__host__ __device__ inline int table_pad_rows(int cols, int threads) { return ((kPhaseAWidth > 4 ? kPhaseAWidth - 1 : 3) * threads + cols - 1) / cols; }
 __host__ __device__ inline int table_doubles(int rows, int cols, int threads) {
   return 2 * (rows + cols) + 4 * cols + (2 * kRowEntries + 2) * (rows + table_pad_rows(cols, threads));
 }
@@ -331,6 +335,18 @@ __device__ __noinline__ WarpA warp_exact(const PoseDev* pose, double cx, double 
   w.ti = __double2int_rz(__dadd_rz(tr, copysign(0.5, tr)));   // saturated casts fail the caller's range test
   return w;
 }
+
+// Experiment hook (tools/section_clocks.py): -DPHOVO_SECTION_CLOCKS accumulates, from thread 0 of every CTA,
+// the clocks between the section boundaries of an iteration.  Not compiled into the product library.
+#ifdef PHOVO_SECTION_CLOCKS
+__device__ unsigned long long g_section_clocks[2][8];
+#define SEC_INIT() long long sec_t = clock64()
+#define SEC_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); \
+  atomicAdd(&g_section_clocks[BT == kBatchThreads ? 1 : 0][k], (unsigned long long)(now_ - sec_t)); sec_t = now_; } } while (0)
+#else
+#define SEC_INIT() do {} while (0)
+#define SEC_MARK(k) do {} while (0)
+#endif
 
 struct IterConst {          // per-iteration scalars besides the tables
   double x, y, z, cy, sy, rho;
@@ -471,14 +487,16 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
   // issued a whole reduction + solve ahead (before the loop / at the end of phase B) instead of behind
   // the barrier that opens phase A, where every warp of the CTA would wait out the L2 latency at once.
   // (column-fixed kernels: phase A reads the fp32 copy of the depth, phase B the fp64 one)
-  double first_d[COLFIX ? 2 : 4]; float first_f[4]; unsigned first_u[4];
+  constexpr int FW = COLFIX ? kPhaseAWidth : 4;
+  double first_d[COLFIX ? 2 : 4]; float first_f[FW]; unsigned first_u[FW];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < FW; ++j) {
     if (COLFIX) first_f[j] = ldg_f32(L.gD32 + tid + j * BT);
     if (!COLFIX || j < 2) first_d[j] = ldg_f64(L.gD0 + tid + j * BT);
     first_u[j] = ldg_u16(L.gI0 + tid + j * BT);
   }
 
+  SEC_INIT();
   for (int it = 0; it < max_iters; ++it) {
     Pose T;
     pose_load(&sh->pose, T);
@@ -487,8 +505,9 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     // stops as soon as 0 < min_gradient_norm.  Here invalid rows are "finite table entry times zero",
     // so the tables are built from the identity pose instead (warp_exact still reads the real one and
     // rejects every pixel).
-    const bool finite_pose = isfinite(T.x + T.y + T.z + T.R00 + T.R01 + T.R02 + T.R10 + T.R11 + T.R12 + T.R20 + T.R21 + T.R22 +
-                                      T.sy + T.cy + T.sp + T.cp + T.sr + T.cr);
+    // (balanced sum: a chain of 17 dependent adds is 140 cycles of latency in front of every iteration)
+    const bool finite_pose = isfinite((((T.x + T.y) + (T.z + T.R00)) + ((T.R01 + T.R02) + (T.R10 + T.R11))) +
+                                      (((T.R12 + T.R20) + (T.R21 + T.R22)) + ((T.sy + T.cy) + (T.sp + T.cp))) + (T.sr + T.cr));
     if (!finite_pose) {
       T.x = T.y = T.z = 0.;
       T.R00 = T.R11 = T.R22 = 1.; T.R01 = T.R02 = T.R10 = T.R12 = T.R20 = T.R21 = 0.;
@@ -529,6 +548,7 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     mycolA.as = make_double2(__dmul_rn(K.fxs, mycol.a.x), __dmul_rn(K.fys, mycol.a.y));
     mycolA.bx = mycol.b.x;
     __syncthreads();
+    SEC_MARK(0);
     // ---- phase A: warp every source pixel and bid for its target slot (AN:279-303, 358) ----
     // FOUR pixels per trip (i, i + BT, i + 2 BT, i + 3 BT): this phase has registers to spare, and four
     // independent estimate chains hide more of their own latency than two.  D0 / I0 are read through
@@ -540,7 +560,8 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
     if (COLFIX) {
       // ---- fp32 estimate (see est32_margins).  Per-thread constants of the iteration, rounded once ----
       unsigned ex = sh->ex, ey = sh->ey;             // computed once, by the thread that published the pose
-      if (!(lv.est32 && ordinary && finite_pose) || lv.exact_always) ex = ey = kFrac32One;   // nothing trusted: every pixel takes warp_exact
+      // (a pose or depth range that is not an ordinary number makes est32_margins return "nothing trusted" by itself)
+      if (!(lv.est32 && finite_pose) || lv.exact_always) ex = ey = kFrac32One;   // nothing trusted: every pixel takes warp_exact
       const unsigned limx = ex < kFrac32One / 2 ? kFrac32One - 2u * ex : 0u, limy = ey < kFrac32One / 2 ? kFrac32One - 2u * ey : 0u;
       const float a0f = (float)(fma(T.R00, my_cxi, T.R02) - my_cxi * fma(T.R20, my_cxi, T.R22)), b0f = (float)fma(-T.R21, my_cxi, T.R01);
       const float a1f = (float)fma(T.R10, my_cxi, T.R12), b1f = (float)((T.R11 - T.R22) - T.R20 * my_cxi);
@@ -550,21 +571,23 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
       const int cprime = c0_first - kMagic32Whole;
       int rprime = r0_first - kMagic32Whole;       // row of the trip's first pixel, mantissa offset folded in
       const char* rq = (const char*)(tb.rowf + r0_first);
-      const int rq_step = 4 * dr1 * (int)sizeof(float4);
+      constexpr int W = kPhaseAWidth;              // pixels per trip: independent estimate chains in flight per thread
+      const int groups = (2 * trips + W - 1) / W;  // W-pixel trips of this thread
+      const int rq_step = W * dr1 * (int)sizeof(float4);
       const float* pf = L.gD32 + tid;
       const unsigned short* pu = L.gI0 + tid;
-      float p[4], f[4]; unsigned u[4], w[4];
+      float p[W], f[W]; unsigned u[W], w[W];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { p[j] = first_f[j]; u[j] = first_u[j]; f[j] = 0.f; w[j] = 0u; }
+      for (int j = 0; j < W; ++j) { p[j] = first_f[j]; u[j] = first_u[j]; f[j] = 0.f; w[j] = 0u; }
       unsigned vhi = 0u, vlo = 0u, uhi = 0u, ulo = 0u;   // validity / "needs the exact warp" bits, shifted in at the top
       unsigned bid = (unsigned)(tid + 1) << 16;
-      auto trip = [&](const float (&cd)[4], const unsigned (&cu)[4], float (&nd)[4], unsigned (&nu)[4], const int i) {
+      auto trip = [&](const float (&cd)[W], const unsigned (&cu)[W], float (&nd)[W], unsigned (&nu)[W], const int i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { nd[j] = ldg_f32(pf + (4 + j) * BT); nu[j] = ldg_u16(pu + (4 + j) * BT); }
-        pf += 4 * BT; pu += 4 * BT;
+        for (int j = 0; j < W; ++j) { nd[j] = ldg_f32(pf + (W + j) * BT); nu[j] = ldg_u16(pu + (W + j) * BT); }
+        pf += W * BT; pu += W * BT;
         unsigned vbits = 0u, ubits = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < W; ++j) {
           const float4 rf = *(const float4*)(rq + j * dr1 * (int)sizeof(float4));
           const float d = cd[j];
           const float D0 = fmaf(b0f, rf.x, a0f);
@@ -578,29 +601,29 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
           const int tj = (int)(ux >> kFrac32Bits) + cprime, ti = (int)(uy >> kFrac32Bits) + rprime + j * dr1;
           const bool ok = dep & sure & ((unsigned)tj < (unsigned)cols) & ((unsigned)ti < (unsigned)rows);
           smem_red_max(ok ? L.sWinAddr + 4u * (unsigned)(ti * cols + tj) : dummy, bid + ((unsigned)(j * BT) << 16) + cu[j]);
-          vbits |= (unsigned)ok << (28 + j);
-          ubits |= (unsigned)(dep & !sure) << (28 + j);
+          vbits |= (unsigned)ok << (32 - W + j);
+          ubits |= (unsigned)(dep & !sure) << (32 - W + j);
         }
-        bid += (unsigned)(4 * BT) << 16;
-        vlo = __funnelshift_r(vlo, vhi, 4); vhi = (vhi >> 4) | vbits;
-        ulo = __funnelshift_r(ulo, uhi, 4); uhi = (uhi >> 4) | ubits;
-        rq += rq_step; rprime += 4 * dr1;
+        bid += (unsigned)(W * BT) << 16;
+        vlo = __funnelshift_r(vlo, vhi, W); vhi = (vhi >> W) | vbits;
+        ulo = __funnelshift_r(ulo, uhi, W); uhi = (uhi >> W) | ubits;
+        rq += rq_step; rprime += W * dr1;
       };
       int i = tid;
-      if (quads & 1) {
+      if (groups & 1) {
         trip(p, u, f, w, i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { p[j] = f[j]; u[j] = w[j]; }
-        i += 4 * BT;
+        for (int j = 0; j < W; ++j) { p[j] = f[j]; u[j] = w[j]; }
+        i += W * BT;
       }
-      for (; i < n; i += 8 * BT) {
+      for (; i < n; i += 2 * W * BT) {
         trip(p, u, f, w, i);
-        trip(f, w, p, u, i + 4 * BT);
+        trip(f, w, p, u, i + W * BT);
       }
       valid = ((unsigned long long)vhi << 32) | vlo;
-      valid = quads > 0 ? valid >> (64 - 4 * quads) : 0ull;
+      valid = groups > 0 ? valid >> (64 - W * groups) : 0ull;
       unsigned long long unsure = ((unsigned long long)uhi << 32) | ulo;
-      unsure = quads > 0 ? unsure >> (64 - 4 * quads) : 0ull;
+      unsure = groups > 0 ? unsure >> (64 - W * groups) : 0ull;
       // ---- the pixels the estimate could not decide (a few per warp and iteration): the reference's own arithmetic ----
       while (unsure) {
         const int k = __ffsll((long long)unsure) - 1;
@@ -693,7 +716,9 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
       valid = ((unsigned long long)vhi << 32) | vlo;
       valid = quads > 0 ? valid >> (64 - 4 * quads) : 0ull;
     }
+    SEC_MARK(1);
     __syncthreads();
+    SEC_MARK(2);
     // ---- phase B: residual + Jacobian + normal equations (AN:308-366, 538-539) ----
     // The second pixel of the last trip may lie past the level: its slots are padding (winner word
     // 0, so residual 0) and its validity bit is 0 (so its Jacobian row is 0).
@@ -753,9 +778,10 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
         trip(f0, f1, p0, p1);
       }
     }
+    SEC_MARK(3);
     // first trip of the next iteration: in flight during the reduction and the solve
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < FW; ++j) {
       if (COLFIX) first_f[j] = ldg_f32(L.gD32 + tid + j * BT);
       if (!COLFIX || j < 2) first_d[j] = ldg_f64(L.gD0 + tid + j * BT);
       first_u[j] = ldg_u16(L.gI0 + tid + j * BT);
@@ -769,15 +795,18 @@ __device__ __forceinline__ void gn_level(const BatchLevelParams& lv, const Level
       L.sRed[wid * 32 + lane] = warp_transpose_sum(x, lane);
     }
     __syncthreads();
+    SEC_MARK(4);
     if (wid == 0) {
       double t0 = 0., t1 = 0.;   // two interleaved chains, fixed order
 #pragma unroll
       for (int w = 0; w < NW; w += 2) { t0 += L.sRed[w * 32 + lane]; if (w + 1 < NW) t1 += L.sRed[(w + 1) * 32 + lane]; }
       warp_gn_step((t0 + t1) * scale, lane, lv, it, L.pair, sh, log);
     }
+    SEC_MARK(5);
     __syncthreads();
     if (sh->done) break;
   }
+  SEC_MARK(6);
 }
 
 // K3-batch, one launch per ACTIVE pyramid level (coarse to fine; the state of every pair travels
@@ -822,6 +851,9 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
   // between pairs) start on the next level instead of idling.  Every CTA of this grid is resident before any
   // CTA of the next one can be scheduled, so the waits below cannot starve this grid.
   asm volatile("griddepcontrol.launch_dependents;");
+#ifdef PHOVO_SECTION_CLOCKS
+  const long long kernel_t0 = clock64();
+#endif
   for (;;) {
     __syncthreads();   // the previous pair's outputs have been read from shared memory
     if (tid == 0) {
@@ -912,9 +944,20 @@ __global__ void __launch_bounds__(BT, MINB) k_batch_level(const __grid_constant_
       asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(iters + (size_t)pair * PHOVO_MAX_LEVELS + lv.level), "r"(done_iterations) : "memory");
     }
   }
+#ifdef PHOVO_SECTION_CLOCKS
+  if (tid == 0) atomicAdd(&g_section_clocks[BT == kBatchThreads ? 1 : 0][7], (unsigned long long)(clock64() - kernel_t0));
+#endif
 }
 
 }  // namespace
+
+#ifdef PHOVO_SECTION_CLOCKS
+extern "C" int phovo_debug_section_clocks(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, g_section_clocks, sizeof(g_section_clocks)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {}; if (cudaMemcpyToSymbol(g_section_clocks, z, sizeof(z)) != cudaSuccess) return -1; }
+  return 0;
+}
+#endif
 
 // dynamic shared memory of one CTA working on a level of rows x cols pixels with `threads` threads
 static size_t level_smem_bytes(int rows, int cols, int threads) {

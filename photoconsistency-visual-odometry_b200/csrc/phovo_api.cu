@@ -89,6 +89,58 @@ static cudaError_t ensure(T** p, size_t* cap, size_t want) {
   return e;
 }
 
+// slots allocate from their arena (bump pointer; arena_reset starts over), everything else with cudaMalloc
+template <class T>
+static cudaError_t ctx_ensure(phovo_ctx* ctx, T** p, size_t* cap, size_t want) {
+  if (!ctx->arena_base) return ensure(p, cap, want);
+  if (*cap >= want && *p) return cudaSuccess;
+  const size_t off = (ctx->arena_used + 255) & ~(size_t)255, bytes = want * sizeof(T);
+  if (off + bytes > ctx->arena_bytes) return cudaErrorMemoryAllocation;
+  *p = (T*)(ctx->arena_base + off);
+  *cap = want;
+  ctx->arena_used = off + bytes;
+  return cudaSuccess;
+}
+
+void phovo_ctx::arena_reset(char* base, size_t bytes) {
+  for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
+    I0[l] = D0[l] = I1[l] = Gx[l] = Gy[l] = nullptr;
+    D1[l] = GxD[l] = GyD[l] = nullptr;
+    for (int a = 0; a < 5; ++a) lcap[l][a] = 0;
+    for (int a = 0; a < 3; ++a) bcap[l][a] = 0;
+  }
+  winner = nullptr; winner_cap = 0; valid = nullptr; valid_cap = 0;
+  scratch64[0] = scratch64[1] = nullptr; scratch_cap[0] = scratch_cap[1] = 0;
+  partials = nullptr; partials_cap = 0;
+  d_gain = nullptr; d_pose = nullptr;
+  have_src = have_tgt = have_tgt_depth = false;
+  rows = cols = 0;
+  arena_base = base; arena_bytes = bytes; arena_used = 0;
+  if (base) {
+    d_pose = (PoseDev*)base;
+    d_gain = (double*)(base + 256);
+    arena_used = 512;
+    static_assert(sizeof(PoseDev) <= 256 && sizeof(double) * PHOVO_MAX_LEVELS <= 256, "slot header layout");
+  }
+}
+
+size_t phovo_internal_slot_bytes(const phovo_ctx* ctx, int rows, int cols) {
+  size_t total = 512, max_px = 1;
+  auto add = [&](size_t bytes) { total = ((total + 255) & ~(size_t)255) + bytes; };
+  for (int l = 0; l < ctx->cfg.num_levels; ++l) {
+    if (!ctx->level_active(l)) continue;
+    int r, c;
+    level_size(rows, cols, l, &r, &c);
+    const size_t n = (size_t)(r > 0 ? r : 1) * (c > 0 ? c : 1);
+    if (n > max_px) max_px = n;
+    for (int a = 0; a < 8; ++a) add(n * sizeof(double));      // I0 D0 I1 Gx Gy (+ D1 GxD GyD)
+  }
+  add(2 * max_px * sizeof(int)); add(max_px);                 // winner (2N slots), valid
+  add(max_px * sizeof(double)); add(max_px * sizeof(double)); // scratch
+  add((size_t)partials_blocks(ctx->sm_count) * PHOVO_ACC_STRIDE * sizeof(double));
+  return (total + 4095) & ~(size_t)4095;
+}
+
 static bool is_device_pointer(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -117,7 +169,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
     for (int a = 0; a < 5; ++a) {
       size_t cap = ctx->lcap[l][a];
       double* before = *arrs[a];
-      CK(ensure(arrs[a], &cap, n));
+      CK(ctx_ensure(ctx, arrs[a], &cap, n));
       ctx->lcap[l][a] = cap;
       if (before != *arrs[a]) changed = true;
     }
@@ -125,7 +177,7 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
   if (max_px == 0) max_px = 1;
   {
     int* before = ctx->winner;
-    CK(ensure(&ctx->winner, &ctx->winner_cap, 2 * max_px));   // the photometric + depth solver stacks 2N rows
+    CK(ctx_ensure(ctx, &ctx->winner, &ctx->winner_cap, 2 * max_px));   // the photometric + depth solver stacks 2N rows
     if (before != ctx->winner) {
       changed = true;
       launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap, ctx->sm_count);
@@ -134,13 +186,13 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
   }
   {
     unsigned char* before = ctx->valid;
-    CK(ensure(&ctx->valid, &ctx->valid_cap, max_px));
+    CK(ctx_ensure(ctx, &ctx->valid, &ctx->valid_cap, max_px));
     if (before != ctx->valid) changed = true;
   }
-  for (int s = 0; s < 2; ++s) CK(ensure(&ctx->scratch64[s], &ctx->scratch_cap[s], max_px));
+  for (int s = 0; s < 2; ++s) CK(ctx_ensure(ctx, &ctx->scratch64[s], &ctx->scratch_cap[s], max_px));
   {
     double* before = ctx->partials;
-    CK(ensure(&ctx->partials, &ctx->partials_cap, (size_t)partials_blocks(ctx->sm_count) * PHOVO_ACC_STRIDE));
+    CK(ctx_ensure(ctx, &ctx->partials, &ctx->partials_cap, (size_t)partials_blocks(ctx->sm_count) * PHOVO_ACC_STRIDE));
     if (before != ctx->partials) changed = true;
   }
   if (changed) ctx->invalidate_graph();
@@ -181,7 +233,7 @@ static int wait_uploads(phovo_ctx* ctx) {
   if (ctx->device_input_in_flight) {   // kernels are still reading the caller's device buffer: drain them
     ctx->device_input_in_flight = false;
     ctx->copy_event_armed = false;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->defer_device_input_drain) CK(cudaStreamSynchronize(ctx->stream));
     return PHOVO_OK;
   }
   if (ctx->copy_event_armed) { CK(cudaEventSynchronize(ctx->ev_copy)); ctx->copy_event_armed = false; }
@@ -275,7 +327,7 @@ extern "C" const char* phovo_last_error(const phovo_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }
 
-extern "C" int phovo_create(int device, phovo_ctx** out) {
+static int create_context(int device, phovo_ctx** out, bool slot) {
   if (!out) return PHOVO_E_INVALID;
   *out = nullptr;
   int ndev = 0;
@@ -303,11 +355,15 @@ extern "C" int phovo_create(int device, phovo_ctx** out) {
     delete ctx;
     return PHOVO_E_CUDA;
   };
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  ctx->own_stream = true;
+  ctx->is_slot = slot;
+  if (!slot) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    ctx->own_stream = true;
+  }
   if ((e = cudaEventCreate(&ctx->ev_copy)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (int i = 0; i < 4; ++i)
     if ((e = cudaEventCreate(&ctx->ev_time[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+  if (slot) { *out = ctx; return PHOVO_OK; }   // device buffers come from the arena, results are gathered by the batch state
   ctx->log_cap = 1024;
   if ((e = cudaMalloc((void**)&ctx->d_pose, sizeof(PoseDev))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->d_pose, 0, sizeof(PoseDev))) != cudaSuccess) return bail("cudaMemset", e);
@@ -324,10 +380,14 @@ extern "C" int phovo_create(int device, phovo_ctx** out) {
   return PHOVO_OK;
 }
 
+extern "C" int phovo_create(int device, phovo_ctx** out) { return create_context(device, out, false); }
+int phovo_internal_create_slot(int device, phovo_ctx** out) { return create_context(device, out, true); }
+
 extern "C" int phovo_destroy(phovo_ctx* ctx) {
   if (!ctx) return PHOVO_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream || !ctx->is_slot) cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena_base) ctx->arena_reset(nullptr, 0);   // arena-backed buffers belong to the batch state
   ctx->invalidate_graph();
   phovo_batch_release(ctx);
   for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) {
@@ -517,7 +577,7 @@ extern "C" int phovo_set_target_depth(phovo_ctx* ctx, const void* depth, int dep
   if (src_type_of_depth(depth_type) < 0) return ctx->fail(PHOVO_E_INVALID, "unknown depth_type");
   if (depth_step < (size_t)ctx->cols * depth_elt(depth_type)) return ctx->fail(PHOVO_E_INVALID, "row stride smaller than a row");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->d_gain) CK(cudaMalloc((void**)&ctx->d_gain, sizeof(double) * PHOVO_MAX_LEVELS));
+  if (!ctx->d_gain) CK(cudaMalloc((void**)&ctx->d_gain, sizeof(double) * PHOVO_MAX_LEVELS));   // (a slot's lives in its arena)
   const void* dd; size_t dds; int rc;
   if ((rc = stage_image(ctx, depth, depth_step, depth_elt(depth_type), ctx->rows, ctx->cols, &ctx->stage_depth, &ctx->stage_depth_cap, &dd, &dds))) return rc;
   if ((rc = finish_uploads(ctx))) return rc;
@@ -528,7 +588,7 @@ extern "C" int phovo_set_target_depth(phovo_ctx* ctx, const void* depth, int dep
     double** arrs[3] = {&ctx->D1[l], &ctx->GxD[l], &ctx->GyD[l]};
     for (int a = 0; a < 3; ++a) {
       double* before = *arrs[a];
-      CK(ensure(arrs[a], &ctx->bcap[l][a], n));
+      CK(ctx_ensure(ctx, arrs[a], &ctx->bcap[l][a], n));
       if (before != *arrs[a]) ctx->invalidate_graph();
     }
     // BiObjective.h:574 (depth pyramid, no blur), :224-237 (Scharr of depth / m_MaxDepth), :299 (gain)

@@ -12,6 +12,9 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -19,6 +22,8 @@
 #include "phovo_ctx.h"
 
 using namespace phovo;
+
+constexpr int kWaveSetupThreads = 4;   // host threads (and streams) that build the pyramids of a wave's slots
 
 struct phovo_batch_state {
   // packed level records
@@ -49,7 +54,17 @@ struct phovo_batch_state {
   // batches the shared-memory-resident kernels cannot take (Ceres / photometric + depth solver, blurred levels, levels
   // beyond the shared-memory budget) run pair by pair on a small pool of per-pair contexts, one host thread each
   std::vector<phovo_ctx*> pool;
-  int last_path = 0;                                   // 1: shared-memory-resident batch kernels, 2: pool of per-pair contexts
+  int last_path = 0;                                   // 1: shared-memory-resident batch kernels, 2: pool of per-pair contexts, 3: slot waves
+  // slot waves (batch_waves): two halves of per-pair slots; one half aligns while the other is being set up
+  std::vector<phovo_ctx*> slots;
+  cudaStream_t setup_stream[kWaveSetupThreads] = {}; cudaEvent_t ev_setup[kWaveSetupThreads] = {};
+  cudaStream_t align_stream[2] = {nullptr, nullptr}; cudaEvent_t ev_wave_done[2] = {nullptr, nullptr}; cudaEvent_t ev_wave_in[2] = {nullptr, nullptr};
+  char* arena = nullptr; size_t arena_cap = 0, slot_bytes = 0; int arena_rows = 0, arena_cols = 0; phovo_config arena_cfg = {};
+  SlotArgs* d_slot_args = nullptr; size_t slot_args_cap = 0; std::vector<SlotArgs> h_slot_args;
+  double* d_wave_init[2] = {nullptr, nullptr}; double* d_wave_states[2] = {nullptr, nullptr}; int32_t* d_wave_iters[2] = {nullptr, nullptr};
+  double* h_wave_states[2] = {nullptr, nullptr}; int32_t* h_wave_iters[2] = {nullptr, nullptr}; size_t wave_cap = 0;
+  uint8_t* wave_g0[2] = {nullptr, nullptr}; uint8_t* wave_g1[2] = {nullptr, nullptr}; char* wave_d0[2] = {nullptr, nullptr}; char* wave_d1[2] = {nullptr, nullptr};
+  size_t wave_g_cap[2] = {0, 0}, wave_g1_cap[2] = {0, 0}, wave_d0_cap[2] = {0, 0}, wave_d1_cap[2] = {0, 0};
 };
 
 #define CK(call)                                                      \
@@ -81,6 +96,21 @@ void phovo_batch_release(phovo_ctx* ctx) {
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   cudaFreeHost(b->h_states_pinned); cudaFreeHost(b->h_iters_pinned);
   for (phovo_ctx* c : b->pool) phovo_destroy(c);
+  for (phovo_ctx* c : b->slots) phovo_destroy(c);      // (their streams are the setup streams below: not owned)
+  for (int t = 0; t < kWaveSetupThreads; ++t) {
+    if (b->setup_stream[t]) cudaStreamDestroy(b->setup_stream[t]);
+    if (b->ev_setup[t]) cudaEventDestroy(b->ev_setup[t]);
+  }
+  for (int h = 0; h < 2; ++h) {
+    if (b->align_stream[h]) cudaStreamDestroy(b->align_stream[h]);
+    if (b->ev_wave_done[h]) cudaEventDestroy(b->ev_wave_done[h]);
+    if (b->ev_wave_in[h]) cudaEventDestroy(b->ev_wave_in[h]);
+    cudaFree(b->d_wave_init[h]); cudaFree(b->d_wave_states[h]); cudaFree(b->d_wave_iters[h]);
+    cudaFreeHost(b->h_wave_states[h]); cudaFreeHost(b->h_wave_iters[h]);
+    cudaFree(b->wave_g0[h]); cudaFree(b->wave_g1[h]); cudaFree(b->wave_d0[h]); cudaFree(b->wave_d1[h]);
+  }
+  cudaFree(b->d_slot_args);
+  cudaFree(b->arena);
   delete b;
   ctx->batch = nullptr;
 }
@@ -278,6 +308,13 @@ static int prepare_log(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int*
 // as calling the per-pair API in a loop, by construction.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPoolContexts = 4;
+constexpr int kPoolContextsMax = 32;
+// PHOVO_POOL_CONTEXTS overrides the number of child contexts (1..32): a tuning knob, results do not depend on it
+static int pool_contexts() {
+  const char* e = getenv("PHOVO_POOL_CONTEXTS");
+  const int v = e ? atoi(e) : 0;
+  return v >= 1 && v <= kPoolContextsMax ? v : kPoolContexts;
+}
 
 static bool host_readable(const void* p) {
   cudaPointerAttributes a;
@@ -294,7 +331,7 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
     return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth: use phovo_batch_align_with_target_depth");
   // the pool's contexts run on their own streams: device-resident inputs produced on this context's stream must be complete
   CK(cudaStreamSynchronize(ctx->stream));
-  const int workers = std::min(kPoolContexts, num_pairs);
+  const int workers = std::min(pool_contexts(), num_pairs);
   while ((int)b->pool.size() < workers) {
     phovo_ctx* c = nullptr;
     if (phovo_create(ctx->device, &c) != PHOVO_OK) return ctx->fail(PHOVO_E_CUDA, std::string("batch pool: ") + phovo_last_error(nullptr));
@@ -317,6 +354,7 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
     int rc = phovo_set_config(c, &ctx->cfg);
     if (!rc) rc = phovo_set_intrinsics(c, ctx->K);
     if (!rc) rc = phovo_set_execution(c, ctx->execution);
+    { const char* e = getenv("PHOVO_POOL_SM_SHARE"); const int d = e ? atoi(e) : 1; if (d > 1) c->sm_count = std::max(4, ctx->sm_count / d); }
     if (rc) { fail(rc); return; }
     const double zeros[6] = {0, 0, 0, 0, 0, 0};
     for (;;) {
@@ -351,7 +389,240 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
   return PHOVO_OK;
 }
 
-// true if the batch must take the pool path (see make_params for what the shared-memory-resident kernels accept)
+// ---------------------------------------------------------------------------------------------
+// The wave path: what the shared-memory-resident kernels cannot take (Ceres mode, the photometric + depth solver,
+// blurred or large levels) runs in WAVES of slots.  A slot is a child context used for its device side only: its
+// pyramids are built with the general path's kernels (phovo_set_source / phovo_set_target / phovo_set_target_depth,
+// asynchronously, kWaveSetupThreads host threads each on a stream of its own), then ONE launch of k_align_slots runs
+// the complete coarse-to-fine alignment of every pair of the wave, one CTA per pair (kernels_align.cu).  The slots
+// come in two halves: while one half aligns, the other is being set up.  Results equal the per-pair API's up to the
+// grouping of the partial sums (one CTA instead of a grid), i.e. to the last bits of the normal equations.
+// ---------------------------------------------------------------------------------------------
+#ifndef PHOVO_SLOT_MINB
+#define PHOVO_SLOT_MINB 2
+#endif
+static int wave_slots_per_half(const phovo_batch_state* b) { return PHOVO_SLOT_MINB * std::max(1, b->sm_count); }   // CTAs of k_align_slots resident per SM
+
+static int wave_resources(phovo_ctx* ctx, phovo_batch_state* b, int want_slots, int rows, int cols) {
+  for (int t = 0; t < kWaveSetupThreads; ++t)
+    if (!b->setup_stream[t]) {
+      CK(cudaStreamCreateWithFlags(&b->setup_stream[t], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&b->ev_setup[t], cudaEventDisableTiming));
+    }
+  for (int h = 0; h < 2; ++h)
+    if (!b->align_stream[h]) {
+      CK(cudaStreamCreateWithFlags(&b->align_stream[h], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&b->ev_wave_done[h], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&b->ev_wave_in[h], cudaEventDisableTiming));
+    }
+  const bool grew = (int)b->slots.size() < want_slots;
+  while ((int)b->slots.size() < want_slots) {
+    phovo_ctx* c = nullptr;
+    if (phovo_internal_create_slot(ctx->device, &c) != PHOVO_OK) return ctx->fail(PHOVO_E_CUDA, std::string("batch slots: ") + phovo_last_error(nullptr));
+    const int s = (int)b->slots.size();
+    c->stream = b->setup_stream[(s % wave_slots_per_half(b)) % kWaveSetupThreads];   // not owned: the setup thread's stream
+    c->defer_device_input_drain = true;   // the wave's inputs outlive its kernels (batch_waves waits for the wave before they go)
+    b->slots.push_back(c);
+  }
+  // ---- the arena: ONE allocation, slot s at s * slot_bytes; laid out again whenever the configuration or the frame size changes ----
+  phovo_ctx* c0 = b->slots[0];
+  int rc = PHOVO_OK;
+  if (memcmp(&c0->cfg, &ctx->cfg, sizeof(phovo_config)) != 0 && (rc = phovo_set_config(c0, &ctx->cfg))) return ctx->fail(rc, phovo_last_error(c0));
+  const size_t need = phovo_internal_slot_bytes(c0, rows, cols);
+  const bool same = !grew && need == b->slot_bytes && rows == b->arena_rows && cols == b->arena_cols && memcmp(&b->arena_cfg, &ctx->cfg, sizeof(phovo_config)) == 0;
+  if (!same) {
+    CK(cudaDeviceSynchronize());                       // nothing of an earlier call is still running on the old layout
+    const size_t total = need * b->slots.size();
+    if (total > b->arena_cap) {
+      cudaFree(b->arena); b->arena = nullptr; b->arena_cap = 0;
+      CK(cudaMalloc((void**)&b->arena, total));
+      b->arena_cap = total;
+    }
+    for (size_t s = 0; s < b->slots.size(); ++s) b->slots[s]->arena_reset(b->arena + s * need, need);
+    b->slot_bytes = need; b->arena_rows = rows; b->arena_cols = cols; b->arena_cfg = ctx->cfg;
+    for (auto& a : b->h_slot_args) memset(&a, 0, sizeof(a));
+  }
+  const size_t half = (size_t)wave_slots_per_half(b);
+  if (b->wave_cap < half) {
+    for (int h = 0; h < 2; ++h) {
+      cudaFree(b->d_wave_init[h]); cudaFree(b->d_wave_states[h]); cudaFree(b->d_wave_iters[h]);
+      cudaFreeHost(b->h_wave_states[h]); cudaFreeHost(b->h_wave_iters[h]);
+      CK(cudaMalloc((void**)&b->d_wave_init[h], sizeof(double) * 6 * half));
+      CK(cudaMalloc((void**)&b->d_wave_states[h], sizeof(double) * 6 * half));
+      CK(cudaMalloc((void**)&b->d_wave_iters[h], sizeof(int32_t) * PHOVO_MAX_LEVELS * half));
+      CK(cudaMallocHost((void**)&b->h_wave_states[h], sizeof(double) * 6 * half));
+      CK(cudaMallocHost((void**)&b->h_wave_iters[h], sizeof(int32_t) * PHOVO_MAX_LEVELS * half));
+    }
+    b->wave_cap = half;
+  }
+  CK(ensure(&b->d_slot_args, &b->slot_args_cap, 2 * half));
+  if (b->h_slot_args.size() < 2 * half) b->h_slot_args.resize(2 * half);
+  return PHOVO_OK;
+}
+
+static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                       const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
+                       const double* initial_states, double* states, int32_t* iterations) {
+  if (!ctx->have_K) return ctx->fail(PHOVO_E_INVALID, "SetIntrinsicMatrix has not been called");
+  if (num_pairs < 1 || rows < 1 || cols < 1) return ctx->fail(PHOVO_E_INVALID, "empty batch");
+  const bool bi = ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE;
+  if (bi && !depth1)
+    return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth: use phovo_batch_align_with_target_depth");
+  // device-resident inputs produced on this context's stream must be complete: the slots run on streams of their own
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int half = wave_slots_per_half(b);
+  const int waves = (num_pairs + half - 1) / half;
+  int rc = wave_resources(ctx, b, waves > 1 ? 2 * half : std::min(half, num_pairs), rows, cols);
+  if (rc) return rc;
+  const size_t frame = (size_t)rows * cols, delt = depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2;
+  b->last_h2d_bytes = 0;
+  const bool host_in = host_readable(gray0) || host_readable(depth0) || host_readable(gray1) || (bi && host_readable(depth1));
+
+  // the active levels, coarse to fine (AN:502-503; CE:437 skips levels without iterations)
+  SlotLevels LS;
+  memset(&LS, 0, sizeof(LS));
+  bool levels_known = false;
+
+  struct Pending { int start = 0, n = 0; bool active = false; } pend[2];
+  const bool trace = getenv("PHOVO_WAVE_TRACE") != nullptr;   // stderr: host set-up time and device align time per wave
+  cudaEvent_t tr0[2] = {nullptr, nullptr}, tr1[2] = {nullptr, nullptr};
+  if (trace) for (int h = 0; h < 2; ++h) { cudaEventCreate(&tr0[h]); cudaEventCreate(&tr1[h]); }
+  auto harvest = [&](int h) -> int {
+    if (!pend[h].active) return PHOVO_OK;
+    CK(cudaEventSynchronize(b->ev_wave_done[h]));
+    if (trace) { float ms = 0.f; cudaEventElapsedTime(&ms, tr0[h], tr1[h]); fprintf(stderr, "[wave] start %d n %d align %.3f ms\n", pend[h].start, pend[h].n, ms); }
+    if (states) memcpy(states + (size_t)pend[h].start * 6, b->h_wave_states[h], sizeof(double) * 6 * (size_t)pend[h].n);
+    if (iterations) memcpy(iterations + (size_t)pend[h].start * PHOVO_MAX_LEVELS, b->h_wave_iters[h], sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)pend[h].n);
+    pend[h].active = false;
+    return PHOVO_OK;
+  };
+
+  for (int k = 0; k < waves; ++k) {
+    const int h = k & 1, start = k * half, n = std::min(half, num_pairs - start);
+    if ((rc = harvest(h))) return rc;          // wave k - 2 used these slots (and these input buffers)
+    // ---- inputs of the wave on the device ----
+    const uint8_t* g0 = gray0 + (size_t)start * frame; const uint8_t* g1 = gray1 + (size_t)start * frame;
+    const char* d0 = (const char*)depth0 + (size_t)start * frame * delt;
+    const char* d1 = bi ? (const char*)depth1 + (size_t)start * frame * delt : nullptr;
+    if (host_in) {
+      const size_t nb = (size_t)n * frame;
+      CK(ensure(&b->wave_g0[h], &b->wave_g_cap[h], nb)); CK(ensure(&b->wave_g1[h], &b->wave_g1_cap[h], nb));
+      CK(ensure(&b->wave_d0[h], &b->wave_d0_cap[h], nb * delt));
+      if (bi) CK(ensure(&b->wave_d1[h], &b->wave_d1_cap[h], nb * delt));
+      cudaStream_t cs = b->align_stream[h];
+      CK(cudaMemcpyAsync(b->wave_g0[h], g0, nb, cudaMemcpyDefault, cs));
+      CK(cudaMemcpyAsync(b->wave_g1[h], g1, nb, cudaMemcpyDefault, cs));
+      CK(cudaMemcpyAsync(b->wave_d0[h], d0, nb * delt, cudaMemcpyDefault, cs));
+      if (bi) CK(cudaMemcpyAsync(b->wave_d1[h], d1, nb * delt, cudaMemcpyDefault, cs));
+      CK(cudaEventRecord(b->ev_wave_in[h], cs));
+      for (int t = 0; t < kWaveSetupThreads; ++t) CK(cudaStreamWaitEvent(b->setup_stream[t], b->ev_wave_in[h], 0));
+      g0 = b->wave_g0[h]; g1 = b->wave_g1[h]; d0 = b->wave_d0[h]; d1 = bi ? b->wave_d1[h] : nullptr;
+      b->last_h2d_bytes += nb * (2 + delt * (bi ? 2 : 1));
+    }
+    // ---- pyramids of the wave's slots: kWaveSetupThreads host threads, each on its own stream ----
+    const auto t_setup = std::chrono::steady_clock::now();
+    std::atomic<int> first_rc(PHOVO_OK);
+    std::mutex mu; std::string message;
+    auto work = [&](int t) {
+      for (int s = t; s < n; s += kWaveSetupThreads) {
+        if (first_rc.load() != PHOVO_OK) return;
+        phovo_ctx* c = b->slots[(size_t)h * half + s];
+        int r = PHOVO_OK;
+        if (memcmp(&c->cfg, &ctx->cfg, sizeof(phovo_config)) != 0) r = phovo_set_config(c, &ctx->cfg);
+        if (!r) r = phovo_set_intrinsics(c, ctx->K);
+        if (!r) r = phovo_set_source(c, g0 + (size_t)s * frame, cols, d0 + (size_t)s * frame * delt, depth_type, cols * delt, depth_scale, rows, cols);
+        if (!r) r = phovo_set_target(c, g1 + (size_t)s * frame, cols, rows, cols);
+        if (!r && bi) r = phovo_set_target_depth(c, d1 + (size_t)s * frame * delt, depth_type, cols * delt, depth_scale);
+        if (r) {
+          std::lock_guard<std::mutex> g(mu);
+          if (first_rc.load() == PHOVO_OK) { first_rc.store(r); message = phovo_last_error(c); }
+          return;
+        }
+      }
+    };
+    {
+      std::vector<std::thread> threads;
+      const int nt = std::min(kWaveSetupThreads, n);
+      for (int t = 1; t < nt; ++t) threads.emplace_back(work, t);
+      work(0);
+      for (auto& t : threads) t.join();
+    }
+    if (first_rc.load() != PHOVO_OK) {
+      cudaDeviceSynchronize();
+      return ctx->fail(first_rc.load(), "batch slots: " + message);
+    }
+    if (trace) fprintf(stderr, "[wave] start %d n %d host set-up %.3f ms\n", start, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup).count());
+    cudaStream_t as = b->align_stream[h];
+    for (int t = 0; t < kWaveSetupThreads; ++t) {
+      CK(cudaEventRecord(b->ev_setup[t], b->setup_stream[t]));
+      CK(cudaStreamWaitEvent(as, b->ev_setup[t], 0));
+    }
+    // ---- slot table (the buffers of a slot stay where they are once allocated for a frame size) ----
+    bool table_changed = false;
+    for (int s = 0; s < n; ++s) {
+      phovo_ctx* c = b->slots[(size_t)h * half + s];
+      SlotArgs A;
+      memset(&A, 0, sizeof(A));
+      for (int l = 0; l < c->cfg.num_levels; ++l) A.P[l] = c->level_ptrs(l);
+      A.pose = c->d_pose; A.partials = c->partials;
+      SlotArgs& cached = b->h_slot_args[(size_t)h * half + s];
+      if (memcmp(&cached, &A, sizeof(A)) != 0) { cached = A; table_changed = true; }
+      ctx->launches += c->launches; c->launches = 0;
+    }
+    if (table_changed) {
+      CK(cudaMemcpyAsync(b->d_slot_args + (size_t)h * half, b->h_slot_args.data() + (size_t)h * half, sizeof(SlotArgs) * (size_t)n, cudaMemcpyHostToDevice, as));
+      CK(cudaStreamSynchronize(as));   // pageable source: keep it simple, this happens once per frame size
+    }
+    if (!levels_known) {
+      const phovo_ctx* c0 = b->slots[(size_t)h * half];
+      for (int level = ctx->cfg.num_levels - 1; level >= 0; --level) {
+        const int M = ctx->cfg.max_num_iterations[level];
+        if (!(M > 0)) continue;
+        const int a = LS.count++;
+        LS.L[a] = c0->level_params(level);
+        LmParams& lm = LS.lm[a];
+        lm.function_tolerance = ctx->cfg.function_tolerance[level]; lm.gradient_tolerance = ctx->cfg.gradient_tolerance[level];
+        lm.parameter_tolerance = ctx->cfg.parameter_tolerance[level]; lm.initial_radius = ctx->cfg.initial_trust_region_radius[level];
+        lm.max_radius = ctx->cfg.max_trust_region_radius[level]; lm.min_radius = ctx->cfg.min_trust_region_radius[level];
+        lm.min_relative_decrease = ctx->cfg.min_relative_decrease[level]; lm.max_iterations = M;
+      }
+      levels_known = true;
+    }
+    // ---- one launch aligns the wave; results to pinned memory ----
+    const double* d_init = nullptr;
+    if (initial_states) {
+      CK(cudaMemcpyAsync(b->d_wave_init[h], initial_states + (size_t)start * 6, sizeof(double) * 6 * (size_t)n, cudaMemcpyDefault, as));
+      d_init = b->d_wave_init[h];
+    }
+    if (trace) cudaEventRecord(tr0[h], as);
+    ctx->launches += launch_align_slots(as, ctx->cfg.mode, LS, b->d_slot_args + (size_t)h * half, n, d_init);
+    if (trace) cudaEventRecord(tr1[h], as);
+    ctx->launches += launch_gather_slots(as, b->d_slot_args + (size_t)h * half, n, b->d_wave_states[h], b->d_wave_iters[h]);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(b->h_wave_states[h], b->d_wave_states[h], sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, as));
+    CK(cudaMemcpyAsync(b->h_wave_iters[h], b->d_wave_iters[h], sizeof(int32_t) * PHOVO_MAX_LEVELS * (size_t)n, cudaMemcpyDeviceToHost, as));
+    CK(cudaEventRecord(b->ev_wave_done[h], as));
+    pend[h].start = start; pend[h].n = n; pend[h].active = true;
+  }
+  // in wave order: the older half first
+  const int last = (waves - 1) & 1;
+  if ((rc = harvest(1 - last))) return rc;
+  if ((rc = harvest(last))) return rc;
+  if (trace) for (int h = 0; h < 2; ++h) { cudaEventDestroy(tr0[h]); cudaEventDestroy(tr1[h]); }
+  b->last_pairs = 0; b->log_fetched = false; b->timed = false; b->last_path = 3;
+  return PHOVO_OK;
+}
+
+// what the shared-memory-resident kernels do not take: slot waves; the pool of per-pair contexts (same results as the
+// per-pair API by construction) stays selectable as a cross-check (phovo_batch_set_debug_flags bit 2)
+static int batch_other(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, const uint8_t* gray0,
+                       const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
+                       const double* initial_states, double* states, int32_t* iterations) {
+  if (b->debug_flags & 4) return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
+  return batch_waves(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
+}
+
+// true if the batch must take the wave (or pool) path (see make_params for what the shared-memory-resident kernels accept)
 static bool needs_pool(phovo_ctx* ctx, int num_pairs, int rows, int cols, int log_cap, BatchParams* bp, size_t* smem, int* rc_out) {
   if (ctx->cfg.mode == PHOVO_MODE_CERES || ctx->cfg.mode == PHOVO_MODE_BIOBJECTIVE) { *rc_out = PHOVO_OK; return true; }
   *rc_out = make_params(ctx, num_pairs, rows, cols, log_cap, bp, smem);
@@ -375,7 +646,7 @@ extern "C" int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows,
   if (needs_pool(ctx, num_pairs, rows, cols, log_cap, &bp, &smem, &rc)) {
     // pool path: synchronous; results go to the caller's device arrays through host temporaries
     std::vector<double> hs((size_t)num_pairs * 6); std::vector<int32_t> hi((size_t)num_pairs * PHOVO_MAX_LEVELS);
-    if ((rc = batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, hs.data(), hi.data()))) return rc;
+    if ((rc = batch_other(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, hs.data(), hi.data()))) return rc;
     CK(cudaMemcpyAsync(states, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(iters, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -406,7 +677,7 @@ extern "C" int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int co
   if ((rc = prepare_log(ctx, b, num_pairs, &log_cap))) return rc;
   BatchParams bp; size_t smem = 0;
   if (needs_pool(ctx, num_pairs, rows, cols, log_cap, &bp, &smem, &rc))
-    return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, states, iterations);
+    return batch_other(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, nullptr, initial_states, states, iterations);
   if (rc) return rc;
   b->last_path = 1;
   CK(ensure(&b->states, &b->states_cap, (size_t)num_pairs * 6));
@@ -525,5 +796,5 @@ extern "C" int phovo_batch_align_with_target_depth(phovo_ctx* ctx, int num_pairs
   CK(cudaSetDevice(ctx->device));
   phovo_batch_state* b; int rc = get_state(ctx, &b);
   if (rc) return rc;
-  return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
+  return batch_other(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
 }

@@ -87,11 +87,19 @@ struct phovo_ctx {
   // bookkeeping
   cudaEvent_t ev_copy = nullptr; cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};
   bool h2d_pending = false, copy_event_armed = false, setup_timed = false;
+  bool defer_device_input_drain = false; // batch slots: the owner of the context keeps device inputs alive and waits itself
   bool device_input_in_flight = false;   // a Set*Frame call was given a device pointer and its kernels are queued
   phovo::LaunchState launch_state;       // per-DEVICE function attributes / occupancy of the persistent kernels
   int64_t launches = 0;
 
   phovo_batch_state* batch = nullptr;
+
+  // Batch slots (phovo_batch.cu, wave path): a context used for its device side only.  Its level images, winner map,
+  // scratch and PoseDev are carved out of ONE allocation owned by the batch state (several hundred slots otherwise
+  // cost tens of cudaMalloc / cudaMallocHost calls each: seconds); no stream of its own, no pinned host buffers.
+  bool is_slot = false;
+  char* arena_base = nullptr; size_t arena_bytes = 0, arena_used = 0;
+  void arena_reset(char* base, size_t bytes);   // forget every arena-backed buffer; base == nullptr: leave the arena
 
   int fail(int code, const std::string& what);
   int cuda_fail(const char* what, cudaError_t e);
@@ -102,5 +110,9 @@ struct phovo_ctx {
 };
 
 void phovo_batch_release(phovo_ctx* ctx);
+// a slot context on `device` (see phovo_ctx::is_slot): set the stream and the arena before the first frame
+int phovo_internal_create_slot(int device, phovo_ctx** out);
+// device bytes a slot needs for rows x cols frames under its current config (upper bound, incl. alignment)
+size_t phovo_internal_slot_bytes(const phovo_ctx* ctx, int rows, int cols);
 
 #endif

@@ -59,6 +59,28 @@ struct LevelPtrs {
   const double* D1; const double* GxD; const double* GyD; const double* gain;
 };
 
+// Levenberg-Marquardt options of one level (Ceres mode, CE:464-477)
+struct LmParams {
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_radius, max_radius, min_radius, min_relative_decrease;
+  int max_iterations;
+};
+
+// Batch wave path (phovo_batch.cu): a SLOT is the device side of a child context -- the pyramids of one pair, its
+// winner map, its PoseDev.  k_align_slots runs one CTA per slot through every active level (coarse to fine).
+struct SlotArgs {
+  LevelPtrs P[PHOVO_MAX_LEVELS];
+  PoseDev* pose;
+  double* partials;              // one row of PHOVO_ACC_STRIDE doubles is used
+};
+struct SlotLevels {               // kernel parameter: the active levels, coarse to fine (the same for every slot)
+  int count;
+  LevelParams L[PHOVO_MAX_LEVELS];
+  LmParams lm[PHOVO_MAX_LEVELS];  // Ceres mode only
+};
+int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states);
+int launch_gather_slots(cudaStream_t stream, const SlotArgs* slots, int num_slots, double* states, int32_t* iters);
+
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);
 int launch_begin_level(cudaStream_t stream, PoseDev* pose, int max_iters);
 // K3a + K3b (+ optional dense residual / Jacobian dump) for one iteration; respects pose->done.

@@ -9,6 +9,11 @@ from test_gpu_parity import conv_cfg, make_odo, run_gpu
 pytestmark = pytest.mark.gpu
 
 
+def torch_cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
 def oracle_batch(oracle, cfg, K, g0, d0, g1, threads=8):
     st, it, _, _ = oracle.align_batch(conv_cfg(oracle, cfg), K, g0, d0.astype(np.float64), g1, num_threads=threads, lean=True)
     return st, it
@@ -245,10 +250,11 @@ def test_batch_unusual_depth_values_and_ranges(phovo, oracle):
                 assert np.array_equal(np.isnan(st[p]), np.isnan(o.state()))
 
 
-def test_batch_configurations_beyond_the_resident_kernels_take_the_pool_path(phovo):
+def test_batch_configurations_beyond_the_resident_kernels_take_the_wave_path(phovo):
     """phovo_batch_align never refuses a configuration: a level that does not fit in shared memory, blurred levels and the
-    Ceres-mode solver go pair by pair through the general path on a pool of per-pair contexts -- bitwise the states
-    and iteration counts of the per-pair API."""
+    Ceres-mode solver run in waves of per-pair slots -- pyramids by the general path's kernels, then one CTA per pair
+    through every level (k_align_slots).  Same iteration counts as the per-pair API and its states to the last bits
+    (one CTA sums what a grid summed); the pool of per-pair contexts (debug flag 4) gives them bitwise."""
     K = phovo.synth.K_FRAME_ALIGNMENT
     P = 6
     g0, d0, g1, _ = phovo.synth.make_batch(P, 480, 640, K=K, seed0=1)
@@ -262,16 +268,25 @@ def test_batch_configurations_beyond_the_resident_kernels_take_the_pool_path(pho
     cases.append(cfg)
     cases.append(phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi))
     odo = make_odo(phovo, cases[0], K)
+    init = np.zeros((P, 6)); init[:, 0] = 1e-3 * np.arange(P)
     for cfg in cases:
         odo.SetConfig(cfg)
-        st, it = odo.BatchAlign(g0, d0, g1)
-        assert odo.BatchLastPath() == 2
         single = make_odo(phovo, cfg, K)
+        ref_states, ref_iters = [], []
         for p in range(P):
-            single.SetSourceFrame(g0[p], d0[p]); single.SetTargetFrame(g1[p]); single.SetInitialStateVector(np.zeros(6))
+            single.SetSourceFrame(g0[p], d0[p]); single.SetTargetFrame(g1[p]); single.SetInitialStateVector(init[p])
             single.Optimize()
-            assert np.array_equal(st[p], single.GetOptimalStateVector()), (cfg.mode, p)
-            assert int(it[p].sum()) == len(single.IterationStats()) > 0
+            ref_states.append(single.GetOptimalStateVector()); ref_iters.append(len(single.IterationStats()))
+        for flags, path in ((0, 3), (4, 2)):
+            odo.BatchSetDebugFlags(flags)
+            for inputs in ((g0, d0, g1), tuple(torch_cuda(a) for a in (g0, d0, g1))):   # host and device-resident batches
+                st, it = odo.BatchAlign(*inputs, initial_states=init)
+                assert odo.BatchLastPath() == path
+                for p in range(P):
+                    if path == 2: assert np.array_equal(st[p], ref_states[p]), (cfg.mode, p)
+                    else: assert np.max(np.abs(st[p] - ref_states[p])) < 1e-10, (cfg.mode, p, st[p] - ref_states[p])
+                    assert int(it[p].sum()) == ref_iters[p] > 0, (cfg.mode, path, p)
+        odo.BatchSetDebugFlags(0)
     # back on the resident kernels
     odo.SetConfig(phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi))
     odo.BatchAlign(g0, d0, g1)

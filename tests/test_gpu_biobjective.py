@@ -80,11 +80,16 @@ def test_biobjective_needs_target_depth_also_in_a_batch(phovo):
     with pytest.raises(phovo.PhovoError) as e:
         odo.BatchAlign(g0[None], d0[None], g1[None])           # the batch entry needs the target depth too
     assert e.value.code == phovo.capi.E_INVALID
-    # with it, the batch goes pair by pair through the general path (pool of per-pair contexts): same as the per-pair API
+    # with it, the batch runs in waves of per-pair slots (one CTA per pair): same iterations, states to the last bits;
+    # the pool of per-pair contexts (debug flag 4) is bitwise the per-pair API
     odo.SetTargetFrame(g1, d1)
     odo.Optimize()
-    st, it = odo.BatchAlign(np.stack([g0, g0, g0]), np.stack([d0, d0, d0]), np.stack([g1, g1, g1]), depth1=np.stack([d1, d1, d1]))
-    assert odo.BatchLastPath() == 2
-    for p in range(3):
-        assert np.array_equal(st[p], odo.GetOptimalStateVector())
-        assert int(it[p].sum()) == len(odo.IterationStats()) > 0
+    for flags, path in ((0, 3), (4, 2)):
+        odo.BatchSetDebugFlags(flags)
+        st, it = odo.BatchAlign(np.stack([g0, g0, g0]), np.stack([d0, d0, d0]), np.stack([g1, g1, g1]), depth1=np.stack([d1, d1, d1]))
+        assert odo.BatchLastPath() == path
+        for p in range(3):
+            if path == 2: assert np.array_equal(st[p], odo.GetOptimalStateVector())
+            else: assert np.max(np.abs(st[p] - odo.GetOptimalStateVector())) < 1e-10
+            assert int(it[p].sum()) == len(odo.IterationStats()) > 0
+    odo.BatchSetDebugFlags(0)

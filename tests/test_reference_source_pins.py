@@ -107,7 +107,7 @@ def test_cuda_matches_reference_golden(phovo, name):
     assert np.max(np.abs(odo.GetOptimalRigidTransformationMatrix() - gd["rt"])) < 1e-10
     # the batch entry on the same pair: the shared-memory-resident kernels when its levels fit, else the pool path
     st, it = odo.BatchAlign(gd["gray0"][None], gd["depth0"][None], gd["gray1"][None])
-    assert odo.BatchLastPath() in (1, 2)
+    assert odo.BatchLastPath() in (1, 3)
     assert int(it.sum()) == len(gd["n"])
     assert_pose_close(st[0], gd["state"], name + " (batch)")
     assert np.max(np.abs(st[0] - gd["state"])) < 1e-10
