@@ -387,6 +387,32 @@ def secondary_block(phovo, torch, dev, local_rank, frames):
                                     "iterations_equal_cpu": len(log) == len(o.iter_stats()), "pose_abs_diff_vs_cpu": float(np.max(np.abs(s - o.state()))),
                                     "clocks": clocks}
     odo.close()
+
+    # ---- the batch entry for the other two solvers of the apps' METHOD macro (FrameAlignment.cpp:34-44): waves of per-pair
+    # slots, one CTA per pair through every level (k_align_slots); device-resident 640x480 pairs, wall clock around the call
+    K = phovo.synth.K_FRAME_ALIGNMENT
+    P = 1184
+    g0, d0, g1, _ = phovo.synth.render_batch_torch(P + 1, ROWS, COLS, K, dev, seed0=11)
+    waves = {}
+    for key, cfg_name, mode in (("photometric_plus_depth", CONFIG, phovo.MODE_BIOBJECTIVE), ("ceres_mode", "config_5_level_optimization_ceres", None)):
+        odo = phovo.CPhotoconsistencyOdometryCuda(device=local_rank)
+        odo.SetConfig(phovo.configs.to_config(cfg_name, phovo.capi, mode=mode) if mode is not None else phovo.configs.to_config(cfg_name, phovo.capi))
+        odo.SetIntrinsicMatrix(K)
+        kw = {"depth1": d0[1:P + 1].contiguous()} if mode is not None else {}
+        odo.BatchAlign(g0[:P], d0[:P], g1[:P], **kw)        # slots, arena, pinned result buffers
+        torch.cuda.synchronize(dev)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = odo.LaunchCount()
+        t0 = time.perf_counter()
+        st, it = odo.BatchAlign(g0[:P], d0[:P], g1[:P], **kw)
+        dt = time.perf_counter() - t0
+        waves[key] = {"config": cfg_name, "pairs": P, "pairs_per_s": P / dt, "ms_per_step": 1e3 * dt, "path": odo.BatchLastPath(),
+                      "mean_iterations_per_pair": float(it.sum()) / P, "finite": bool(np.isfinite(st).all()),
+                      "gpu_launches": int(odo.LaunchCount() - l0), "clocks": sampler.stop()}
+        odo.close()
+    out["batch_other_solvers_640x480"] = dict(waves, what="phovo_batch_align for the Ceres-mode and the photometric + depth solver: waves of per-pair slots (path 3), device-resident inputs, poses on the host")
+    del g0, d0, g1
     return out
 
 
