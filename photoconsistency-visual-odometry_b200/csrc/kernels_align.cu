@@ -554,42 +554,63 @@ __device__ __forceinline__ void level_loop(const LevelParams& L, const LevelPtrs
     const double spsr = T.sp * T.sr, spcr = T.sp * T.cr;
     if (MODE == 3) {
       const double gain = __ldg(P.gain);
-      for (int k = bid * kCoopBlock + tid; k < 2 * n; k += stride) {
-        // every array the row may read is loaded BEFORE anything depends on a loaded value: one or two memory round trips
-        // per row instead of six in a chain (winner -> I0[src]; valid[k] -> valid[k/2] -> D0[p] -> gradient), at the price
-        // of loads whose values are not used (the loop is latency-bound, not bandwidth-bound)
+      // Every array a row may read is loaded BEFORE anything depends on a loaded value, and ONE TRIP AHEAD: one memory
+      // round trip per row (I0 / D0 of the winner) overlapped with the next row's loads, instead of six in a chain
+      // (winner -> I0[src]; valid[k] -> valid[k/2] -> D0[p] -> gradient) -- at the price of loads whose values are not
+      // used: the loop is latency-bound, not bandwidth-bound.
+      struct RowLoads { int wkey; bool vk, vh; double i1, d1, d0k, d0h, gxk, gyk, gxh, gyh; };
+      auto load_row = [&](int k, RowLoads& R) {
         const int kh = k >> 1;
         const bool lo = k < n;
-        const int wkey = __ldcg(P.winner + k);
-        const bool vk = lo && __ldcg(P.valid + k) != 0;
-        const bool vh = __ldcg(P.valid + kh) != 0;
-        const double i1 = lo ? __ldg(P.I1 + k) : 0., d1 = __ldg(P.D1 + kh);
-        const double d0k = lo ? __ldg(P.D0 + k) : 0., d0h = __ldg(P.D0 + kh);
-        const double gxk = lo ? __ldg(P.Gx + k) : 0., gyk = lo ? __ldg(P.Gy + k) : 0.;
-        const double gxh = __ldg(P.GxD + kh), gyh = __ldg(P.GyD + kh);
+        R.wkey = __ldcg(P.winner + k);
+        R.vk = lo && __ldcg(P.valid + k) != 0;
+        R.vh = __ldcg(P.valid + kh) != 0;
+        R.i1 = lo ? __ldg(P.I1 + k) : 0.; R.d1 = __ldg(P.D1 + kh);
+        R.d0k = lo ? __ldg(P.D0 + k) : 0.; R.d0h = __ldg(P.D0 + kh);
+        R.gxk = lo ? __ldg(P.Gx + k) : 0.; R.gyk = lo ? __ldg(P.Gy + k) : 0.;
+        R.gxh = __ldg(P.GxD + kh); R.gyh = __ldg(P.GyD + kh);
+      };
+      const int k_first = bid * kCoopBlock + tid;
+      RowLoads N = {};
+      if (k_first < 2 * n) load_row(k_first, N);
+      for (int k = k_first; k < 2 * n; k += stride) {
+        const RowLoads R = N;
+        if (k + stride < 2 * n) load_row(k + stride, N);
         P.winner[k] = -1;
         double res = 0.;
-        if (wkey > 0) {
-          const int src = (wkey - 1) >> 1;
-          if (((wkey - 1) & 1) == 0) res = i1 - __ldg(P.I0 + src);                 // slot k = t
-          else res = gain * (d1 - __ldg(P.D0 + src));                               // slot k = 2 t
+        if (R.wkey > 0) {
+          const int src = (R.wkey - 1) >> 1;
+          if (((R.wkey - 1) & 1) == 0) res = R.i1 - __ldg(P.I0 + src);                 // slot k = t
+          else res = gain * (R.d1 - __ldg(P.D0 + src));                               // slot k = 2 t
           acc[27] = fma(res, res, acc[27]);
         }
-        if (vk) acc[28] += 1.;
+        if (R.vk) acc[28] += 1.;
         bool depth_row;
-        const int p = bi_row_owner(k, vk, vh, &depth_row);
+        const int p = bi_row_owner(k, R.vk, R.vh, &depth_row);
         if (p < 0) continue;
         double J[6];
-        bi_jacobian_core(L, T, spsr, spcr, gain, p, depth_row, depth_row ? d0h : d0k, depth_row ? gxh : gxk, depth_row ? gyh : gyk, J);
+        bi_jacobian_core(L, T, spsr, spcr, gain, p, depth_row, depth_row ? R.d0h : R.d0k, depth_row ? R.gxh : R.gxk, depth_row ? R.gyh : R.gyk, J);
         accumulate_row(acc, J, res);
       }
     } else {
       const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;   // the whole level unless row-sharded
-      for (int i = i_begin + bid * kCoopBlock + tid; i < i_end; i += stride) {
-        // everything indexed by i is loaded up front (coalesced, independent); only I0[winner] waits for a loaded value
-        const int win = __ldcg(P.winner + i);
-        const bool ok = __ldcg(P.valid + i) != 0;
-        const double i1 = __ldg(P.I1 + i), d = __ldg(P.D0 + i), gx = __ldg(P.Gx + i), gy = __ldg(P.Gy + i);
+      // Everything indexed by i is loaded up front (coalesced, independent) and ONE TRIP AHEAD: while this trip waits for
+      // I0[winner] and computes, the next trip's six loads are in flight.  (The winner word of the next trip is final:
+      // phase A ended at the barrier, and only this thread resets it.)
+      const int b_first = i_begin + bid * kCoopBlock + tid;
+      int win_n = -1; bool ok_n = false; double i1_n = 0., d_n = 0., gx_n = 0., gy_n = 0.;
+      if (b_first < i_end) {
+        win_n = __ldcg(P.winner + b_first); ok_n = __ldcg(P.valid + b_first) != 0;
+        i1_n = __ldg(P.I1 + b_first); d_n = __ldg(P.D0 + b_first); gx_n = __ldg(P.Gx + b_first); gy_n = __ldg(P.Gy + b_first);
+      }
+      for (int i = b_first; i < i_end; i += stride) {
+        const int win = win_n; const bool ok = ok_n;
+        const double i1 = i1_n, d = d_n, gx = gx_n, gy = gy_n;
+        const int j = i + stride;
+        if (j < i_end) {
+          win_n = __ldcg(P.winner + j); ok_n = __ldcg(P.valid + j) != 0;
+          i1_n = __ldg(P.I1 + j); d_n = __ldg(P.D0 + j); gx_n = __ldg(P.Gx + j); gy_n = __ldg(P.Gy + j);
+        }
         P.winner[i] = -1;
         double res = 0.;
         if (win >= 0) {
@@ -954,15 +975,19 @@ __device__ __forceinline__ void level_loop_ceres(const LevelParams& L, const Lev
       Warped w;
       if (!warp_pixel<true>(L, T, r, c, d, w)) continue;
       acc[28] += 1.;
-      if (__ldcg(P.winner + w.t) != i) continue;   // overwritten by a later source pixel (CE:261)
-      P.winner[w.t] = -1;                            // the winner cleans its slot (a loser that reads -1 has lost all the same)
+      // the twelve taps and I0 do not depend on who won the slot: they are issued together with the winner word (one
+      // memory round trip instead of two; a loser's taps are wasted, losers are few)
+      const int win = __ldcg(P.winner + w.t);
       int x1, x2, y1, y2; double dx, dy;
       linear_init_axis(w.tr - 0.5, L.rows, y1, y2, dy);   // sample.h:67-71
       linear_init_axis(w.tc - 0.5, L.cols, x1, x2, dx);
       const double s0 = bilinear(P.I1, L.cols, y1, y2, x1, x2, dy, dx);
       const double s1 = bilinear(P.Gx, L.cols, y1, y2, x1, x2, dy, dx);
       const double s2 = bilinear(P.Gy, L.cols, y1, y2, x1, x2, dy, dx);
-      const double res = s0 - __ldg(P.I0 + i);
+      const double i0 = __ldg(P.I0 + i);
+      if (win != i) continue;                        // overwritten by a later source pixel (CE:261)
+      P.winner[w.t] = -1;                            // the winner cleans its slot (a loser that reads -1 has lost all the same)
+      const double res = s0 - i0;
       double Ju[6], Jv[6], J[6];
       projection_jacobian<false>(L, T, w, d, Ju, Jv);
 #pragma unroll
