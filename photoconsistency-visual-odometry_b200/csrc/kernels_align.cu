@@ -594,34 +594,55 @@ __device__ __forceinline__ void level_loop(const LevelParams& L, const LevelPtrs
       }
     } else {
       const int i_begin = L.row_begin * L.cols, i_end = L.row_end * L.cols;   // the whole level unless row-sharded
-      // Everything indexed by i is loaded up front (coalesced, independent) and ONE TRIP AHEAD: while this trip waits for
-      // I0[winner] and computes, the next trip's six loads are in flight.  (The winner word of the next trip is final:
-      // phase A ended at the barrier, and only this thread resets it.)
-      const int b_first = i_begin + bid * kCoopBlock + tid;
-      int win_n = -1; bool ok_n = false; double i1_n = 0., d_n = 0., gx_n = 0., gy_n = 0.;
-      if (b_first < i_end) {
-        win_n = __ldcg(P.winner + b_first); ok_n = __ldcg(P.valid + b_first) != 0;
-        i1_n = __ldg(P.I1 + b_first); d_n = __ldg(P.D0 + b_first); gx_n = __ldg(P.Gx + b_first); gy_n = __ldg(P.Gy + b_first);
-      }
-      for (int i = b_first; i < i_end; i += stride) {
-        const int win = win_n; const bool ok = ok_n;
-        const double i1 = i1_n, d = d_n, gx = gx_n, gy = gy_n;
-        const int j = i + stride;
-        if (j < i_end) {
-          win_n = __ldcg(P.winner + j); ok_n = __ldcg(P.valid + j) != 0;
-          i1_n = __ldg(P.I1 + j); d_n = __ldg(P.D0 + j); gx_n = __ldg(P.Gx + j); gy_n = __ldg(P.Gy + j);
+      if (SHARD) {
+        // (a band is a few trips per thread: loading one trip ahead costs more than it hides there -- measured on 4 GPUs,
+        // 0.55 vs 0.63 ms for the 8K pair)
+        for (int i = i_begin + bid * kCoopBlock + tid; i < i_end; i += stride) {
+          const int win = __ldcg(P.winner + i);
+          const bool ok = __ldcg(P.valid + i) != 0;
+          const double i1 = __ldg(P.I1 + i), d = __ldg(P.D0 + i), gx = __ldg(P.Gx + i), gy = __ldg(P.Gy + i);
+          P.winner[i] = -1;
+          double res = 0.;
+          if (win >= 0) {
+            res = i1 - __ldg(P.I0 + win);
+            acc[27] = fma(res, res, acc[27]);
+          }
+          if (!ok) continue;
+          double J[6];
+          analytic_jacobian_core<MODE>(L, T, spsr, spcr, i, d, gx, gy, J);
+          accumulate_row(acc, J, res);
+          acc[28] += 1.;
         }
-        P.winner[i] = -1;
-        double res = 0.;
-        if (win >= 0) {
-          res = i1 - __ldg(P.I0 + win);
-          acc[27] = fma(res, res, acc[27]);
+      } else {
+        // Everything indexed by i is loaded up front (coalesced, independent) and ONE TRIP AHEAD: while this trip waits for
+        // I0[winner] and computes, the next trip's six loads are in flight.  (The winner word of the next trip is final:
+        // phase A ended at the barrier, and only this thread resets it.)
+        const int b_first = i_begin + bid * kCoopBlock + tid;
+        int win_n = -1; bool ok_n = false; double i1_n = 0., d_n = 0., gx_n = 0., gy_n = 0.;
+        if (b_first < i_end) {
+          win_n = __ldcg(P.winner + b_first); ok_n = __ldcg(P.valid + b_first) != 0;
+          i1_n = __ldg(P.I1 + b_first); d_n = __ldg(P.D0 + b_first); gx_n = __ldg(P.Gx + b_first); gy_n = __ldg(P.Gy + b_first);
         }
-        if (!ok) continue;
-        double J[6];
-        analytic_jacobian_core<MODE>(L, T, spsr, spcr, i, d, gx, gy, J);
-        accumulate_row(acc, J, res);
-        acc[28] += 1.;
+        for (int i = b_first; i < i_end; i += stride) {
+          const int win = win_n; const bool ok = ok_n;
+          const double i1 = i1_n, d = d_n, gx = gx_n, gy = gy_n;
+          const int j = i + stride;
+          if (j < i_end) {
+            win_n = __ldcg(P.winner + j); ok_n = __ldcg(P.valid + j) != 0;
+            i1_n = __ldg(P.I1 + j); d_n = __ldg(P.D0 + j); gx_n = __ldg(P.Gx + j); gy_n = __ldg(P.Gy + j);
+          }
+          P.winner[i] = -1;
+          double res = 0.;
+          if (win >= 0) {
+            res = i1 - __ldg(P.I0 + win);
+            acc[27] = fma(res, res, acc[27]);
+          }
+          if (!ok) continue;
+          double J[6];
+          analytic_jacobian_core<MODE>(L, T, spsr, spcr, i, d, gx, gy, J);
+          accumulate_row(acc, J, res);
+          acc[28] += 1.;
+        }
       }
       // row-sharded: slots outside the band that the warped rows may have bid for must be clean for the next iteration
       if (SHARD && (i_begin > 0 || i_end < n)) {
