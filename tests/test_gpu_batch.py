@@ -327,6 +327,49 @@ def test_batch_at_scale_matches_general_path(phovo):
     assert worst < 1e-9, worst
 
 
+def test_wave_path_over_several_waves_matches_the_pool_and_the_oracle(phovo, oracle):
+    """More pairs than slots: the two halves of slots alternate (a half is harvested before it is set up again), host
+    and device inputs, caller's initial states, both other solvers and a blurred analytic configuration.  Every pair
+    gets the iteration counts of the per-pair API (the pool, bitwise that API) and its state to 1e-10; a sample is
+    checked against the CPU oracle as well."""
+    import torch
+    K = phovo.synth.K_FRAME_ALIGNMENT.copy(); K[:2] *= 80 / 640.
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    P = 4 * sms + 37                                   # two full waves + a partial third: half 0 is reused
+    g0, d0, g1, _ = phovo.synth.make_batch(P + 1, 60, 80, K=K, seed0=5)
+    d1 = d0[1:P + 1].copy(); g0, d0, g1 = g0[:P], d0[:P], g1[:P]
+    init = np.zeros((P, 6)); init[:, 1] = 1e-4 * (np.arange(P) % 11)
+    cases = []
+    cfg = phovo.configs.to_config("test_3_level_all_active", phovo.capi); cfg.blur_filter_size[1] = 3
+    cases.append(("blurred analytic", cfg, {}))
+    cases.append(("photometric + depth", phovo.configs.to_config("test_3_level_all_active", phovo.capi, mode=phovo.MODE_BIOBJECTIVE), {"depth1": d1}))
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi); cfg.num_levels = 3
+    cases.append(("ceres-mode", cfg, {}))
+    for name, cfg, kw in cases:
+        odo = make_odo(phovo, cfg, K)
+        odo.BatchSetDebugFlags(4)
+        st_pool, it_pool = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+        assert odo.BatchLastPath() == 2
+        odo.BatchSetDebugFlags(0)
+        dev_kw = {k: torch_cuda(v) for k, v in kw.items()}
+        for inputs, kws in (((g0, d0, g1), kw), (tuple(torch_cuda(a) for a in (g0, d0, g1)), dev_kw)):
+            st, it = odo.BatchAlign(*inputs, initial_states=init, **kws)
+            assert odo.BatchLastPath() == 3
+            assert np.array_equal(it, it_pool), (name, np.nonzero((it != it_pool).any(axis=1))[0][:10])
+            fin = np.isfinite(st_pool).all(axis=1)
+            assert np.array_equal(np.isfinite(st).all(axis=1), fin), name
+            assert np.max(np.abs(st[fin] - st_pool[fin])) < 1e-10, (name, float(np.max(np.abs(st[fin] - st_pool[fin]))))
+        if name == "blurred analytic":                 # the oracle on a sample (analytic modes run in its batch entry)
+            sel = np.arange(0, P, 97)
+            for p in sel:
+                o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+                o.set_source(g0[p], d0[p].astype(np.float64)); o.set_target(g1[p]); o.set_initial_state(init[p]); o.optimize()
+                assert len(o.iter_stats()) == int(it[p].sum()), (name, p)
+                if np.isfinite(o.state()).all():
+                    assert_pose_close(st[p], o.state(), "%s pair %d" % (name, p))
+        odo.close()
+
+
 def test_randomised_parity_sweep(phovo, oracle):
     """A small slice of tools/fuzz_parity.py as a regression test: random sizes / intrinsics / configs."""
     import json
