@@ -59,7 +59,7 @@ struct phovo_batch_state {
   std::vector<phovo_ctx*> slots;
   cudaStream_t setup_stream[kWaveSetupThreads] = {}; cudaEvent_t ev_setup[kWaveSetupThreads] = {};
   cudaStream_t align_stream[2] = {nullptr, nullptr}; cudaEvent_t ev_wave_done[2] = {nullptr, nullptr}; cudaEvent_t ev_wave_in[2] = {nullptr, nullptr};
-  char* arena = nullptr; size_t arena_cap = 0, slot_bytes = 0; int arena_rows = 0, arena_cols = 0; phovo_config arena_cfg = {};
+  char* arena = nullptr; size_t arena_cap = 0, slot_bytes = 0; int arena_rows = 0, arena_cols = 0, arena_slots = 0, wave_half = 0; phovo_config arena_cfg = {};
   SlotArgs* d_slot_args = nullptr; size_t slot_args_cap = 0; std::vector<SlotArgs> h_slot_args;
   double* d_wave_init[2] = {nullptr, nullptr}; double* d_wave_states[2] = {nullptr, nullptr}; int32_t* d_wave_iters[2] = {nullptr, nullptr};
   double* h_wave_states[2] = {nullptr, nullptr}; int32_t* h_wave_iters[2] = {nullptr, nullptr}; size_t wave_cap = 0;
@@ -403,7 +403,7 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
 #endif
 static int wave_slots_per_half(const phovo_batch_state* b) { return PHOVO_SLOT_MINB * std::max(1, b->sm_count); }   // CTAs of k_align_slots resident per SM
 
-static int wave_resources(phovo_ctx* ctx, phovo_batch_state* b, int want_slots, int rows, int cols) {
+static int wave_resources(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, int* half_out) {
   for (int t = 0; t < kWaveSetupThreads; ++t)
     if (!b->setup_stream[t]) {
       CK(cudaStreamCreateWithFlags(&b->setup_stream[t], cudaStreamNonBlocking));
@@ -415,35 +415,50 @@ static int wave_resources(phovo_ctx* ctx, phovo_batch_state* b, int want_slots, 
       CK(cudaEventCreateWithFlags(&b->ev_wave_done[h], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&b->ev_wave_in[h], cudaEventDisableTiming));
     }
-  const bool grew = (int)b->slots.size() < want_slots;
-  while ((int)b->slots.size() < want_slots) {
-    phovo_ctx* c = nullptr;
-    if (phovo_internal_create_slot(ctx->device, &c) != PHOVO_OK) return ctx->fail(PHOVO_E_CUDA, std::string("batch slots: ") + phovo_last_error(nullptr));
-    const int s = (int)b->slots.size();
-    c->stream = b->setup_stream[(s % wave_slots_per_half(b)) % kWaveSetupThreads];   // not owned: the setup thread's stream
-    c->defer_device_input_drain = true;   // the wave's inputs outlive its kernels (batch_waves waits for the wave before they go)
-    b->slots.push_back(c);
-  }
-  // ---- the arena: ONE allocation, slot s at s * slot_bytes; laid out again whenever the configuration or the frame size changes ----
+  auto add_slots = [&](int want) -> int {
+    while ((int)b->slots.size() < want) {
+      phovo_ctx* c = nullptr;
+      if (phovo_internal_create_slot(ctx->device, &c) != PHOVO_OK) return ctx->fail(PHOVO_E_CUDA, std::string("batch slots: ") + phovo_last_error(nullptr));
+      c->defer_device_input_drain = true;   // the wave's inputs outlive its kernels (batch_waves waits for the wave before they go)
+      b->slots.push_back(c);
+    }
+    return PHOVO_OK;
+  };
+  int rc = add_slots(1);
+  if (rc) return rc;
+  // ---- bytes per slot under this configuration and frame size ----
   phovo_ctx* c0 = b->slots[0];
-  int rc = PHOVO_OK;
   if (memcmp(&c0->cfg, &ctx->cfg, sizeof(phovo_config)) != 0 && (rc = phovo_set_config(c0, &ctx->cfg))) return ctx->fail(rc, phovo_last_error(c0));
   const size_t need = phovo_internal_slot_bytes(c0, rows, cols);
-  const bool same = !grew && need == b->slot_bytes && rows == b->arena_rows && cols == b->arena_cols && memcmp(&b->arena_cfg, &ctx->cfg, sizeof(phovo_config)) == 0;
+  // ---- slots per half: the CTAs of k_align_slots one wave keeps resident -- fewer if two halves of them would take more
+  // than half of the device memory that is free (counting what the arena already holds) ----
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = (free_b + b->arena_cap) / 2;
+  if (const char* e = getenv("PHOVO_WAVE_BUDGET_MB")) budget = std::min(budget, (size_t)std::max(1LL, atoll(e)) << 20);   // test hook
+  int half = wave_slots_per_half(b);
+  if ((size_t)2 * half * need > budget) half = (int)std::max<size_t>(1, budget / need / 2);
+  const int want = num_pairs > half ? 2 * half : num_pairs;
+  if ((rc = add_slots(want))) return rc;
+  // ---- the arena: ONE allocation, slot s at s * slot_bytes; laid out again whenever configuration, frame size or slot count change ----
+  const bool same = want <= b->arena_slots && half == b->wave_half && need == b->slot_bytes && rows == b->arena_rows && cols == b->arena_cols &&
+                    memcmp(&b->arena_cfg, &ctx->cfg, sizeof(phovo_config)) == 0;
   if (!same) {
     CK(cudaDeviceSynchronize());                       // nothing of an earlier call is still running on the old layout
-    const size_t total = need * b->slots.size();
+    const size_t total = need * (size_t)want;
     if (total > b->arena_cap) {
       cudaFree(b->arena); b->arena = nullptr; b->arena_cap = 0;
       CK(cudaMalloc((void**)&b->arena, total));
       b->arena_cap = total;
     }
-    for (size_t s = 0; s < b->slots.size(); ++s) b->slots[s]->arena_reset(b->arena + s * need, need);
-    b->slot_bytes = need; b->arena_rows = rows; b->arena_cols = cols; b->arena_cfg = ctx->cfg;
+    for (size_t s = 0; s < b->slots.size(); ++s) {
+      if ((int)s < want) b->slots[s]->arena_reset(b->arena + s * need, need);
+      else b->slots[s]->arena_reset(nullptr, 0);       // not part of this layout (never used until the next one)
+    }
+    b->slot_bytes = need; b->arena_rows = rows; b->arena_cols = cols; b->arena_cfg = ctx->cfg; b->arena_slots = want; b->wave_half = half;
     for (auto& a : b->h_slot_args) memset(&a, 0, sizeof(a));
   }
-  const size_t half = (size_t)wave_slots_per_half(b);
-  if (b->wave_cap < half) {
+  if (b->wave_cap < (size_t)half) {
     for (int h = 0; h < 2; ++h) {
       cudaFree(b->d_wave_init[h]); cudaFree(b->d_wave_states[h]); cudaFree(b->d_wave_iters[h]);
       cudaFreeHost(b->h_wave_states[h]); cudaFreeHost(b->h_wave_iters[h]);
@@ -455,8 +470,9 @@ static int wave_resources(phovo_ctx* ctx, phovo_batch_state* b, int want_slots, 
     }
     b->wave_cap = half;
   }
-  CK(ensure(&b->d_slot_args, &b->slot_args_cap, 2 * half));
-  if (b->h_slot_args.size() < 2 * half) b->h_slot_args.resize(2 * half);
+  CK(ensure(&b->d_slot_args, &b->slot_args_cap, (size_t)2 * half));
+  if (b->h_slot_args.size() < (size_t)2 * half) b->h_slot_args.resize((size_t)2 * half);
+  *half_out = half;
   return PHOVO_OK;
 }
 
@@ -470,10 +486,10 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
     return ctx->fail(PHOVO_E_INVALID, "the photometric + depth solver needs the target depth: use phovo_batch_align_with_target_depth");
   // device-resident inputs produced on this context's stream must be complete: the slots run on streams of their own
   CK(cudaStreamSynchronize(ctx->stream));
-  const int half = wave_slots_per_half(b);
-  const int waves = (num_pairs + half - 1) / half;
-  int rc = wave_resources(ctx, b, waves > 1 ? 2 * half : std::min(half, num_pairs), rows, cols);
+  int half = 0;
+  int rc = wave_resources(ctx, b, num_pairs, rows, cols, &half);
   if (rc) return rc;
+  const int waves = (num_pairs + half - 1) / half;
   const size_t frame = (size_t)rows * cols, delt = depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2;
   b->last_h2d_bytes = 0;
   const bool host_in = host_readable(gray0) || host_readable(depth0) || host_readable(gray1) || (bi && host_readable(depth1));
@@ -527,6 +543,7 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
       for (int s = t; s < n; s += kWaveSetupThreads) {
         if (first_rc.load() != PHOVO_OK) return;
         phovo_ctx* c = b->slots[(size_t)h * half + s];
+        c->stream = b->setup_stream[t];      // not owned: this thread's stream
         int r = PHOVO_OK;
         if (memcmp(&c->cfg, &ctx->cfg, sizeof(phovo_config)) != 0) r = phovo_set_config(c, &ctx->cfg);
         if (!r) r = phovo_set_intrinsics(c, ctx->K);

@@ -370,6 +370,26 @@ def test_wave_path_over_several_waves_matches_the_pool_and_the_oracle(phovo, ora
         odo.close()
 
 
+def test_wave_path_with_a_small_memory_budget_runs_more_smaller_waves(phovo, monkeypatch):
+    """The slot arena takes at most half of the free device memory: with little of it the waves get smaller, the results
+    do not change (PHOVO_WAVE_BUDGET_MB is the test hook for 'little')."""
+    K = phovo.synth.K_FRAME_ALIGNMENT.copy(); K[:2] *= 160 / 640.
+    P = 23
+    g0, d0, g1, _ = phovo.synth.make_batch(P, 120, 160, K=K, seed0=3)
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi); cfg.num_levels = 3
+    odo = make_odo(phovo, cfg, K)
+    st_ref, it_ref = odo.BatchAlign(g0, d0, g1)
+    assert odo.BatchLastPath() == 3
+    monkeypatch.setenv("PHOVO_WAVE_BUDGET_MB", "8")       # a slot of this configuration is ~1.3 MB: 3 slots per half, 8 waves
+    st, it = odo.BatchAlign(g0, d0, g1)
+    assert odo.BatchLastPath() == 3
+    assert np.array_equal(it, it_ref) and np.array_equal(st, st_ref)   # same kernel, same order of sums: bitwise
+    monkeypatch.delenv("PHOVO_WAVE_BUDGET_MB")
+    st, it = odo.BatchAlign(g0, d0, g1)
+    assert np.array_equal(it, it_ref) and np.array_equal(st, st_ref)
+    odo.close()
+
+
 def test_randomised_parity_sweep(phovo, oracle):
     """A small slice of tools/fuzz_parity.py as a regression test: random sizes / intrinsics / configs."""
     import json
