@@ -10,12 +10,97 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 
 
+def wave_sweep(args):
+    phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
+    phovo.build()
+    import oracle_py
+    oracle_py.build()
+    rng = np.random.default_rng(args.seed)
+    stats = dict(pairs=0, groups=0, by_solver={}, iter_mismatch_vs_pool=0, worst_vs_pool=0., oracle_checked=0, iter_mismatch_vs_oracle=0,
+                 pose_over_bar_vs_oracle=0, worst_trans_vs_oracle=0., worst_rot_vs_oracle=0., nonfinite_mismatch=0)
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    t0 = time.time()
+    for gi in range(args.groups):
+        rows = int(rng.integers(40, 150)); cols = int(rng.choice([80, 160, 96, 120, 64, int(rng.integers(50, 200))]))
+        f = float(rng.uniform(0.7, 1.4)) * cols
+        K = np.array([[f, 0, (cols - 1) / 2 + rng.uniform(-3, 3)], [0, f * rng.uniform(0.97, 1.03), (rows - 1) / 2 + rng.uniform(-3, 3)], [0, 0, 1.]])
+        levels = int(rng.integers(2, 4))
+        solver = str(rng.choice(["blur", "ceres", "bi"]))
+        if solver == "ceres":
+            cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
+        else:
+            cfg = phovo.default_config()
+            cfg.mode = 3 if solver == "bi" else int(rng.integers(0, 2))
+        cfg.num_levels = levels
+        for l in range(levels):
+            cfg.max_num_iterations[l] = int(rng.integers(0, 12)) if l > 0 or rng.random() < 0.5 else 0
+            if solver != "ceres":
+                cfg.min_gradient_norm[l] = float(rng.choice([1., 30., 300.]))
+                cfg.lambda_step[l] = float(rng.choice([1., 1., 0.8]))
+            cfg.blur_filter_size[l] = int(rng.choice([0, 3, 5])) if solver == "blur" else 0
+        if sum(cfg.max_num_iterations[l] for l in range(levels)) == 0:
+            cfg.max_num_iterations[levels - 1] = 5
+        if solver == "blur" and not any(cfg.blur_filter_size[l] > 1 and cfg.max_num_iterations[l] > 0 for l in range(levels)):
+            l = max(l for l in range(levels) if cfg.max_num_iterations[l] > 0); cfg.blur_filter_size[l] = 3
+        cfg.min_depth, cfg.max_depth = float(rng.uniform(0.2, 1.0)), float(rng.uniform(2.1, 6.5))
+        P = args.pairs
+        scale = float(rng.choice([1., 1., 3.]))
+        g0 = np.empty((P + 1, rows, cols), np.uint8); g1 = np.empty_like(g0); d0 = np.empty((P + 1, rows, cols))
+        for p in range(P + 1):
+            xi = phovo.synth.random_motion(int(rng.integers(0, 1 << 30))) * scale
+            g0[p], d0[p], g1[p], _ = phovo.synth.make_pair(rows, cols, K, xi, int(rng.integers(0, 1 << 30)))
+        kw = {"depth1": d0[1:P + 1].copy()} if solver == "bi" else {}
+        g0, d0, g1 = g0[:P], d0[:P], g1[:P]
+        init = np.zeros((P, 6)); init[:, :3] = rng.uniform(-2e-3, 2e-3, (P, 3))
+        odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
+        odo.BatchSetDebugFlags(0)
+        st, it = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+        assert odo.BatchLastPath() == 3, odo.BatchLastPath()
+        odo.BatchSetDebugFlags(4)
+        pst, pit = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+        assert odo.BatchLastPath() == 2
+        odo.BatchSetDebugFlags(0)
+        stats["groups"] += 1; stats["pairs"] += P; stats["by_solver"][solver] = stats["by_solver"].get(solver, 0) + P
+        for p in range(P):
+            fin, pfin = np.isfinite(st[p]).all(), np.isfinite(pst[p]).all()
+            if fin != pfin:
+                stats["nonfinite_mismatch"] += 1
+                continue
+            if not np.array_equal(it[p], pit[p]):
+                stats["iter_mismatch_vs_pool"] += 1
+            elif fin:
+                stats["worst_vs_pool"] = max(stats["worst_vs_pool"], float(np.max(np.abs(st[p] - pst[p]))))
+        if solver != "bi":                                   # the oracle has the analytic and the Ceres-mode solver
+            ocfg = oracle_py.Config.from_buffer_copy(bytes(cfg))
+            for p in range(0, P, 3):
+                o = oracle_py.Oracle(ocfg, K)
+                o.set_source(g0[p], d0[p]); o.set_target(g1[p]); o.set_initial_state(init[p]); o.optimize()
+                os_ = o.state()
+                stats["oracle_checked"] += 1
+                if not (np.isfinite(os_).all() and np.isfinite(st[p]).all()):
+                    stats["nonfinite_mismatch"] += int(np.isfinite(os_).all() != np.isfinite(st[p]).all())
+                    continue
+                if len(o.iter_stats()) != int(it[p].sum()):
+                    stats["iter_mismatch_vs_oracle"] += 1
+                    continue
+                dt, dr = float(np.max(np.abs(st[p, :3] - os_[:3]))), float(np.max(np.abs(st[p, 3:] - os_[3:])))
+                stats["worst_trans_vs_oracle"] = max(stats["worst_trans_vs_oracle"], dt); stats["worst_rot_vs_oracle"] = max(stats["worst_rot_vs_oracle"], dr)
+                if dt >= 1e-4 or dr >= 1e-5:
+                    stats["pose_over_bar_vs_oracle"] += 1
+    stats["seconds"] = time.time() - t0
+    print(json.dumps(stats))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--groups", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=24)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--wave", action="store_true", help="the wave path of the batch entry (Ceres-mode, photometric + depth solver, blurred "
+                    "analytic levels) against the pool of per-pair contexts and, where the oracle has the solver, the CPU oracle")
     args = ap.parse_args()
+    if args.wave:
+        return wave_sweep(args)
     phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
     phovo.build()
     import oracle_py
