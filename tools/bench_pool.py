@@ -20,7 +20,7 @@ def one(pool, pairs):
     phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
     K = phovo.synth.K_FRAME_ALIGNMENT
     g0, d0, g1, _ = phovo.synth.render_batch_torch(pairs + 1, 480, 640, K, device="cuda")
-    out = {"pool_contexts": pool, "pairs": pairs}
+    out = {"pairs": pairs}
     for key, name, mode in (("biobjective", "config_4_level_optimization_analytic", phovo.MODE_BIOBJECTIVE),
                                          ("ceres", "config_5_level_optimization_ceres", None)):
         odo = phovo.CPhotoconsistencyOdometryCuda(device=0)

@@ -41,3 +41,14 @@ python tools/bench_dataset.py > "$OUT/${TAG}_dataset_vo_on_disk.json"
 for p in fp64_peak fp64_latency dmma_probe issue_probe; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o "tools/$p" "tools/$p.cu" && "./tools/$p" > "$OUT/${TAG}_$p.jsonl"
 done
+
+# 6. the wave path of the batch entry (Ceres-mode, photometric + depth solver, blurred / large levels)
+python tools/bench_pool.py 4 2048 > "$OUT/${TAG}_wave_path_throughput.json"            # pairs/s of both other solvers
+python tools/fuzz_parity.py --wave --groups 1500 --pairs 12 --seed 7 > "$OUT/${TAG}_fuzz_parity_wave_path_18k_pairs.json"
+ncu --set full --clock-control none --import-source on -k regex:k_align_slots --launch-skip 2 -c 1 -f -o "$OUT/prof_${TAG}_slots_bi" \
+    python tools/bench_pool.py 4 592 > /dev/null && python tools/ncu_summary.py "$OUT/prof_${TAG}_slots_bi.ncu-rep" > "$OUT/${TAG}_k_align_slots_bi.txt"
+ncu --set full --clock-control none --import-source on -k regex:k_align_slots --launch-skip 6 -c 1 -f -o "$OUT/prof_${TAG}_slots_ceres" \
+    python tools/bench_pool.py 4 592 > /dev/null && python tools/ncu_summary.py "$OUT/prof_${TAG}_slots_ceres.ncu-rep" > "$OUT/${TAG}_k_align_slots_ceres.txt"
+
+# 7. where the clocks of k_batch_level go (a variant library with clock64() around the sections of an iteration)
+bash tools/build_variant.sh secclk -- -DPHOVO_SECTION_CLOCKS && python tools/section_clocks.py build/variants/secclk.so 4096 > "$OUT/${TAG}_section_clocks.json"
