@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Throughput of the pool path of phovo_batch_align (modes / configurations the shared-memory-resident kernels do
-not take: Ceres mode, photometric + depth solver, blurred levels) for several pool sizes.
-usage (GPU box): python tools/bench_pool.py [pairs]"""
+"""Throughput of phovo_batch_align for what the shared-memory-resident kernels do not take (Ceres mode, photometric +
+depth solver): the wave path (path 3), device-resident 640x480 pairs.  PHOVO_WAVE_TRACE=1 prints per-wave timings.
+usage (GPU box): python tools/bench_pool.py <ignored> [pairs]     (first argument kept for old command lines)"""
 import importlib
 import json
 import os
@@ -44,6 +44,4 @@ if __name__ == "__main__":
     if len(sys.argv) > 2:
         one(int(sys.argv[1]), int(sys.argv[2]))
     else:
-        pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-        for pool in (1, 2, 4, 8, 16):
-            subprocess.run([sys.executable, __file__, str(pool), str(pairs)], check=False)
+        one(4, int(sys.argv[1]) if len(sys.argv) > 1 else 2048)
