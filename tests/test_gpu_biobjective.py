@@ -46,6 +46,13 @@ def test_biobjective_matches_reference_golden(phovo, name):
     _, s2, log2 = run(phovo, str(gd["config"]), gd["K"], gd["gray0"], gd["depth0"], gd["gray1"], gd["depth1"], graph=False)
     assert np.array_equal(s1, s2) and len(log1) == len(log2) == len(log)
     assert np.max(np.abs(s1 - s)) < 1e-11
+    # the batch entry (waves of per-pair slots, one CTA per pair through every level) on the same pair, twice in a batch
+    st, it = odo.BatchAlign(np.stack([gd["gray0"]] * 2), np.stack([gd["depth0"]] * 2), np.stack([gd["gray1"]] * 2), depth1=np.stack([gd["depth1"]] * 2))
+    assert odo.BatchLastPath() == 3
+    for p in range(2):
+        assert int(it[p].sum()) == len(gd["n"])
+        assert_pose_close(st[p], gd["state"], name + " (batch)")
+        assert np.max(np.abs(st[p] - gd["state"])) < 1e-9
 
 
 def test_biobjective_matches_reference_source_live_640x480(phovo, tmp_path):
@@ -62,6 +69,10 @@ def test_biobjective_matches_reference_source_live_640x480(phovo, tmp_path):
     for e, it in zip(log, iters):
         assert h_rel_err(e["H"], pack(it["H"])) < 1e-9 and g_rel_err(e["g"], it["g"]) < 1e-8
     assert np.max(np.abs(s - sref)) < 1e-9
+    # the batch entry at 640x480 against the reference's own solver (wave path)
+    st, itb = odo.BatchAlign(g0[None], d0[None], g1[None], depth1=d1[None])
+    assert odo.BatchLastPath() == 3 and int(itb.sum()) == len(iters)
+    assert np.max(np.abs(st[0] - sref)) < 1e-9
 
 
 def test_biobjective_needs_target_depth_also_in_a_batch(phovo):
