@@ -1347,7 +1347,7 @@ int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev*
 }
 
 int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states) {
-  if (num_slots < 1 || LS.count < 1) return 0;
+  if (num_slots < 1) return 0;   // (no active level: the kernel still writes the initial state into every slot's PoseDev)
   switch (mode) {
     case PHOVO_MODE_ANALYTIC_REF:   k_align_slots<0><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
     case PHOVO_MODE_ANALYTIC_FIXED: k_align_slots<1><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;

@@ -239,8 +239,8 @@ class CPhotoconsistencyOdometryCuda:
 
     # batch of independent pairs --------------------------------------------------------------
     def BatchLastPath(self):
-        """1: the shared-memory-resident batch kernels ran; 2: the pool of per-pair contexts (Ceres / photometric + depth
-        solver, blurred or large levels)."""
+        """1: the shared-memory-resident batch kernels ran; 3: waves of per-pair slots, one CTA per pair through every level
+        (Ceres / photometric + depth solver, blurred or large levels); 2: the pool of per-pair contexts (debug flag 4)."""
         return int(self._L.phovo_batch_last_path(self._h))
 
     def BatchAlign(self, gray0, depth0, gray1, initial_states=None, depth_scale=1.0, depth1=None):

@@ -298,6 +298,17 @@ def test_batch_configurations_beyond_the_resident_kernels_take_the_wave_path(pho
     odo.SetConfig(cfg)
     st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((P, 6), 0.01))
     assert np.array_equal(st, np.full((P, 6), 0.01)) and not it.any()
+    # the same through the wave path (Ceres mode) and the pool
+    cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
+    for l in range(5):
+        cfg.max_num_iterations[l] = 0
+    odo.SetConfig(cfg)
+    for flags, path in ((0, 3), (4, 2)):
+        odo.BatchSetDebugFlags(flags)
+        st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((P, 6), 0.02))
+        assert odo.BatchLastPath() == path
+        assert np.array_equal(st, np.full((P, 6), 0.02)) and not it.any()
+    odo.BatchSetDebugFlags(0)
 
 
 def test_batch_at_scale_matches_general_path(phovo):
