@@ -230,12 +230,13 @@ int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int cols,
                       const double* initial_states /* [P][6] or NULL = zeros */,
                       double* states, int32_t* iterations);
 /* Which implementation the last batch call took: 1 = the shared-memory-resident batch kernels (analytic solvers, no blur,
- * active levels up to ~22 K px: one streaming pyramid pass + one persistent launch per level); 3 = everything else
- * (Ceres-mode and photometric + depth solver, blurred levels, larger levels) runs in WAVES of per-pair slots: the pyramids
+ * active levels up to ~22 K px: one streaming pyramid pass + one persistent launch per level).  Everything else
+ * (Ceres-mode and photometric + depth solver, blurred levels, larger levels): 3 = WAVES of per-pair slots -- the pyramids
  * of a wave are built with the general path's kernels, then one launch aligns the whole wave, one CTA per pair through
- * every level and iteration -- the per-pair API's iteration counts, and its states up to the grouping of the partial
- * sums (last bits); 2 = the cross-check selected by debug flag 4: the pairs go one by one through the general path on a
- * pool of per-pair contexts, one host thread each -- bitwise the results of a loop over the per-pair API. */
+ * every level and iteration -- for batches from about half an SM count (Ceres-mode) / one SM count (other solvers) of
+ * pairs on; 2 = smaller batches: the pairs go one by one through the general path on a pool of per-pair contexts, one
+ * host thread each -- bitwise the results of a loop over the per-pair API.  Paths 2 and 3 give the same iteration counts
+ * and states equal up to the grouping of the partial sums (last bits). */
 int phovo_batch_last_path(const phovo_ctx* ctx);
 /* phovo_batch_align for the photometric + depth solver (PHOVO_MODE_BIOBJECTIVE), which also reads the TARGET depth
  * (depth1 [P][rows][cols], same type / scale as depth0; BiObjective.h:567-579).  Other modes ignore depth1. */
@@ -255,8 +256,8 @@ int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int index, phovo_
 int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);
 /* test hooks of the batch kernel (results must not change): bit 0 = every pixel takes the exact
  * reference warp instead of the estimate-then-verify shortcut; bit 1 = use the generic
- * thread->pixel bookkeeping even when the CTA width is a multiple of the level width; bit 2 = what the
- * resident kernels do not take goes through the pool of per-pair contexts instead of the slot waves */
+ * thread->pixel bookkeeping even when the CTA width is a multiple of the level width; bit 2 / bit 3 = what the
+ * resident kernels do not take goes through the pool of per-pair contexts / the slot waves whatever the batch size */
 int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags);
 /* bytes the last phovo_batch_align call copied host -> device.  Host batches are uploaded without
  * the source rows no active pyramid level reads (the levels are point-decimated from the original

@@ -307,7 +307,7 @@ static int prepare_log(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int*
 // by its own host thread, so that the frame set-up of one pair overlaps the iteration loop of another.  Same results
 // as calling the per-pair API in a loop, by construction.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPoolContexts = 4;
+constexpr int kPoolContexts = 8;   // measured: 1 / 2 / 4 / 8 contexts 2.5 / 4.8 / 8.9 / 12.2 K pairs/s; beyond the 8 hardware queues it collapses
 constexpr int kPoolContextsMax = 32;
 // PHOVO_POOL_CONTEXTS overrides the number of child contexts (1..32): a tuning knob, results do not depend on it
 static int pool_contexts() {
@@ -630,12 +630,18 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
   return PHOVO_OK;
 }
 
-// what the shared-memory-resident kernels do not take: slot waves; the pool of per-pair contexts (same results as the
-// per-pair API by construction) stays selectable as a cross-check (phovo_batch_set_debug_flags bit 2)
+// What the shared-memory-resident kernels do not take.  A wave gives every pair ONE CTA: the GPU is full from about one pair
+// per SM on, but the wave lasts as long as its slowest pair takes alone on one CTA (10-20 ms for a 640x480 pair), however few
+// pairs there are.  The pool of per-pair contexts gives every pair the whole GPU, one after the other (about 0.1-0.2 ms per
+// pair).  So: small batches go through the pool, the others in waves -- measured crossover on B200 (tools/wave_crossover.py,
+// 640x480): about 80 pairs for the Ceres-mode solver, 150 for the photometric + depth solver, i.e. half an SM count / one SM
+// count; debug flag 4 forces the pool, 8 the waves.  Same iteration counts either way, states equal to the last bits.
 static int batch_other(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, const uint8_t* gray0,
                        const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
                        const double* initial_states, double* states, int32_t* iterations) {
-  if (b->debug_flags & 4) return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
+  const int min_pairs = ctx->cfg.mode == PHOVO_MODE_CERES ? std::max(1, b->sm_count / 2) : std::max(1, b->sm_count);
+  const bool pool = (b->debug_flags & 4) || (!(b->debug_flags & 8) && num_pairs < min_pairs);
+  if (pool) return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
   return batch_waves(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
 }
 

@@ -277,7 +277,9 @@ def test_batch_configurations_beyond_the_resident_kernels_take_the_wave_path(pho
             single.SetSourceFrame(g0[p], d0[p]); single.SetTargetFrame(g1[p]); single.SetInitialStateVector(init[p])
             single.Optimize()
             ref_states.append(single.GetOptimalStateVector()); ref_iters.append(len(single.IterationStats()))
-        for flags, path in ((0, 3), (4, 2)):
+        st, it = odo.BatchAlign(g0, d0, g1, initial_states=init)
+        assert odo.BatchLastPath() == 2                       # a small batch: the pool by default
+        for flags, path in ((8, 3), (4, 2)):
             odo.BatchSetDebugFlags(flags)
             for inputs in ((g0, d0, g1), tuple(torch_cuda(a) for a in (g0, d0, g1))):   # host and device-resident batches
                 st, it = odo.BatchAlign(*inputs, initial_states=init)
@@ -303,7 +305,7 @@ def test_batch_configurations_beyond_the_resident_kernels_take_the_wave_path(pho
     for l in range(5):
         cfg.max_num_iterations[l] = 0
     odo.SetConfig(cfg)
-    for flags, path in ((0, 3), (4, 2)):
+    for flags, path in ((8, 3), (4, 2)):
         odo.BatchSetDebugFlags(flags)
         st, it = odo.BatchAlign(g0, d0, g1, initial_states=np.full((P, 6), 0.02))
         assert odo.BatchLastPath() == path
@@ -389,6 +391,7 @@ def test_wave_path_with_a_small_memory_budget_runs_more_smaller_waves(phovo, mon
     g0, d0, g1, _ = phovo.synth.make_batch(P, 120, 160, K=K, seed0=3)
     cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi); cfg.num_levels = 3
     odo = make_odo(phovo, cfg, K)
+    odo.BatchSetDebugFlags(8)                              # waves whatever the batch size
     st_ref, it_ref = odo.BatchAlign(g0, d0, g1)
     assert odo.BatchLastPath() == 3
     monkeypatch.setenv("PHOVO_WAVE_BUDGET_MB", "8")       # a slot of this configuration is ~1.3 MB: 3 slots per half, 8 waves

@@ -47,6 +47,7 @@ def test_biobjective_matches_reference_golden(phovo, name):
     assert np.array_equal(s1, s2) and len(log1) == len(log2) == len(log)
     assert np.max(np.abs(s1 - s)) < 1e-11
     # the batch entry (waves of per-pair slots, one CTA per pair through every level) on the same pair, twice in a batch
+    odo.BatchSetDebugFlags(8)
     st, it = odo.BatchAlign(np.stack([gd["gray0"]] * 2), np.stack([gd["depth0"]] * 2), np.stack([gd["gray1"]] * 2), depth1=np.stack([gd["depth1"]] * 2))
     assert odo.BatchLastPath() == 3
     for p in range(2):
@@ -70,6 +71,7 @@ def test_biobjective_matches_reference_source_live_640x480(phovo, tmp_path):
         assert h_rel_err(e["H"], pack(it["H"])) < 1e-9 and g_rel_err(e["g"], it["g"]) < 1e-8
     assert np.max(np.abs(s - sref)) < 1e-9
     # the batch entry at 640x480 against the reference's own solver (wave path)
+    odo.BatchSetDebugFlags(8)
     st, itb = odo.BatchAlign(g0[None], d0[None], g1[None], depth1=d1[None])
     assert odo.BatchLastPath() == 3 and int(itb.sum()) == len(iters)
     assert np.max(np.abs(st[0] - sref)) < 1e-9
@@ -95,7 +97,7 @@ def test_biobjective_needs_target_depth_also_in_a_batch(phovo):
     # the pool of per-pair contexts (debug flag 4) is bitwise the per-pair API
     odo.SetTargetFrame(g1, d1)
     odo.Optimize()
-    for flags, path in ((0, 3), (4, 2)):
+    for flags, path in ((8, 3), (4, 2), (0, 2)):
         odo.BatchSetDebugFlags(flags)
         st, it = odo.BatchAlign(np.stack([g0, g0, g0]), np.stack([d0, d0, d0]), np.stack([g1, g1, g1]), depth1=np.stack([d1, d1, d1]))
         assert odo.BatchLastPath() == path

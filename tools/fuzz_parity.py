@@ -53,7 +53,7 @@ def wave_sweep(args):
         g0, d0, g1 = g0[:P], d0[:P], g1[:P]
         init = np.zeros((P, 6)); init[:, :3] = rng.uniform(-2e-3, 2e-3, (P, 3))
         odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
-        odo.BatchSetDebugFlags(0)
+        odo.BatchSetDebugFlags(8)
         st, it = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
         assert odo.BatchLastPath() == 3, odo.BatchLastPath()
         odo.BatchSetDebugFlags(4)
