@@ -233,8 +233,8 @@ int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int cols,
  * active levels up to ~22 K px: one streaming pyramid pass + one persistent launch per level).  Everything else
  * (Ceres-mode and photometric + depth solver, blurred levels, larger levels): 3 = WAVES of per-pair slots -- the pyramids
  * of a wave are built with the general path's kernels, then one launch aligns the whole wave, one CTA per pair through
- * every level and iteration -- for batches from about half an SM count (Ceres-mode) / one SM count (other solvers) of
- * pairs on; 2 = smaller batches: the pairs go one by one through the general path on a pool of per-pair contexts, one
+ * every level and iteration (a thread-block cluster of 2 / 4 / 8 CTAs per pair while the wave is too small to fill the
+ * GPU) -- for batches of 16 (Ceres-mode) / 24 (other solvers) pairs or more; 2 = smaller batches: the pairs go one by one through the general path on a pool of per-pair contexts, one
  * host thread each -- bitwise the results of a loop over the per-pair API.  Paths 2 and 3 give the same iteration counts
  * and states equal up to the grouping of the partial sums (last bits). */
 int phovo_batch_last_path(const phovo_ctx* ctx);

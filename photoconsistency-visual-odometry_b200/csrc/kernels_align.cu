@@ -490,18 +490,27 @@ __device__ __forceinline__ int shard_halo_rows(const LevelParams& L, const Pose&
   return (int)ceil(dy) + 2;
 }
 
-// SLOT: the same loop run by ONE CTA on its own pair (the batch slot kernels below): the grid barriers become
-// block barriers, the CTA is "block 0 of a grid of 1".
-template <bool SLOT>
+// SLOT 1: the same loop run by ONE CTA on its own pair (the batch slot kernels below): the grid barriers become block
+// barriers, the CTA is "block 0 of a grid of 1".  SLOT 2: by one thread-block CLUSTER per pair (small waves: more CTAs per
+// pair than pairs per SM), cluster barriers.  SLOT 0: the cooperative grid.
+template <int SLOT>
 __device__ __forceinline__ void level_barrier() {
-  if (SLOT) __syncthreads();
+  if (SLOT == 1) __syncthreads();
+  else if (SLOT == 2) cooperative_groups::this_cluster().sync();   // release / acquire at cluster scope: orders the global writes too
   else cooperative_groups::this_grid().sync();
 }
+// the CTA's index among the CTAs that share the pair, and their number
+template <int SLOT> __device__ __forceinline__ int level_block_rank() {
+  return SLOT == 1 ? 0 : SLOT == 2 ? (int)cooperative_groups::this_cluster().block_rank() : (int)blockIdx.x;
+}
+template <int SLOT> __device__ __forceinline__ int level_num_blocks() {
+  return SLOT == 1 ? 1 : SLOT == 2 ? (int)cooperative_groups::this_cluster().num_blocks() : (int)gridDim.x;
+}
 
-template <int MODE, bool SHARD, bool SLOT>
+template <int MODE, bool SHARD, int SLOT>
 __device__ __forceinline__ void level_loop(const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                                            phovo_iter_stats* log, const ShardArgs& S) {
-  const int bid = SLOT ? 0 : (int)blockIdx.x, nblk = SLOT ? 1 : (int)gridDim.x;
+  const int bid = level_block_rank<SLOT>(), nblk = level_num_blocks<SLOT>();
   __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
   __shared__ double s_tot[32];
   __shared__ PoseDev s_pose;
@@ -738,7 +747,7 @@ __device__ __forceinline__ void level_loop(const LevelParams& L, const LevelPtrs
 template <int MODE, bool SHARD>
 __global__ void __launch_bounds__(kCoopBlock, 2) k_level_coop(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
                                                                phovo_iter_stats* log, ShardArgs S) {
-  level_loop<MODE, SHARD, false>(L, P, pose, partials, log, S);
+  level_loop<MODE, SHARD, 0>(L, P, pose, partials, log, S);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -948,10 +957,10 @@ __device__ bool lm_next_step(const LevelParams& L, const LmParams& lm, LmState& 
   return true;
 }
 
-template <bool SLOT>
+template <int SLOT>
 __device__ __forceinline__ void level_loop_ceres(const LevelParams& L, const LevelPtrs& P, PoseDev* pose, double* partials,
                                                  phovo_iter_stats* log, const LmParams& lm) {
-  const int bid = SLOT ? 0 : (int)blockIdx.x, nblk = SLOT ? 1 : (int)gridDim.x;
+  const int bid = level_block_rank<SLOT>(), nblk = level_num_blocks<SLOT>();
   __shared__ double smem[(kCoopBlock / 32) * PHOVO_ACC_STRIDE];
   __shared__ double s_tot[32];
   __shared__ PoseDev s_pose;
@@ -1102,7 +1111,7 @@ __device__ __forceinline__ void level_loop_ceres(const LevelParams& L, const Lev
 #endif
 __global__ void __launch_bounds__(kCoopBlock, PHOVO_CERES_COOP_MINB) k_level_coop_ceres(LevelParams L, LevelPtrs P, PoseDev* pose, double* partials,
                                                                      phovo_iter_stats* log, LmParams lm) {
-  level_loop_ceres<false>(L, P, pose, partials, log, lm);
+  level_loop_ceres<0>(L, P, pose, partials, log, lm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1116,13 +1125,15 @@ __global__ void __launch_bounds__(kCoopBlock, PHOVO_CERES_COOP_MINB) k_level_coo
 #ifndef PHOVO_SLOT_MINB
 #define PHOVO_SLOT_MINB 2
 #endif
-template <int MODE>
+template <int MODE, bool CLUSTER>
 __global__ void __launch_bounds__(kCoopBlock, PHOVO_SLOT_MINB) k_align_slots(const __grid_constant__ SlotLevels LS, const SlotArgs* __restrict__ slots,
                                                                 const double* __restrict__ init_states) {
-  const SlotArgs& A = slots[blockIdx.x];
-  if (threadIdx.x == 0) {   // k_set_state for this slot: the caller's initial state (zero if none), counters cleared, no log
+  constexpr int S = CLUSTER ? 2 : 1;
+  const int slot = (int)blockIdx.x / level_num_blocks<S>();      // clusters are runs of consecutive blocks
+  const SlotArgs& A = slots[slot];
+  if (level_block_rank<S>() == 0 && threadIdx.x == 0) {   // k_set_state for this slot: the caller's initial state (zero if none), counters cleared, no log
     double s[6];
-    for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)blockIdx.x * 6 + k] : 0.;
+    for (int k = 0; k < 6; ++k) s[k] = init_states ? init_states[(size_t)slot * 6 + k] : 0.;
     Pose P0;
     pose_from_state(s, P0);
     PoseDev* pose = A.pose;
@@ -1131,12 +1142,12 @@ __global__ void __launch_bounds__(kCoopBlock, PHOVO_SLOT_MINB) k_align_slots(con
     pose->iteration = 0; pose->done = 0; pose->log_count = 0; pose->log_capacity = 0;
     for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) pose->iters_per_level[l] = 0;
   }
-  __syncthreads();
+  level_barrier<S>();
   for (int a = 0; a < LS.count; ++a) {
     const LevelParams& L = LS.L[a];
-    if (MODE == PHOVO_MODE_CERES) level_loop_ceres<true>(L, A.P[L.level], A.pose, A.partials, nullptr, LS.lm[a]);
-    else level_loop<MODE, false, true>(L, A.P[L.level], A.pose, A.partials, nullptr, ShardArgs{nullptr, 0, 1, 0ull, nullptr});
-    __syncthreads();   // the level's PoseDev is in global memory (written and re-read by thread 0); shared scratch is free again
+    if (MODE == PHOVO_MODE_CERES) level_loop_ceres<S>(L, A.P[L.level], A.pose, A.partials, nullptr, LS.lm[a]);
+    else level_loop<MODE, false, S>(L, A.P[L.level], A.pose, A.partials, nullptr, ShardArgs{nullptr, 0, 1, 0ull, nullptr});
+    level_barrier<S>();   // the level's PoseDev is in global memory (written by rank 0, re-read by every CTA of the pair); shared scratch is free again
   }
 }
 
@@ -1346,15 +1357,32 @@ int launch_solve_from_buffer(cudaStream_t stream, const LevelParams& L, PoseDev*
   return 1;
 }
 
-int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states) {
-  if (num_slots < 1) return 0;   // (no active level: the kernel still writes the initial state into every slot's PoseDev)
-  switch (mode) {
-    case PHOVO_MODE_ANALYTIC_REF:   k_align_slots<0><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
-    case PHOVO_MODE_ANALYTIC_FIXED: k_align_slots<1><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
-    case PHOVO_MODE_CERES:          k_align_slots<2><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
-    default:                        k_align_slots<3><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states); break;
+template <int MODE>
+static cudaError_t launch_align_slots_mode(cudaStream_t stream, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states, int cluster) {
+  if (cluster <= 1) {
+    k_align_slots<MODE, false><<<num_slots, kCoopBlock, 0, stream>>>(LS, slots, init_states);
+    return cudaGetLastError();
   }
-  return 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_slots * cluster)); cfg.blockDim = dim3(kCoopBlock); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_align_slots<MODE, true>, LS, slots, init_states);
+}
+
+// `cluster` CTAs per slot (1, 2, 4 or 8: the portable cluster sizes)
+int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states, int cluster) {
+  if (num_slots < 1) return 0;   // (no active level: the kernel still writes the initial state into every slot's PoseDev)
+  cudaError_t e;
+  switch (mode) {
+    case PHOVO_MODE_ANALYTIC_REF:   e = launch_align_slots_mode<0>(stream, LS, slots, num_slots, init_states, cluster); break;
+    case PHOVO_MODE_ANALYTIC_FIXED: e = launch_align_slots_mode<1>(stream, LS, slots, num_slots, init_states, cluster); break;
+    case PHOVO_MODE_CERES:          e = launch_align_slots_mode<2>(stream, LS, slots, num_slots, init_states, cluster); break;
+    default:                        e = launch_align_slots_mode<3>(stream, LS, slots, num_slots, init_states, cluster); break;
+  }
+  return e == cudaSuccess ? 1 : -1;
 }
 
 int launch_gather_slots(cudaStream_t stream, const SlotArgs* slots, int num_slots, double* states, int32_t* iters) {

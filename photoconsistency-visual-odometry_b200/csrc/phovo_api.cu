@@ -76,7 +76,7 @@ LevelPtrs phovo_ctx::level_ptrs(int level) const {
 #define CK(call)                                                      \
   do {                                                                \
     cudaError_t e_ = (call);                                          \
-    if (e_ != cudaSuccess) return ctx->cuda_fail(#call, e_);          \
+    if (e_ != cudaSuccess) return ctx->cuda_fail((std::string(__func__) + ": " #call).c_str(), e_); \
   } while (0)
 
 template <class T>
@@ -176,9 +176,13 @@ static int prepare_levels(phovo_ctx* ctx, int rows, int cols) {
   }
   if (max_px == 0) max_px = 1;
   {
+    // (re)allocated <=> refill with -1.  NOT "the pointer changed": cudaFree + cudaMalloc may hand the same address back
+    // with a larger extent, whose tail is garbage -- winner indices nobody wrote (found by the randomised sweep on a
+    // pool of 8 contexts: illegal addresses in phase B after a frame-size change)
+    const bool reallocated = !(ctx->winner && ctx->winner_cap >= 2 * max_px);
     int* before = ctx->winner;
     CK(ctx_ensure(ctx, &ctx->winner, &ctx->winner_cap, 2 * max_px));   // the photometric + depth solver stacks 2N rows
-    if (before != ctx->winner) {
+    if (reallocated || before != ctx->winner) {
       changed = true;
       launch_fill_i32(ctx->stream, ctx->winner, -1, ctx->winner_cap, ctx->sm_count);
       ctx->launches += 1;

@@ -70,7 +70,7 @@ struct phovo_batch_state {
 #define CK(call)                                                      \
   do {                                                                \
     cudaError_t e_ = (call);                                          \
-    if (e_ != cudaSuccess) return ctx->cuda_fail(#call, e_);          \
+    if (e_ != cudaSuccess) return ctx->cuda_fail((std::string(__func__) + ": " #call).c_str(), e_); \
   } while (0)
 
 template <class T>
@@ -612,7 +612,16 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
       d_init = b->d_wave_init[h];
     }
     if (trace) cudaEventRecord(tr0[h], as);
-    ctx->launches += launch_align_slots(as, ctx->cfg.mode, LS, b->d_slot_args + (size_t)h * half, n, d_init);
+    // CTAs per pair: one when the wave fills the GPU; a small wave gives every pair a thread-block cluster (2, 4 or 8 CTAs,
+    // cluster barriers) so that the SMs it would leave idle shorten the wave instead
+    int cluster = 1;
+    for (int c = 8; c > 1; c >>= 1)
+      if (n * c <= PHOVO_SLOT_MINB * b->sm_count) { cluster = c; break; }
+    if (const char* e = getenv("PHOVO_WAVE_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v; }   // experiment hook
+    int launched = launch_align_slots(as, ctx->cfg.mode, LS, b->d_slot_args + (size_t)h * half, n, d_init, cluster);
+    if (launched < 0 && cluster > 1) { cudaGetLastError(); launched = launch_align_slots(as, ctx->cfg.mode, LS, b->d_slot_args + (size_t)h * half, n, d_init, 1); }
+    if (launched < 0) return ctx->cuda_fail("k_align_slots", cudaGetLastError());
+    ctx->launches += launched;
     if (trace) cudaEventRecord(tr1[h], as);
     ctx->launches += launch_gather_slots(as, b->d_slot_args + (size_t)h * half, n, b->d_wave_states[h], b->d_wave_iters[h]);
     CK(cudaGetLastError());
@@ -630,16 +639,16 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
   return PHOVO_OK;
 }
 
-// What the shared-memory-resident kernels do not take.  A wave gives every pair ONE CTA: the GPU is full from about one pair
-// per SM on, but the wave lasts as long as its slowest pair takes alone on one CTA (10-20 ms for a 640x480 pair), however few
-// pairs there are.  The pool of per-pair contexts gives every pair the whole GPU, one after the other (about 0.1-0.2 ms per
-// pair).  So: small batches go through the pool, the others in waves -- measured crossover on B200 (tools/wave_crossover.py,
-// 640x480): about 80 pairs for the Ceres-mode solver, 150 for the photometric + depth solver, i.e. half an SM count / one SM
-// count; debug flag 4 forces the pool, 8 the waves.  Same iteration counts either way, states equal to the last bits.
+// What the shared-memory-resident kernels do not take.  A wave gives every pair one CTA -- or, while the wave is too small
+// to fill the GPU, one thread-block cluster of 2 / 4 / 8 CTAs -- and lasts as long as its slowest pair takes on that.  The
+// pool of per-pair contexts gives every pair the whole GPU, one after the other (about 0.1-0.2 ms per pair).  Measured on
+// B200 at 640x480 (tools/wave_cluster_sweep.py, profiles/r02_wave_cluster_sweep.jsonl): the pool wins below about 12 pairs
+// (Ceres-mode solver) / 24 pairs (photometric + depth solver), the waves above.  Debug flag 4 forces the pool, 8 the
+// waves.  Same iteration counts either way, states equal to the last bits.
 static int batch_other(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int rows, int cols, const uint8_t* gray0,
                        const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
                        const double* initial_states, double* states, int32_t* iterations) {
-  const int min_pairs = ctx->cfg.mode == PHOVO_MODE_CERES ? std::max(1, b->sm_count / 2) : std::max(1, b->sm_count);
+  const int min_pairs = ctx->cfg.mode == PHOVO_MODE_CERES ? 16 : 24;
   const bool pool = (b->debug_flags & 4) || (!(b->debug_flags & 8) && num_pairs < min_pairs);
   if (pool) return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
   return batch_waves(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);

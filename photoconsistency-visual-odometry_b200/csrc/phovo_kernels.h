@@ -78,7 +78,8 @@ struct SlotLevels {               // kernel parameter: the active levels, coarse
   LevelParams L[PHOVO_MAX_LEVELS];
   LmParams lm[PHOVO_MAX_LEVELS];  // Ceres mode only
 };
-int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states);
+int launch_align_slots(cudaStream_t stream, int mode, const SlotLevels& LS, const SlotArgs* slots, int num_slots, const double* init_states,
+                       int cluster /* CTAs per slot: 1, 2, 4 or 8 */);   // < 0: the launch failed
 int launch_gather_slots(cudaStream_t stream, const SlotArgs* slots, int num_slots, double* states, int32_t* iters);
 
 int launch_set_state(cudaStream_t stream, PoseDev* pose, const double* state_dev_or_null, const double state_host[6], int log_capacity);

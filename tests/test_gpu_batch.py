@@ -401,6 +401,45 @@ def test_wave_path_with_a_small_memory_budget_runs_more_smaller_waves(phovo, mon
     monkeypatch.delenv("PHOVO_WAVE_BUDGET_MB")
     st, it = odo.BatchAlign(g0, d0, g1)
     assert np.array_equal(it, it_ref) and np.array_equal(st, st_ref)
+    # CTAs per pair: a small wave gives every pair a thread-block cluster (here 8 by default); every size gives the same
+    # iterations and the same states up to the grouping of the partial sums
+    for c in (1, 2, 4, 8):
+        monkeypatch.setenv("PHOVO_WAVE_CLUSTER", str(c))
+        st, it = odo.BatchAlign(g0, d0, g1)
+        assert odo.BatchLastPath() == 3
+        assert np.array_equal(it, it_ref), c
+        assert np.max(np.abs(st - st_ref)) < 1e-11, (c, float(np.max(np.abs(st - st_ref))))
+        if c == 8: assert np.array_equal(st, st_ref)
+    monkeypatch.delenv("PHOVO_WAVE_CLUSTER")
+    odo.close()
+
+
+def test_growing_frame_sizes_keep_the_winner_map_initialised(phovo, oracle):
+    """Regression: after a frame-size change the winner map is reallocated; cudaFree + cudaMalloc can return the SAME address
+    with a larger extent, whose tail holds garbage indices unless the map is refilled (it used to be refilled only when
+    the pointer changed -> sporadic illegal addresses in phase B, found by the randomised sweep on the pool of 8 contexts).
+    Alternating small and large frames through the pool and the per-pair API, checked against the CPU oracle."""
+    rng = np.random.default_rng(5)
+    odo = phovo.CPhotoconsistencyOdometryCuda()
+    odo.BatchSetDebugFlags(4)
+    for rep in range(10):
+        for rows, cols in ((40 + 4 * rep, 56), (128, 64 + 8 * rep)):
+            f = 1.1 * cols
+            K = np.array([[f, 0, (cols - 1) / 2], [0, f, (rows - 1) / 2], [0, 0, 1.]])
+            cfg = phovo.default_config(); cfg.num_levels = 3
+            for l, (it, bl) in enumerate(zip((9, 0, 8), (5, 5, 0))):
+                cfg.max_num_iterations[l] = it; cfg.blur_filter_size[l] = bl
+            P = 12
+            g0, d0, g1, _ = phovo.synth.make_batch(P, rows, cols, K=K, seed0=int(rng.integers(0, 1 << 20)))
+            odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
+            st, it = odo.BatchAlign(g0, d0, g1)
+            assert odo.BatchLastPath() == 2
+            for p in (0, P - 1):
+                o = oracle.Oracle(conv_cfg(oracle, cfg), K)
+                o.set_source(g0[p], d0[p].astype(np.float64)); o.set_target(g1[p]); o.set_initial_state(np.zeros(6)); o.optimize()
+                assert len(o.iter_stats()) == int(it[p].sum())
+                if np.isfinite(o.state()).all():
+                    assert_pose_close(st[p], o.state(), "rep %d %dx%d pair %d" % (rep, rows, cols, p))
     odo.close()
 
 

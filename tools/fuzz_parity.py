@@ -26,6 +26,7 @@ def wave_sweep(args):
         K = np.array([[f, 0, (cols - 1) / 2 + rng.uniform(-3, 3)], [0, f * rng.uniform(0.97, 1.03), (rows - 1) / 2 + rng.uniform(-3, 3)], [0, 0, 1.]])
         levels = int(rng.integers(2, 4))
         solver = str(rng.choice(["blur", "ceres", "bi"]))
+        if args.solver: solver = args.solver
         if solver == "ceres":
             cfg = phovo.configs.to_config("config_5_level_optimization_ceres", phovo.capi)
         else:
@@ -53,11 +54,17 @@ def wave_sweep(args):
         g0, d0, g1 = g0[:P], d0[:P], g1[:P]
         init = np.zeros((P, 6)); init[:, :3] = rng.uniform(-2e-3, 2e-3, (P, 3))
         odo.SetConfig(cfg); odo.SetIntrinsicMatrix(K)
-        odo.BatchSetDebugFlags(8)
-        st, it = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
-        assert odo.BatchLastPath() == 3, odo.BatchLastPath()
-        odo.BatchSetDebugFlags(4)
-        pst, pit = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+        if os.environ.get("PHOVO_FUZZ_EXEC"): odo.SetExecution(int(os.environ["PHOVO_FUZZ_EXEC"]))
+        try:
+            odo.BatchSetDebugFlags(4 if os.environ.get("PHOVO_FUZZ_POOL_ONLY") else 8)
+            st, it = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+            assert odo.BatchLastPath() == (2 if os.environ.get("PHOVO_FUZZ_POOL_ONLY") else 3), odo.BatchLastPath()
+            odo.BatchSetDebugFlags(4)
+            pst, pit = odo.BatchAlign(g0, d0, g1, initial_states=init, **kw)
+        except Exception:
+            print("FAILED in group", gi, solver, rows, cols, levels, [cfg.max_num_iterations[l] for l in range(levels)],
+                  [cfg.blur_filter_size[l] for l in range(levels)], "after", odo.BatchLastPath(), file=sys.stderr)
+            raise
         assert odo.BatchLastPath() == 2
         odo.BatchSetDebugFlags(0)
         stats["groups"] += 1; stats["pairs"] += P; stats["by_solver"][solver] = stats["by_solver"].get(solver, 0) + P
@@ -96,6 +103,7 @@ def main():
     ap.add_argument("--groups", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=24)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--solver", default="", help="--wave: only this kind of group (blur, ceres, bi)")
     ap.add_argument("--wave", action="store_true", help="the wave path of the batch entry (Ceres-mode, photometric + depth solver, blurred "
                     "analytic levels) against the pool of per-pair contexts and, where the oracle has the solver, the CPU oracle")
     args = ap.parse_args()
