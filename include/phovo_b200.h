@@ -259,6 +259,11 @@ int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);
  * thread->pixel bookkeeping even when the CTA width is a multiple of the level width; bit 2 / bit 3 = what the
  * resident kernels do not take goes through the pool of per-pair contexts / the slot waves whatever the batch size */
 int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags);
+/* The batch entries keep what they allocate between calls: the packed level store, the slots' arena (up to half of the
+ * free device memory for frames with large active levels), the pool's contexts, pinned result buffers.  This frees all
+ * of it (blocks until the device is idle); the next batch call allocates again.  Debug flags and the record-stats
+ * switch return to their defaults. */
+int phovo_batch_release_memory(phovo_ctx* ctx);
 /* bytes the last phovo_batch_align call copied host -> device.  Host batches are uploaded without
  * the source rows no active pyramid level reads (the levels are point-decimated from the original
  * image, AN:132), so this can be less than the size of the inputs. */

@@ -101,6 +101,7 @@ SIGNATURES = {
     "phovo_batch_get_iter_stats": (C.c_int, [_vp, C.c_int, C.c_int, _stp]),
     "phovo_batch_num_iter_stats": (C.c_int, [_vp, C.c_int]),
     "phovo_batch_set_debug_flags": (C.c_int, [_vp, C.c_int]),
+    "phovo_batch_release_memory": (C.c_int, [_vp]),
     "phovo_batch_get_last_h2d_bytes": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "phovo_synchronize": (C.c_int, [_vp]),
     "phovo_batch_get_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

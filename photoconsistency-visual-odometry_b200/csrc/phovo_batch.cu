@@ -278,6 +278,14 @@ extern "C" int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable) {
   return PHOVO_OK;
 }
 
+extern "C" int phovo_batch_release_memory(phovo_ctx* ctx) {
+  if (!ctx) return PHOVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  phovo_batch_release(ctx);
+  return PHOVO_OK;
+}
+
 extern "C" int phovo_batch_set_debug_flags(phovo_ctx* ctx, int flags) {
   if (!ctx) return PHOVO_E_INVALID;
   phovo_batch_state* b; int rc = get_state(ctx, &b);

@@ -325,8 +325,13 @@ class CPhotoconsistencyOdometryCuda:
         return int(n.value)
 
     def BatchSetDebugFlags(self, flags):
-        """bit 0: exact warp for every pixel; bit 1: generic pixel bookkeeping (results must not change)."""
+        """bit 0: exact warp for every pixel; bit 1: generic pixel bookkeeping (results must not change); bit 2 / bit 3: what the
+        resident kernels do not take goes through the pool of per-pair contexts / the slot waves whatever the batch size."""
         self._check(self._L.phovo_batch_set_debug_flags(self._h, int(flags)))
+
+    def BatchReleaseMemory(self):
+        """Free what the batch entries keep between calls (level store, slot arena, pool contexts, pinned buffers)."""
+        self._check(self._L.phovo_batch_release_memory(self._h))
 
     def BatchIterationStats(self, pair):
         out = []

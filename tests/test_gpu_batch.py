@@ -411,6 +411,14 @@ def test_wave_path_with_a_small_memory_budget_runs_more_smaller_waves(phovo, mon
         assert np.max(np.abs(st - st_ref)) < 1e-11, (c, float(np.max(np.abs(st - st_ref))))
         if c == 8: assert np.array_equal(st, st_ref)
     monkeypatch.delenv("PHOVO_WAVE_CLUSTER")
+    # the arena, the slots and the pool can be given back; the next call builds them again (flags back to defaults)
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    odo.BatchReleaseMemory()
+    assert torch.cuda.mem_get_info()[0] > free0
+    odo.BatchSetDebugFlags(8)
+    st, it = odo.BatchAlign(g0, d0, g1)
+    assert odo.BatchLastPath() == 3 and np.array_equal(it, it_ref) and np.array_equal(st, st_ref)
     odo.close()
 
 
