@@ -250,7 +250,8 @@ int phovo_batch_align_device(phovo_ctx* ctx, int num_pairs, int rows, int cols,
                              const uint8_t* gray0_dev, const void* depth0_dev, int depth_type,
                              double depth_scale, const uint8_t* gray1_dev,
                              const double* initial_states_dev, double* states_dev, int32_t* iters_dev);
-/* per-pair per-iteration stats of the last batch call (only recorded when enabled: costs HBM) */
+/* per-pair per-iteration stats of the last batch call (only recorded when enabled: costs HBM; what the resident
+ * kernels do not take then goes through the pool of per-pair contexts, whose logs these are) */
 int phovo_batch_set_record_stats(phovo_ctx* ctx, int enable);
 int phovo_batch_get_iter_stats(const phovo_ctx* ctx, int pair, int index, phovo_iter_stats* out);
 int phovo_batch_num_iter_stats(const phovo_ctx* ctx, int pair);

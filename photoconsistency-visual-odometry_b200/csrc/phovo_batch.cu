@@ -352,6 +352,14 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
     initial_states = init_host.data();
   }
   const size_t frame = (size_t)rows * cols, delt = depth_type == PHOVO_DEPTH_F64 ? 8 : depth_type == PHOVO_DEPTH_F32 ? 4 : 2;
+  // per-pair per-iteration stats (phovo_batch_set_record_stats): the children's logs, kept in the host mirrors
+  int log_per_pair = 0;
+  if (b->record_stats) {
+    for (int l = 0; l < ctx->cfg.num_levels; ++l) log_per_pair += ctx->cfg.max_num_iterations[l];
+    log_per_pair += 1;
+    b->h_log.assign((size_t)num_pairs * log_per_pair, phovo_iter_stats{});
+    b->h_log_counts.assign(num_pairs, 0);
+  }
   std::atomic<int> next(0), first_rc(PHOVO_OK);
   std::mutex mu; std::string message;
   auto work = [&](phovo_ctx* c) {
@@ -377,13 +385,17 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
       if (!rc) rc = phovo_optimize(c);
       if (rc && rc != PHOVO_E_NUMERIC) { fail(rc); return; }     // a non-finite state is a result (the reference returns NaN too)
       if (states) phovo_get_state(c, states + (size_t)p * 6);
-      if (iterations) {
-        int32_t* it = iterations + (size_t)p * PHOVO_MAX_LEVELS;
-        for (int l = 0; l < PHOVO_MAX_LEVELS; ++l) it[l] = 0;
+      if (iterations || log_per_pair) {
+        int32_t* it = iterations ? iterations + (size_t)p * PHOVO_MAX_LEVELS : nullptr;
+        for (int l = 0; it && l < PHOVO_MAX_LEVELS; ++l) it[l] = 0;
         phovo_iter_stats e;
         const int n = phovo_num_iter_stats(c);
-        for (int k = 0; k < n; ++k)
-          if (phovo_get_iter_stats(c, k, &e) == PHOVO_OK && e.level >= 0 && e.level < PHOVO_MAX_LEVELS) it[e.level] += 1;
+        for (int k = 0; k < n; ++k) {
+          if (phovo_get_iter_stats(c, k, &e) != PHOVO_OK) continue;
+          if (it && e.level >= 0 && e.level < PHOVO_MAX_LEVELS) it[e.level] += 1;
+          if (k < log_per_pair) b->h_log[(size_t)p * log_per_pair + k] = e;      // (distinct pairs: no two threads share an entry)
+        }
+        if (log_per_pair) b->h_log_counts[p] = std::min(n, log_per_pair);
       }
     }
   };
@@ -392,7 +404,8 @@ static int batch_general(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, in
   work(b->pool[0]);
   for (auto& t : threads) t.join();
   for (int w = 0; w < workers; ++w) ctx->launches += b->pool[w]->launches, b->pool[w]->launches = 0;
-  b->last_pairs = 0; b->log_fetched = false; b->last_h2d_bytes = 0; b->timed = false; b->last_path = 2;
+  b->last_pairs = log_per_pair ? num_pairs : 0; b->log_per_pair = log_per_pair; b->log_fetched = log_per_pair > 0;
+  b->last_h2d_bytes = 0; b->timed = false; b->last_path = 2;
   if (first_rc.load() != PHOVO_OK) return ctx->fail(first_rc.load(), "batch pool: " + message);
   return PHOVO_OK;
 }
@@ -643,7 +656,7 @@ static int batch_waves(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
   if ((rc = harvest(1 - last))) return rc;
   if ((rc = harvest(last))) return rc;
   if (trace) for (int h = 0; h < 2; ++h) { cudaEventDestroy(tr0[h]); cudaEventDestroy(tr1[h]); }
-  b->last_pairs = 0; b->log_fetched = false; b->timed = false; b->last_path = 3;
+  b->last_pairs = 0; b->log_per_pair = 0; b->log_fetched = false; b->timed = false; b->last_path = 3;
   return PHOVO_OK;
 }
 
@@ -657,7 +670,8 @@ static int batch_other(phovo_ctx* ctx, phovo_batch_state* b, int num_pairs, int 
                        const void* depth0, int depth_type, double depth_scale, const uint8_t* gray1, const void* depth1,
                        const double* initial_states, double* states, int32_t* iterations) {
   const int min_pairs = ctx->cfg.mode == PHOVO_MODE_CERES ? 16 : 24;
-  const bool pool = (b->debug_flags & 4) || (!(b->debug_flags & 8) && num_pairs < min_pairs);
+  // (the per-iteration stats are a debugging aid: a batch that records them takes the pool, whose children keep logs)
+  const bool pool = (b->debug_flags & 4) || b->record_stats || (!(b->debug_flags & 8) && num_pairs < min_pairs);
   if (pool) return batch_general(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
   return batch_waves(ctx, b, num_pairs, rows, cols, gray0, depth0, depth_type, depth_scale, gray1, depth1, initial_states, states, iterations);
 }

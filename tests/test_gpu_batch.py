@@ -289,6 +289,18 @@ def test_batch_configurations_beyond_the_resident_kernels_take_the_wave_path(pho
                     else: assert np.max(np.abs(st[p] - ref_states[p])) < 1e-10, (cfg.mode, p, st[p] - ref_states[p])
                     assert int(it[p].sum()) == ref_iters[p] > 0, (cfg.mode, path, p)
         odo.BatchSetDebugFlags(0)
+        # per-pair per-iteration stats: the per-pair API's own log, entry by entry
+        odo.BatchSetRecordStats(True)
+        st, it = odo.BatchAlign(g0, d0, g1, initial_states=init)
+        assert odo.BatchLastPath() == 2
+        single.SetSourceFrame(g0[P - 1], d0[P - 1]); single.SetTargetFrame(g1[P - 1]); single.SetInitialStateVector(init[P - 1])
+        single.Optimize()
+        blog, slog = odo.BatchIterationStats(P - 1), single.IterationStats()
+        assert len(blog) == len(slog) == ref_iters[P - 1]
+        for a, b in zip(blog, slog):
+            assert a["level"] == b["level"] and a["num_valid"] == b["num_valid"] and a["accepted"] == b["accepted"]
+            assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["g"], b["g"]) and np.array_equal(a["state_out"], b["state_out"])
+        odo.BatchSetRecordStats(False)
     # back on the resident kernels
     odo.SetConfig(phovo.configs.to_config("config_4_level_optimization_analytic", phovo.capi))
     odo.BatchAlign(g0, d0, g1)
