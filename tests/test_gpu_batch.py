@@ -476,6 +476,27 @@ def test_randomised_parity_sweep(phovo, oracle):
     st = json.loads(out.stdout.strip().splitlines()[-1])
     assert st["pairs"] >= 100 and st["iter_mismatch"] == 0 and st["pose_over_bar"] == 0 and st["nonfinite"] == 0, st
     assert st["worst_trans"] < 1e-9 and st["worst_rot"] < 1e-9 and st["worst_general_vs_batch"] < 1e-9, st
+    # where the prebuilt oracle/_ref travelled: the bug-compatible groups are also judged by the reference's own header
+    assert st["iter_mismatch_vs_reference"] == 0 and st["pose_over_bar_vs_reference"] == 0 and st["worst_vs_reference"] < 1e-9, st
+
+
+def test_randomised_parity_sweep_of_the_wave_path(phovo, oracle):
+    """The same for what the resident kernels do not take (Ceres-mode, photometric + depth solver, blurred levels): slot
+    waves against the pool of per-pair contexts, the CPU oracle and -- when oracle/_ref is present -- the reference's own
+    three solver headers."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--wave", "--groups", "45", "--pairs", "12", "--seed", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    st = json.loads(out.stdout.strip().splitlines()[-1])
+    assert st["pairs"] >= 500 and len(st["by_solver"]) == 3, st
+    assert st["iter_mismatch_vs_pool"] == 0 and st["worst_vs_pool"] < 1e-10 and st["nonfinite_mismatch"] == 0, st
+    assert st["oracle_checked"] > 50 and st["iter_mismatch_vs_oracle"] == 0 and st["pose_over_bar_vs_oracle"] == 0, st
+    assert st["iter_mismatch_vs_reference"] == 0 and st["pose_over_bar_vs_reference"] == 0 and st["worst_vs_reference"] < 1e-9, st
 
 
 def test_sequence_as_one_batch_matches_the_vo_loop(phovo, oracle):

@@ -16,7 +16,15 @@ def wave_sweep(args):
     import oracle_py
     oracle_py.build()
     rng = np.random.default_rng(args.seed)
-    stats = dict(pairs=0, groups=0, by_solver={}, iter_mismatch_vs_pool=0, worst_vs_pool=0., oracle_checked=0, iter_mismatch_vs_oracle=0,
+    try:
+        import ref_py
+        if not ref_py.available(): ref_py = None
+    except Exception:
+        ref_py = None
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    stats = dict(reference_checked=0, iter_mismatch_vs_reference=0, pose_over_bar_vs_reference=0, worst_vs_reference=0.,
+                 pairs=0, groups=0, by_solver={}, iter_mismatch_vs_pool=0, worst_vs_pool=0., oracle_checked=0, iter_mismatch_vs_oracle=0,
                  pose_over_bar_vs_oracle=0, worst_trans_vs_oracle=0., worst_rot_vs_oracle=0., nonfinite_mismatch=0)
     odo = phovo.CPhotoconsistencyOdometryCuda()
     t0 = time.time()
@@ -44,6 +52,7 @@ def wave_sweep(args):
         if solver == "blur" and not any(cfg.blur_filter_size[l] > 1 and cfg.max_num_iterations[l] > 0 for l in range(levels)):
             l = max(l for l in range(levels) if cfg.max_num_iterations[l] > 0); cfg.blur_filter_size[l] = 3
         cfg.min_depth, cfg.max_depth = float(rng.uniform(0.2, 1.0)), float(rng.uniform(2.1, 6.5))
+        if ref_py is not None: cfg.min_depth, cfg.max_depth = 0.3, 5.0  # the reference classes' own range (checked against them below)
         P = args.pairs
         scale = float(rng.choice([1., 1., 3.]))
         g0 = np.empty((P + 1, rows, cols), np.uint8); g1 = np.empty_like(g0); d0 = np.empty((P + 1, rows, cols))
@@ -77,6 +86,62 @@ def wave_sweep(args):
                 stats["iter_mismatch_vs_pool"] += 1
             elif fin:
                 stats["worst_vs_pool"] = max(stats["worst_vs_pool"], float(np.max(np.abs(st[p] - pst[p]))))
+        if solver == "bi" and ref_py is not None:            # the REFERENCE'S OWN solver (oracle/_ref: its header, compiled unmodified)
+            C = phovo.configs
+            yml = os.path.join(tmp, "fuzz_bi.yml")
+            with open(yml, "w") as f:
+                f.write(C.to_yaml({C.K_LEVELS: levels, C.K_BLUR: [0] * levels, C.K_GRAD: [float(cfg.grad_scale[l]) for l in range(levels)],
+                                   C.K_LAMBDA: [float(cfg.lambda_step[l]) for l in range(levels)],
+                                   C.K_ITERS: [int(cfg.max_num_iterations[l]) for l in range(levels)],
+                                   C.K_MINGRAD: [float(cfg.min_gradient_norm[l]) for l in range(levels)], "visualizeIterations": 0}))
+            ref = ref_py.ReferenceBiObjective(yml, K)
+            for p in range(0, P, 4):
+                rs, riters = ref.align(g0[p], d0[p], g1[p], kw["depth1"][p], state0=init[p])
+                stats["reference_checked"] += 1
+                if not (np.isfinite(rs).all() and np.isfinite(st[p]).all()):
+                    stats["nonfinite_mismatch"] += int(np.isfinite(rs).all() != np.isfinite(st[p]).all())
+                    continue
+                if len(riters) != int(it[p].sum()):
+                    stats["iter_mismatch_vs_reference"] += 1
+                    continue
+                stats["worst_vs_reference"] = max(stats["worst_vs_reference"], float(np.max(np.abs(st[p] - rs))))
+                if np.max(np.abs(st[p, :3] - rs[:3])) >= 1e-4 or np.max(np.abs(st[p, 3:] - rs[3:])) >= 1e-5:
+                    stats["pose_over_bar_vs_reference"] += 1
+        if solver != "bi" and ref_py is not None and (solver == "ceres" or cfg.mode == 0):
+            # analytic (bug-compatible mode = the reference's Jacobian) and Ceres-mode: the reference's own headers again
+            C = phovo.configs
+            vals = {C.K_LEVELS: levels, C.K_BLUR: [int(cfg.blur_filter_size[l]) for l in range(levels)],
+                    C.K_GRAD: [float(cfg.grad_scale[l]) for l in range(levels)],
+                    C.K_ITERS: [int(cfg.max_num_iterations[l]) for l in range(levels)], "visualizeIterations": 0}
+            if solver == "ceres":
+                for key, arr in ((C.K_FTOL, cfg.function_tolerance), (C.K_GTOL, cfg.gradient_tolerance), (C.K_PTOL, cfg.parameter_tolerance),
+                                 (C.K_R0, cfg.initial_trust_region_radius), (C.K_RMAX, cfg.max_trust_region_radius),
+                                 (C.K_RMIN, cfg.min_trust_region_radius), (C.K_ETA, cfg.min_relative_decrease)):
+                    vals[key] = [float(arr[l]) for l in range(levels)]
+                vals.update({"num_threads": 1, "num_linear_solver_threads": 1, "minimizer_progress_to_stdout": 0})
+            else:
+                vals[C.K_LAMBDA] = [float(cfg.lambda_step[l]) for l in range(levels)]
+                vals[C.K_MINGRAD] = [float(cfg.min_gradient_norm[l]) for l in range(levels)]
+            yml = os.path.join(tmp, "fuzz_%s.yml" % solver)
+            with open(yml, "w") as f:
+                f.write(C.to_yaml(vals))
+            ref = ref_py.ReferenceCeres(yml, K) if solver == "ceres" else ref_py.Reference(yml, K)
+            for p in range(1, P, 4):
+                if solver == "ceres":
+                    ref.set_frames(g0[p], d0[p], g1[p])
+                    rs, rlog = ref.optimize(init[p]); rn = len(rlog)
+                else:
+                    rs, _, riters = ref.align(g0[p], d0[p], g1[p], state0=init[p]); rn = len(riters)
+                stats["reference_checked"] += 1
+                if not (np.isfinite(rs).all() and np.isfinite(st[p]).all()):
+                    stats["nonfinite_mismatch"] += int(np.isfinite(rs).all() != np.isfinite(st[p]).all())
+                    continue
+                if rn != int(it[p].sum()):
+                    stats["iter_mismatch_vs_reference"] += 1
+                    continue
+                stats["worst_vs_reference"] = max(stats["worst_vs_reference"], float(np.max(np.abs(st[p] - rs))))
+                if np.max(np.abs(st[p, :3] - rs[:3])) >= 1e-4 or np.max(np.abs(st[p, 3:] - rs[3:])) >= 1e-5:
+                    stats["pose_over_bar_vs_reference"] += 1
         if solver != "bi":                                   # the oracle has the analytic and the Ceres-mode solver
             ocfg = oracle_py.Config.from_buffer_copy(bytes(cfg))
             for p in range(0, P, 3):
@@ -114,8 +179,16 @@ def main():
     import oracle_py
     oracle_py.build()
     rng = np.random.default_rng(args.seed)
+    try:
+        import ref_py
+        if not ref_py.available(): ref_py = None
+    except Exception:
+        ref_py = None
+    import tempfile
+    tmp = tempfile.mkdtemp()
     stats = dict(pairs=0, groups=0, iter_mismatch=0, pose_over_bar=0, worst_trans=0., worst_rot=0., general_checked=0,
-                 worst_general_vs_batch=0., nonfinite=0, sizes=[])
+                 worst_general_vs_batch=0., nonfinite=0, reference_checked=0, iter_mismatch_vs_reference=0, pose_over_bar_vs_reference=0,
+                 worst_vs_reference=0., sizes=[])
     odo = phovo.CPhotoconsistencyOdometryCuda()
     t0 = time.time()
     for gi in range(args.groups):
@@ -133,6 +206,8 @@ def main():
             cfg.max_num_iterations[levels - 1] = 5
         cfg.min_depth, cfg.max_depth = float(rng.uniform(0.2, 1.0)), float(rng.uniform(2.1, 6.5))
         cfg.mode = int(rng.integers(0, 2))
+        check_ref = ref_py is not None and cfg.mode == 0      # mode 0 IS the reference's Jacobian: its own header is the judge
+        if check_ref: cfg.min_depth, cfg.max_depth = 0.3, 5.0 # (the reference class's range)
         P = args.pairs
         scale = float(rng.choice([1., 1., 3.]))            # some groups with large motions
         g0 = np.empty((P, rows, cols), np.uint8); g1 = np.empty_like(g0); d0 = np.empty((P, rows, cols))
@@ -159,6 +234,26 @@ def main():
             stats["worst_trans"] = max(stats["worst_trans"], dt); stats["worst_rot"] = max(stats["worst_rot"], dr)
             if dt >= 1e-4 or dr >= 1e-5:
                 stats["pose_over_bar"] += 1
+        if check_ref:                                        # oracle/_ref: CPhotoconsistencyOdometryAnalytic.h compiled unmodified
+            C = phovo.configs
+            yml = os.path.join(tmp, "fuzz_analytic.yml")
+            with open(yml, "w") as f:
+                f.write(C.to_yaml({C.K_LEVELS: levels, C.K_BLUR: [0] * levels, C.K_GRAD: [float(cfg.grad_scale[l]) for l in range(levels)],
+                                   C.K_LAMBDA: [float(cfg.lambda_step[l]) for l in range(levels)],
+                                   C.K_ITERS: [int(cfg.max_num_iterations[l]) for l in range(levels)],
+                                   C.K_MINGRAD: [float(cfg.min_gradient_norm[l]) for l in range(levels)], "visualizeIterations": 0}))
+            ref = ref_py.Reference(yml, K)
+            for p in range(0, P, 6):
+                rs, _, riters = ref.align(g0[p], d0[p], g1[p])
+                stats["reference_checked"] += 1
+                if not (np.isfinite(rs).all() and np.isfinite(st[p]).all()):
+                    continue
+                if len(riters) != int(it[p].sum()):
+                    stats["iter_mismatch_vs_reference"] += 1
+                    continue
+                stats["worst_vs_reference"] = max(stats["worst_vs_reference"], float(np.max(np.abs(st[p] - rs))))
+                if np.max(np.abs(st[p, :3] - rs[:3])) >= 1e-4 or np.max(np.abs(st[p, 3:] - rs[3:])) >= 1e-5:
+                    stats["pose_over_bar_vs_reference"] += 1
         for path in (2, 1):                                  # the general path on two pairs of the group
             odo.SetExecution(path)
             for p in (0, P - 1):
