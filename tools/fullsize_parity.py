@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=2048)
     ap.add_argument("--config", default="config_4_level_optimization_analytic")
     ap.add_argument("--depth", default="u16", choices=["u16", "f32"])
+    ap.add_argument("--reference-sample", type=int, default=128, help="pairs also run through the reference's own header (oracle/_ref)")
     args = ap.parse_args()
     phovo = importlib.import_module("photoconsistency-visual-odometry_b200")
     phovo.build()
@@ -34,7 +35,23 @@ def main():
     ost, oit, _, _ = oracle_py.align_batch(oracle_py.Config.from_buffer_copy(bytes(cfg)), K, g0.cpu().numpy(), d_host, g1.cpu().numpy(),
                                            num_threads=os.cpu_count(), lean=True)
     dt = np.max(np.abs(st[:, :3] - ost[:, :3]), axis=1); dr = np.max(np.abs(st[:, 3:] - ost[:, 3:]), axis=1)
-    print(json.dumps({"pairs": args.pairs, "config": args.config, "depth": args.depth, "iteration_count_mismatches": int((it != oit).any(axis=1).sum()),
+    # a sample also against the REFERENCE'S OWN header (oracle/_ref, where the prebuilt library travelled)
+    ref_stats = {}
+    try:
+        import ref_py, tempfile
+        if ref_py.available() and cfg.mode == 0:
+            ref = ref_py.Reference(phovo.configs.write_yaml(args.config, tempfile.mkdtemp()), K)
+            gh0, gh1 = g0.cpu().numpy(), g1.cpu().numpy()
+            worst, mism, n = 0., 0, 0
+            for p in range(0, args.pairs, max(1, args.pairs // args.reference_sample)):
+                rs, _, riters = ref.align(gh0[p], d_host[p], gh1[p])
+                n += 1
+                if len(riters) != int(it[p].sum()): mism += 1
+                else: worst = max(worst, float(np.max(np.abs(st[p] - rs))))
+            ref_stats = {"reference_header_pairs": n, "reference_header_iteration_mismatches": mism, "reference_header_worst_state_diff": worst}
+    except Exception as e:  # pragma: no cover
+        ref_stats = {"reference_header_error": repr(e)}
+    print(json.dumps({**ref_stats, "pairs": args.pairs, "config": args.config, "depth": args.depth, "iteration_count_mismatches": int((it != oit).any(axis=1).sum()),
                       "poses_over_bar": int(((dt >= 1e-4) | (dr >= 1e-5)).sum()), "worst_translation_diff": float(dt.max()), "worst_rotation_diff": float(dr.max()),
                       "mean_iterations": {str(l): float(it[:, l].mean()) for l in range(cfg.num_levels) if cfg.max_num_iterations[l] > 0},
                       "pairs_at_iteration_cap": int((it[:, cfg.num_levels - 1] == cfg.max_num_iterations[cfg.num_levels - 1]).sum()),
