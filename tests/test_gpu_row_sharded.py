@@ -77,3 +77,16 @@ def test_full_size_8k_pair_matches_oracle(phovo, oracle):
         assert h_rel_err(a["H"], b["H"]) < 1e-10 and g_rel_err(a["g"], b["g"]) < 1e-9
     assert_pose_close(odo.GetOptimalStateVector(), o.state(), "8K pair")
     assert np.max(np.abs(odo.GetOptimalStateVector() - o.state())) < 1e-10
+    # BASELINE configs[4] at its stated size against the REFERENCE'S OWN header (oracle/_ref, when the prebuilt library
+    # travelled): iteration counts, normal equations of every executed iteration, final state
+    import ref_py
+    if ref_py.available():
+        import tempfile
+        ref = ref_py.Reference(phovo.configs.write_yaml("config_6_level_optimization_analytic", tempfile.mkdtemp()), K)
+        rs, _, riters = ref.align(g0, d0, g1)
+        assert len(riters) == len(log)
+        idx = [(a, b) for a in range(6) for b in range(a, 6)]
+        for e, it in zip(log, riters):
+            Hp = np.array([it["H"][a, b] for a, b in idx])
+            assert h_rel_err(e["H"], Hp) < 1e-10 and g_rel_err(e["g"], it["g"]) < 1e-9
+        assert np.max(np.abs(odo.GetOptimalStateVector() - rs)) < 1e-10
