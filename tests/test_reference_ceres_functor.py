@@ -176,3 +176,16 @@ def test_cuda_ceres_matches_reference_functor_live(phovo, tmp_path):
             assert np.array_equal(np.abs(res) > 1e-9, np.abs(res_ref) > 1e-9)          # same scatter, also at the identity
             assert np.max(np.abs(res - res_ref)) <= 1e-13
             assert np.max(np.abs(jac - jac_ref)) <= 1e-11 * np.max(np.abs(jac_ref))
+    # closed loop at the stated size of BASELINE configs[2]: the CUDA LM (cooperative kernel and a wave of slots) against
+    # "the reference functor under the restated LM" -- every LM decision (accepted / rejected steps) and the final state
+    s_ref, log_ref = ref.optimize()
+    odo.SetInitialStateVector(np.zeros(6))
+    odo.Optimize()
+    log = odo.IterationStats()
+    assert len(log) == len(log_ref) > 0
+    assert [e["accepted"] for e in log] == [e["accepted"] for e in log_ref]
+    assert np.max(np.abs(odo.GetOptimalStateVector() - s_ref)) < 1e-10
+    odo.BatchSetDebugFlags(8)
+    st, it = odo.BatchAlign(g0[None], d0[None], g1[None])
+    assert odo.BatchLastPath() == 3 and int(it.sum()) == len(log_ref)
+    assert np.max(np.abs(st[0] - s_ref)) < 1e-10
