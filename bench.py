@@ -56,8 +56,9 @@ class ClockSampler:
     nvidia-smi -lms as the fallback when pynvml cannot be loaded)."""
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.001):
         self.index, self.samples, self.stop_flag, self.thread, self.nvml, self.err = index, [], False, None, None, None
+        self.period = period      # sleep between samples; NVML queries take driver locks, so host-launch-heavy regions use a longer one
 
     def start(self):
         try:
@@ -90,12 +91,12 @@ class ClockSampler:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
                 reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
                 # power is a slow query: every 8th sample is enough for the maximum
-                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if len(self.samples) % 8 == 7 else 0.0
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if len(self.samples) % 8 == 0 else 0.0
                 self.samples.append((sm, reasons, power))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            time.sleep(0.001)
+            time.sleep(self.period)
 
     def stop(self):
         self.stop_flag = True
@@ -401,7 +402,9 @@ def secondary_block(phovo, torch, dev, local_rank, frames):
         kw = {"depth1": d0[1:P + 1].contiguous()} if mode is not None else {}
         odo.BatchAlign(g0[:P], d0[:P], g1[:P], **kw)        # slots, arena, pinned result buffers
         torch.cuda.synchronize(dev)
-        sampler = ClockSampler(local_rank)
+        # (the wave path launches thousands of small set-up kernels from four host threads: a 2 ms NVML polling loop slows it by
+        # up to 30 % through the driver's locks -- measured 84 ms steady without, 84-116 ms with -- so this block samples at 20 Hz)
+        sampler = ClockSampler(local_rank, period=0.05)
         sampler.start()
         times = []
         for rep in range(3):                                  # median of three calls
