@@ -222,7 +222,7 @@ int phovo_set_build_all_levels(phovo_ctx* ctx, int enable);
 /* ---- batch of independent pairs (extension; BASELINE config "4096 pairs, sharded by pair") ---- */
 /* All pairs share rows/cols/intrinsics/config.  Inputs are strided arrays of `num_pairs` frames:
  * gray0/gray1 u8 [P][rows][cols], depth0 [P][rows][cols] of depth_type.  Pointers may be host
- * (pinned recommended) or device.  Results: states[P][6] doubles, iterations[P][num_levels] int32
+ * (pinned recommended) or device.  Results: states[P][6] doubles, iterations[P][PHOVO_MAX_LEVELS] int32
  * (executed GN iterations per level), both host pointers (may be NULL). */
 int phovo_batch_align(phovo_ctx* ctx, int num_pairs, int rows, int cols,
                       const uint8_t* gray0, const void* depth0, int depth_type, double depth_scale,
