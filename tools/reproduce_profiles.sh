@@ -52,3 +52,10 @@ ncu --set full --clock-control none --import-source on -k regex:k_align_slots --
 
 # 7. where the clocks of k_batch_level go (a variant library with clock64() around the sections of an iteration)
 bash tools/build_variant.sh secclk -- -DPHOVO_SECTION_CLOCKS && python tools/section_clocks.py build/variants/secclk.so 4096 > "$OUT/${TAG}_section_clocks.json"
+
+# 8. pool vs slot waves vs clusters by batch size; randomised sweeps judged by the CPU oracle AND the reference's own headers (oracle/_ref)
+python tools/wave_cluster_sweep.py 4 8 12 16 24 32 48 64 96 128 148 200 296 400 592 1184 > "$OUT/${TAG}_wave_cluster_sweep.jsonl"
+python tools/fuzz_parity.py --groups 1466 --pairs 24 --seed 1 > "$OUT/${TAG}_fuzz_parity_35k_pairs.json"
+python tools/fuzz_parity.py --groups 500 --pairs 24 --seed 5 > "$OUT/${TAG}_fuzz_parity_12k_pairs.json"
+for pp in "40 80" "100 40" "310 12"; do set -- $pp; python tools/fuzz_parity.py --wave --groups $2 --pairs $1 --seed 31 | tail -1; done > "$OUT/${TAG}_fuzz_parity_wave_path_cluster_sizes.jsonl"
+bash tools/build_variant.sh cminb2 -- -DPHOVO_CERES_COOP_MINB=2 && bash tools/ceres_variants.sh     # k_level_coop_ceres at 2 vs 1 CTAs per SM
